@@ -1,0 +1,36 @@
+"""b4d — B200-native BM4D denoise path for ExaSPIM uint16 volumes.
+
+Drop-in for the one call the reference makes into the closed ``bm4d`` wheel
+(data_handling.py:332, :926; evaluate.py:202) plus the offset / quantize /
+statistics steps around it.  See DESIGN.md and INTEGRATION.md at the repo root.
+"""
+from .api import (  # noqa: F401
+    BM4DProfile,
+    BM4DStages,
+    Denoiser,
+    bm4d,
+    bm4d_batch,
+    get_denoiser,
+    noise_scaled_step,
+    precompute_targets,
+    quantize,
+    tile_stats,
+)
+from .sharding import denoise_volume_sharded, merge_histograms, slab_plan, stats_from_hist  # noqa: F401
+
+__all__ = [
+    "BM4DProfile",
+    "BM4DStages",
+    "Denoiser",
+    "bm4d",
+    "bm4d_batch",
+    "get_denoiser",
+    "noise_scaled_step",
+    "precompute_targets",
+    "quantize",
+    "tile_stats",
+    "slab_plan",
+    "denoise_volume_sharded",
+    "merge_histograms",
+    "stats_from_hist",
+]

@@ -1,0 +1,452 @@
+"""Host-side mirror of the reference's BM4D call surface, over libb4d.so.
+
+What it replaces (paths under /root/reference/src/aind_exaspim_image_compression):
+
+* ``bm4d(z, sigma_psd)``                     machine_learning/data_handling.py:332, :926;
+                                             evaluate.py:202 (uint16, non-contiguous view)
+* ``read_counts`` + ``bm4d`` + ``np.clip``   machine_learning/data_handling.py:315-354
+                                             -> :func:`precompute_targets` (batched)
+* clip + rint + uint16                       machine_learning/transforms.py:150-152, :403-411
+                                             -> :func:`quantize`
+* ``estimate_offset`` / median-MAD sigma     machine_learning/transforms.py:414-438,
+                                             machine_learning/metrics.py:54-58 -> :func:`tile_stats`
+
+Same names, argument meaning and error behaviour as the ``bm4d`` package's entry
+point (``ValueError`` for shape/dtype, ``RuntimeError`` for CUDA,
+``NotImplementedError`` for a coloured PSD).  NumPy in -> NumPy out; torch in ->
+torch out on the same device.  Everything computes on the GPU through the C ABI;
+there is no CPU fallback.
+"""
+import ctypes
+import enum
+import os
+
+import numpy as np
+
+from . import _lib
+
+
+class BM4DStages(enum.Enum):
+    """Same members as ``bm4d.BM4DStages``."""
+
+    HARD_THRESHOLDING = 1
+    WIENER_FILTERING = 2
+    ALL_STAGES = 3
+
+
+class BM4DProfile:
+    """Algorithm constants.  Field names follow the
+    ``bm4d`` package's profile where one exists; each maps onto ``b4d_profile``."""
+
+    def __init__(self, **kw):
+        self.bs_ht = (4, 4, 4)
+        self.step_ht = (3, 3, 3)
+        self.max_stack_size_ht = 16
+        self.search_window_ht = (5, 5, 5)  # half-width per axis: window side 11
+        self.tau_match_ht = 2.9527
+        self.lambda_thr = 2.7
+        self.bs_wiener = (4, 4, 4)
+        self.step_wiener = (3, 3, 3)
+        self.max_stack_size_wiener = 32
+        self.search_window_wiener = (5, 5, 5)
+        self.tau_match_wiener = 0.7693
+        self.beta = 2.0  # Kaiser window parameter of the aggregation window
+        self.deterministic = False  # fixed-point, order-independent aggregation
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError("unknown profile field %r" % k)
+            setattr(self, k, v)
+
+    def key(self):
+        return tuple(sorted((k, tuple(v) if np.ndim(v) else v) for k, v in vars(self).items()))
+
+    def to_c(self, stages=2):
+        def cube(v, name):
+            v = tuple(int(x) for x in (v if np.ndim(v) else (v, v, v)))
+            if len(set(v)) != 1:
+                raise NotImplementedError("%s must be isotropic, got %r" % (name, v))
+            return v[0]
+
+        if cube(self.bs_ht, "bs_ht") != 4 or cube(self.bs_wiener, "bs_wiener") != 4:
+            raise NotImplementedError("only 4x4x4 blocks are implemented")
+        if cube(self.step_ht, "step_ht") != 3 or cube(self.step_wiener, "step_wiener") != 3:
+            raise NotImplementedError("only step 3 is implemented")
+        return _lib.default_profile(
+            search_ht=2 * cube(self.search_window_ht, "search_window_ht") + 1,
+            search_wie=2 * cube(self.search_window_wiener, "search_window_wiener") + 1,
+            k_ht=int(self.max_stack_size_ht),
+            k_wie=int(self.max_stack_size_wiener),
+            tau_ht=float(self.tau_match_ht),
+            tau_wie=float(self.tau_match_wiener),
+            lambda_ht=float(self.lambda_thr),
+            kaiser_beta=float(self.beta),
+            deterministic=1 if self.deterministic else 0,
+            stages=int(stages),
+        )
+
+
+def _profile_from_arg(profile):
+    if isinstance(profile, BM4DProfile):
+        return profile
+    if profile is None or profile == "np":
+        return BM4DProfile()
+    raise ValueError("profile must be 'np' or a BM4DProfile, got %r" % (profile,))
+
+
+def _is_torch(x):
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+class Denoiser:
+    """One ``b4d_handle``: scratch buffers + a stream on one CUDA device.
+    Not thread-safe; one per (process, device)."""
+
+    def __init__(self, device=0, profile=None, stages=2):
+        self.lib = _lib.load()
+        self.device = int(device)
+        self.profile = _profile_from_arg(profile)
+        self._stages = stages
+        self._h = ctypes.c_void_p()
+        cprof = self.profile.to_c(stages)
+        _lib.check(self.lib.b4d_create(self.device, ctypes.byref(cprof), ctypes.byref(self._h)))
+        self._pid = os.getpid()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h and self._pid == os.getpid():
+            self.lib.b4d_destroy(self._h)
+        self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_profile(self, profile=None, stages=2):
+        """Switch algorithm constants (no-op when nothing changes)."""
+        prof = _profile_from_arg(profile)
+        if prof.key() == self.profile.key() and stages == self._stages:
+            return
+        cprof = prof.to_c(stages)
+        _lib.check(self.lib.b4d_set_profile(self._h, ctypes.byref(cprof)))
+        self.profile = prof
+        self._stages = stages
+
+    # ---- raw pointer level -------------------------------------------------
+    def denoise_ptr(self, in_ptr, dtype, n, shape, sigma, out_ptr, in_dev, out_dev):
+        fn = self.lib.b4d_denoise_u16 if dtype == np.uint16 else self.lib.b4d_denoise_f32
+        _lib.check(
+            fn(
+                self._h,
+                ctypes.c_void_p(in_ptr),
+                ctypes.c_int64(n),
+                _lib.shape3(shape),
+                ctypes.c_float(sigma),
+                ctypes.c_void_p(out_ptr),
+                int(in_dev),
+                int(out_dev),
+            )
+        )
+
+    # ---- array level ---------------------------------------------------------
+    def denoise(self, z, sigma):
+        """(D,H,W) or (N,D,H,W); uint16 or float32; NumPy or torch -> float32."""
+        if _is_torch(z):
+            import torch
+
+            if z.dtype not in (torch.uint16, torch.float32):
+                raise ValueError("torch input must be uint16 or float32, got %s" % z.dtype)
+            zc = z.contiguous()
+            if zc.ndim not in (3, 4):
+                raise ValueError("expected a 3-D volume or a 4-D batch, got %d-D" % zc.ndim)
+            n = zc.shape[0] if zc.ndim == 4 else 1
+            on_dev = zc.is_cuda
+            if on_dev and zc.device.index != self.device:
+                raise ValueError("tensor lives on cuda:%s, handle on cuda:%d" % (zc.device.index, self.device))
+            out = torch.empty(zc.shape, dtype=torch.float32, device=zc.device)
+            if on_dev:
+                torch.cuda.current_stream(zc.device).synchronize()
+            self.denoise_ptr(
+                zc.data_ptr(),
+                np.uint16 if zc.dtype == torch.uint16 else np.float32,
+                n,
+                tuple(zc.shape[-3:]),
+                sigma,
+                out.data_ptr(),
+                on_dev,
+                on_dev,
+            )
+            return out
+        z = np.asarray(z)
+        if z.ndim not in (3, 4):
+            raise ValueError("expected a 3-D volume or a 4-D batch, got %d-D" % z.ndim)
+        zc = np.ascontiguousarray(z)
+        n = zc.shape[0] if zc.ndim == 4 else 1
+        out = np.empty(zc.shape, dtype=np.float32)
+        self.denoise_ptr(zc.ctypes.data, zc.dtype.type, n, zc.shape[-3:], sigma, out.ctypes.data, 0, 0)
+        return out
+
+    def denoise_slab(self, slab, z_begin, z_total, own_begin, own_end, sigma):
+        """One z-slab (uint16, with halos) of a larger volume -> float32 owned planes."""
+        if _is_torch(slab):
+            import torch
+
+            sc = slab.contiguous()
+            if sc.dtype != torch.uint16 or sc.ndim != 3:
+                raise ValueError("slab must be a 3-D uint16 tensor")
+            out = torch.empty((own_end - own_begin,) + tuple(sc.shape[1:]), dtype=torch.float32, device=sc.device)
+            on_dev = sc.is_cuda
+            if on_dev:
+                torch.cuda.current_stream(sc.device).synchronize()
+            in_ptr, out_ptr, shape = sc.data_ptr(), out.data_ptr(), tuple(sc.shape)
+        else:
+            sc = np.ascontiguousarray(slab)
+            if sc.dtype != np.uint16 or sc.ndim != 3:
+                raise ValueError("slab must be a 3-D uint16 array")
+            out = np.empty((own_end - own_begin,) + sc.shape[1:], dtype=np.float32)
+            on_dev = False
+            in_ptr, out_ptr, shape = sc.ctypes.data, out.ctypes.data, sc.shape
+        _lib.check(
+            self.lib.b4d_denoise_slab_u16(
+                self._h,
+                ctypes.c_void_p(in_ptr),
+                _lib.shape3(shape),
+                ctypes.c_int64(z_begin),
+                ctypes.c_int64(z_total),
+                ctypes.c_int64(own_begin),
+                ctypes.c_int64(own_end),
+                ctypes.c_float(sigma),
+                ctypes.c_void_p(out_ptr),
+                int(on_dev),
+                int(on_dev),
+            )
+        )
+        return out
+
+    def match_stage1(self, vol, sigma):
+        """Instrumented stage-1 matcher: (idx[R,K] int32, ssd[R,K] uint64, count[R] int32)."""
+        vol = np.ascontiguousarray(vol)
+        if vol.dtype != np.uint16 or vol.ndim != 3:
+            raise ValueError("match_stage1 expects a 3-D uint16 array")
+        shape = _lib.shape3(vol.shape)
+        R = self.lib.b4d_num_refs(shape)
+        K = int(self.profile.max_stack_size_ht)
+        idx = np.empty((R, K), dtype=np.int32)
+        ssd = np.empty((R, K), dtype=np.uint64)
+        cnt = np.empty((R,), dtype=np.int32)
+        _lib.check(
+            self.lib.b4d_match_stage1(
+                self._h,
+                ctypes.c_void_p(vol.ctypes.data),
+                shape,
+                ctypes.c_float(sigma),
+                ctypes.c_void_p(idx.ctypes.data),
+                ctypes.c_void_p(ssd.ctypes.data),
+                ctypes.c_void_p(cnt.ctypes.data),
+            )
+        )
+        return idx, ssd, cnt
+
+    def quantize(self, x, offset_sub=0.0, offset_add=0.0, step=1.0):
+        """K7: rint(clip((x - offset_sub + offset_add)/step, 0, 65535/step)) -> uint16."""
+        if _is_torch(x):
+            import torch
+
+            xc = x.contiguous()
+            if xc.dtype != torch.float32:
+                raise ValueError("quantize expects float32")
+            out = torch.empty(xc.shape, dtype=torch.uint16, device=xc.device)
+            on_dev = xc.is_cuda
+            if on_dev:
+                torch.cuda.current_stream(xc.device).synchronize()
+            in_ptr, out_ptr, n = xc.data_ptr(), out.data_ptr(), xc.numel()
+        else:
+            xc = np.ascontiguousarray(x, dtype=np.float32)
+            out = np.empty(xc.shape, dtype=np.uint16)
+            on_dev = False
+            in_ptr, out_ptr, n = xc.ctypes.data, out.ctypes.data, xc.size
+        _lib.check(
+            self.lib.b4d_quantize_u16(
+                self._h,
+                ctypes.c_void_p(in_ptr),
+                ctypes.c_int64(n),
+                ctypes.c_float(offset_sub),
+                ctypes.c_float(offset_add),
+                ctypes.c_float(step),
+                ctypes.c_void_p(out_ptr),
+                int(on_dev),
+                int(on_dev),
+            )
+        )
+        return out
+
+    def tile_stats(self, x, percentile=1.0, return_hist=False):
+        """K8: offset percentile over non-zero voxels + median / MAD sigma of a uint16 tile."""
+        if _is_torch(x):
+            import torch
+
+            xc = x.contiguous()
+            if xc.dtype != torch.uint16:
+                raise ValueError("tile_stats expects uint16")
+            on_dev = xc.is_cuda
+            if on_dev:
+                torch.cuda.current_stream(xc.device).synchronize()
+            in_ptr, n = xc.data_ptr(), xc.numel()
+        else:
+            xc = np.ascontiguousarray(x)
+            if xc.dtype != np.uint16:
+                raise ValueError("tile_stats expects uint16")
+            on_dev = False
+            in_ptr, n = xc.ctypes.data, xc.size
+        st = _lib.Stats()
+        hist = np.empty(65536, dtype=np.int64) if return_hist else None
+        _lib.check(
+            self.lib.b4d_tile_stats(
+                self._h,
+                ctypes.c_void_p(in_ptr),
+                ctypes.c_int64(n),
+                ctypes.c_double(percentile),
+                ctypes.byref(st),
+                ctypes.c_void_p(hist.ctypes.data) if return_hist else None,
+                int(on_dev),
+            )
+        )
+        d = {k: getattr(st, k) for k, _ in _lib.Stats._fields_}
+        return (d, hist) if return_hist else d
+
+    def last_timings(self):
+        ms = (ctypes.c_float * _lib.T_COUNT)()
+        nl = (ctypes.c_int64 * _lib.T_COUNT)()
+        _lib.check(self.lib.b4d_last_timings(self._h, ms, nl))
+        return {name: (float(ms[i]), int(nl[i])) for i, name in enumerate(_lib.T_NAMES)}
+
+    def last_match_stats(self):
+        out = (ctypes.c_uint64 * 4)()
+        _lib.check(self.lib.b4d_last_match_stats(self._h, out))
+        return {"fallback_refs": int(out[0]), "wide_tiles": int(out[1])}
+
+    def measure_pipe_peaks(self):
+        out = (ctypes.c_double * 4)()
+        _lib.check(self.lib.b4d_measure_pipe_peaks(self._h, out))
+        return {"imad": out[0], "iadd3": out[1], "sub_mad": out[2], "ffma": out[3]}
+
+
+# --------------------------------------------------------------------------
+# module-level call surface (lazy per-process handles: the reference calls
+# bm4d() from forked ProcessPool workers, scripts/precompute.py:215-222)
+# --------------------------------------------------------------------------
+_handles = {}
+
+
+def get_denoiser(device=None):
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if "B4D_DEVICE" not in os.environ else int(
+            os.environ["B4D_DEVICE"]
+        )
+    key = (os.getpid(), int(device))
+    h = _handles.get(key)
+    if h is None:
+        h = Denoiser(device)
+        _handles[key] = h
+    return h
+
+
+def _sigma_scalar(sigma_psd):
+    s = np.asarray(sigma_psd, dtype=np.float64)
+    if s.ndim == 0 or s.size == 1:
+        return float(s.reshape(-1)[0])
+    if np.all(s == s.reshape(-1)[0]):
+        # a constant PSD of an N-voxel transform equals sigma^2 * N (white noise)
+        return float(np.sqrt(s.reshape(-1)[0] / s.size))
+    raise NotImplementedError("coloured-noise PSD input is not implemented; pass a scalar sigma")
+
+
+def _prepare(z):
+    """dtype contract of the drop-in: returns (array for the C ABI, output cast)."""
+    if _is_torch(z):
+        return z, None
+    z = np.asarray(z)
+    if z.dtype == np.uint16 or z.dtype == np.float32:
+        return z, None
+    if z.dtype.kind in "iu" or z.dtype == np.bool_:
+        if z.size and (z.min() < 0 or z.max() > 65535):
+            return z.astype(np.float32), None
+        return z.astype(np.uint16), None
+    if z.dtype.kind == "f":
+        return z.astype(np.float32), z.dtype
+    raise ValueError("unsupported dtype %s" % z.dtype)
+
+
+def bm4d(z, sigma_psd, profile="np", stage_arg=BM4DStages.ALL_STAGES, blockmatches=(False, False), device=None):
+    """Drop-in for ``bm4d.bm4d``: denoise one 3-D volume.
+
+    z          NumPy or torch, 3-D, uint16 or float32 (other real dtypes are
+               converted), any strides.
+    sigma_psd  noise standard deviation in the units of ``z`` (scalar).
+    Returns a new array of the same shape: float32 (input dtype for float64).
+    Unclipped — callers clip (data_handling.py:333, evaluate.py:202).
+    """
+    if blockmatches not in ((False, False), [False, False], None):
+        raise NotImplementedError("returning / reusing block matches is not implemented")
+    if isinstance(stage_arg, BM4DStages):
+        if stage_arg == BM4DStages.WIENER_FILTERING:
+            raise ValueError("WIENER_FILTERING alone needs a basic estimate; pass ALL_STAGES")
+        stages = 1 if stage_arg == BM4DStages.HARD_THRESHOLDING else 2
+    else:
+        raise NotImplementedError("passing a basic estimate as stage_arg is not implemented")
+    if np.ndim(z) != 3 if not _is_torch(z) else z.ndim != 3:
+        raise ValueError("bm4d expects a 3-D array, got %d-D" % (z.ndim if _is_torch(z) else np.ndim(z)))
+    sigma = _sigma_scalar(sigma_psd)
+    h = get_denoiser(device)
+    h.set_profile(profile, stages)
+    zz, cast = _prepare(z)
+    out = h.denoise(zz, sigma)
+    return out.astype(cast) if cast is not None else out
+
+
+def bm4d_batch(patches, sigma, profile="np", device=None):
+    """N independent equal-shape patches in one call: (N,D,H,W) -> float32."""
+    h = get_denoiser(device)
+    h.set_profile(profile, 2)
+    zz, _ = _prepare(patches)
+    if zz.ndim != 4:
+        raise ValueError("bm4d_batch expects (N, D, H, W)")
+    return h.denoise(zz, _sigma_scalar(sigma))
+
+
+def precompute_targets(raw_u16, offsets, sigma, max_count=65535.0, device=None):
+    """Batched ``_sample_counts`` core (data_handling.py:315-354):
+    raw = uint16 -> float32 - offset; teacher = clip(bm4d(raw, sigma), 0, max_count).
+
+    raw_u16  (N,D,H,W) uint16;  offsets scalar or (N,) per-patch scalars.
+    Returns (raw float32, teacher float32) as the cache stores them
+    (scripts/precompute.py:204-228).
+    """
+    raw_u16 = np.asarray(raw_u16)
+    if raw_u16.ndim != 4 or raw_u16.dtype != np.uint16:
+        raise ValueError("raw_u16 must be (N, D, H, W) uint16")
+    off = np.broadcast_to(np.asarray(offsets, dtype=np.float32), (raw_u16.shape[0],))
+    raw = raw_u16.astype(np.float32) - off[:, None, None, None]
+    h = get_denoiser(device)
+    groups = {}
+    for i, o in enumerate(off.tolist()):
+        groups.setdefault(o, []).append(i)
+    teacher = np.empty(raw.shape, dtype=np.float32)
+    for _o, idxs in groups.items():  # one launch per distinct offset: the matching map is per call
+        sel = np.asarray(idxs)
+        teacher[sel] = bm4d_batch(raw[sel], sigma, device=h.device)
+    np.clip(teacher, 0, max_count, out=teacher)
+    return raw, teacher
+
+
+def quantize(x, offset_sub=0.0, offset_add=0.0, step=1.0, device=None):
+    return get_denoiser(device).quantize(x, offset_sub, offset_add, step)
+
+
+def noise_scaled_step(sigma_tile, kappa):
+    """step = max(1, kappa * sigma_tile) (SURVEY §8a, K7 definition)."""
+    return float(max(1.0, float(kappa) * float(sigma_tile)))
+
+
+def tile_stats(x, percentile=1.0, device=None, return_hist=False):
+    return get_denoiser(device).tile_stats(x, percentile, return_hist)

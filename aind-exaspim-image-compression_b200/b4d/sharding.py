@@ -1,0 +1,126 @@
+"""z-slab sharding of one large volume across the GPUs of one box.
+
+One process per GPU.  Every rank denoises its slab plus halos; reference blocks
+sit on the GLOBAL grid, so the union of the owned planes equals the
+whole-volume result and no volume data crosses GPUs.  The only exchange is the
+all-gather of per-slab uint16 histograms (256 KiB per rank) from which every
+rank derives the same global offset percentile / median / MAD sigma — a
+percentile is not decomposable from per-rank percentiles, a histogram is
+(transforms.py:433-438, metrics.py:54-58).
+"""
+import numpy as np
+
+L = 4
+
+
+def halo_planes(search_ht=11, search_wie=11, stages=2):
+    """Planes needed beyond the owned range on each interior face for exact
+    slab == whole equality: (Ns - 1 + L - 1) per stage."""
+    h = search_ht - 1 + L - 1
+    if stages == 2:
+        h += search_wie - 1 + L - 1
+    return h
+
+
+def slab_plan(z_total, world, rank, halo):
+    """Owned planes [own_begin, own_end) and slab planes [z_begin, z_end) of `rank`."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, rem = divmod(int(z_total), int(world))
+    own_begin = rank * base + min(rank, rem)
+    own_end = own_begin + base + (1 if rank < rem else 0)
+    if own_end <= own_begin:
+        raise ValueError("more ranks than planes")
+    z_begin = max(0, own_begin - halo)
+    z_end = min(z_total, own_end + halo)
+    if z_end - z_begin < L:
+        raise ValueError("slab thinner than one block")
+    return own_begin, own_end, z_begin, z_end
+
+
+def denoise_volume_sharded(get_slab, z_total, sigma, denoiser, world=1, rank=0):
+    """Denoise this rank's share of a (z_total, H, W) uint16 volume.
+
+    get_slab(z_begin, z_end) -> uint16 array/tensor of those planes (host or
+    device).  Returns (own_begin, own_end, float32 planes).
+    """
+    p = denoiser.profile
+    halo = halo_planes(2 * int(np.ravel(p.search_window_ht)[0]) + 1, 2 * int(np.ravel(p.search_window_wiener)[0]) + 1,
+                       denoiser._stages)
+    own_begin, own_end, z_begin, z_end = slab_plan(z_total, world, rank, halo)
+    slab = get_slab(z_begin, z_end)
+    out = denoiser.denoise_slab(slab, z_begin, z_total, own_begin, own_end, sigma)
+    return own_begin, own_end, out
+
+
+def merge_histograms(hist, group=None):
+    """All-gather + sum of per-rank 65536-bin histograms (the path's only
+    collective).  `hist` is an int64 torch tensor on the rank's device (NCCL) or
+    on the CPU (gloo).  Without an initialised process group it is returned as is."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return hist
+    world = dist.get_world_size(group)
+    gathered = [torch.empty_like(hist) for _ in range(world)]
+    dist.all_gather(gathered, hist, group=group)
+    return torch.stack(gathered, 0).sum(0)
+
+
+def stats_from_hist(hist, percentile=1.0):
+    """Offset percentile over non-zero voxels, median, MAD, sigma from an exact
+    uint16 histogram, with NumPy-2 float32 semantics (float32 virtual index and
+    interpolation) — the same arithmetic libb4d's b4d_tile_stats performs."""
+    f32 = np.float32
+    h = np.asarray(hist, dtype=np.int64)
+    n = int(h.sum())
+    if n == 0:
+        raise ValueError("empty histogram")
+
+    def order_stat(hh, k):
+        return int(np.searchsorted(np.cumsum(hh), k, side="right"))
+
+    def pct(hh, first, cnt, p):
+        q = f32(p) / f32(100)
+        vi = f32(cnt - 1) * q
+        prev = np.floor(vi)
+        if vi >= f32(cnt - 1):
+            pi = ni = cnt - 1
+        elif vi < 0:
+            pi = ni = 0
+        else:
+            pi = int(prev)
+            ni = pi + 1
+        g = f32(vi - prev)
+        sub = hh.copy()
+        sub[:first] = 0
+        a, b = f32(order_stat(sub, pi)), f32(order_stat(sub, ni))
+        d = f32(b - a)
+        r = f32(a + f32(d * g))
+        if g >= f32(0.5):
+            r = f32(b - f32(d * f32(f32(1) - g)))
+        return float(r)
+
+    nnz = n - int(h[0])
+    offset = pct(h, 1, nnz, percentile) if nnz > 0 else pct(h, 0, n, percentile)
+    m_lo, m_hi = order_stat(h, (n - 1) // 2), order_stat(h, n // 2)
+    med = f32((f32(m_lo) + f32(m_hi)) * f32(0.5))
+    m2 = m_lo + m_hi
+    t = np.abs(2 * np.arange(65536, dtype=np.int64) - m2)
+    h2 = np.bincount(t, weights=None, minlength=131072) * 0
+    np.add.at(h2, t, h)
+    a_lo, a_hi = order_stat(h2, (n - 1) // 2), order_stat(h2, n // 2)
+    mad = f32(f32((f32(a_lo) * f32(0.5) + f32(a_hi) * f32(0.5)) * f32(0.5)) + f32(1e-6))
+    sigma = f32(f32(1.4826) * mad)
+    nz = np.nonzero(h)[0]
+    return {
+        "n": n,
+        "n_nonzero": nnz,
+        "offset": offset,
+        "median": float(med),
+        "mad": float(mad),
+        "sigma": float(sigma),
+        "vmin": float(nz[0]),
+        "vmax": float(nz[-1]),
+    }

@@ -1,0 +1,841 @@
+// b4d_api.cu — the C ABI of include/b4d.h over the sm_100a kernels: handle,
+// scratch buffers, the two-stage pipeline, slab geometry, statistics.
+//
+// There is NO CPU fallback here: every entry point that computes needs a CUDA
+// device and fails with B4D_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b4d_common.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU_TRY(call)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(e_ == cudaErrorMemoryAllocation ? B4D_ERR_NOMEM : B4D_ERR_CUDA,               \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+    } while (0)
+#define B4D_TRY(call)        \
+    do {                     \
+        int rc_ = (call);    \
+        if (rc_) return rc_; \
+    } while (0)
+
+constexpr int L = 4;
+constexpr long long CHUNK_VOXELS = 1342177280ll;  // 1.25 Gi voxels of scratch per pass
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B4D_ERR_NOMEM, "cudaMalloc(" + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
+        }
+        cap = bytes;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+}  // namespace
+
+struct b4d_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    b4d_profile prof;
+    DevBuf in, u16, zf, acc, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats;
+    cudaEvent_t ev[B4D_T_COUNT + 1];
+    float t_ms[B4D_T_COUNT];
+    int64_t launches[B4D_T_COUNT];
+    unsigned long long match_stats[4];
+};
+
+namespace {
+
+void default_profile(b4d_profile *p) {
+    std::memset(p, 0, sizeof(*p));
+    p->abi = B4D_ABI_VERSION;
+    p->block = 4;
+    p->step = 3;
+    p->search_ht = 11;
+    p->search_wie = 11;
+    p->k_ht = 16;
+    p->k_wie = 32;
+    p->stages = 2;
+    p->deterministic = 0;
+    p->tau_ht = 2.9527f;
+    p->tau_wie = 0.7693f;
+    p->lambda_ht = 2.7f;
+    p->kaiser_beta = 2.0f;
+}
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+int check_profile(const b4d_profile &p) {
+    if (p.abi != B4D_ABI_VERSION) return fail(B4D_ERR_INVALID, "profile.abi mismatch");
+    if (p.block != 4 || p.step != 3) return fail(B4D_ERR_UNSUPPORTED, "only block = 4, step = 3 are implemented");
+    for (int ns : {p.search_ht, p.search_wie})
+        if (ns < 3 || ns > 15 || (ns & 1) == 0)
+            return fail(B4D_ERR_INVALID, "search window side must be odd in [3, 15]");
+    for (int k : {p.k_ht, p.k_wie})
+        if (!is_pow2(k) || k > 32) return fail(B4D_ERR_INVALID, "group size must be a power of two <= 32");
+    if (p.stages != 1 && p.stages != 2) return fail(B4D_ERR_INVALID, "stages must be 1 or 2");
+    if (!(p.tau_ht > 0) || !(p.tau_wie > 0) || !(p.lambda_ht >= 0))
+        return fail(B4D_ERR_INVALID, "tau / lambda must be positive");
+    return 0;
+}
+int check_shape(const int64_t shape[3]) {
+    for (int i = 0; i < 3; ++i)
+        if (shape[i] < L || shape[i] > 65535) return fail(B4D_ERR_INVALID, "every dimension must be in [4, 65535]");
+    return 0;
+}
+
+// Reference-block origins along one axis: 0, 3, 6, ... plus N-4.
+std::vector<int> ref_origins(int64_t n) {
+    std::vector<int> o;
+    for (int64_t v = 0; v + L <= n; v += 3) o.push_back((int)v);
+    if ((n - L) % 3 != 0) o.push_back((int)(n - L));
+    return o;
+}
+std::vector<int> slab_origins(int64_t z_total, int64_t z_begin, int64_t depth, int r) {
+    std::vector<int> o;
+    for (int gz : ref_origins(z_total)) {
+        const int64_t lo = std::max<int64_t>(0, gz - r);
+        const int64_t hi = std::min<int64_t>(z_total - L, gz + r) + (L - 1);
+        if (lo >= z_begin && hi < z_begin + depth) o.push_back((int)(gz - z_begin));
+    }
+    return o;
+}
+
+double bessel_i0(double x) {
+    double s = 1.0, t = 1.0;
+    for (int k = 1; k < 64; ++k) {
+        t *= (x / (2.0 * k)) * (x / (2.0 * k));
+        s += t;
+        if (t < 1e-18 * s) break;
+    }
+    return s;
+}
+B4dTables make_tables(const b4d_profile &p, float sigma) {
+    B4dTables t;
+    std::memset(&t, 0, sizeof(t));
+    float kf[4];
+    for (int n = 0; n < 4; ++n) {
+        double w = 1.0;
+        if (p.kaiser_beta > 0) {
+            const double a = 2.0 * n / 3.0 - 1.0;
+            w = bessel_i0((double)p.kaiser_beta * std::sqrt(std::max(0.0, 1.0 - a * a))) /
+                bessel_i0((double)p.kaiser_beta);
+        }
+        kf[n] = (float)w;
+    }
+    for (int z = 0; z < 4; ++z)
+        for (int y = 0; y < 4; ++y)
+            for (int x = 0; x < 4; ++x) {
+                volatile float zy = kf[z] * kf[y];  // two separately rounded float32 products
+                volatile float zyx = zy * kf[x];
+                t.win[(z * 4 + y) * 4 + x] = zyx;
+            }
+    for (int m = 0; m < 16; ++m) {
+        const double s = std::ldexp(1.0, m / 2) * ((m & 1) ? M_SQRT2 : 1.0);
+        t.tht[m] = (float)((double)p.lambda_ht * (double)sigma * s);
+    }
+    for (int l = 0; l < 8; ++l) t.gs[l] = (float)(std::ldexp(1.0, -(l / 2)) * ((l & 1) ? M_SQRT1_2 : 1.0));
+    t.c1 = (float)(std::cos(M_PI / 8.0) * M_SQRT1_2);
+    t.c3 = (float)(std::cos(3.0 * M_PI / 8.0) * M_SQRT1_2);
+    volatile float s2 = sigma * sigma;
+    t.sigma2 = s2;
+    return t;
+}
+
+struct MatchMap {
+    float shift = 0.0f, scale = 1.0f;
+    int integral = 1;
+};
+
+int tau_for(float tau, float sigma, float scale, int Ns, uint32_t *out) {
+    const double s = (double)sigma * (double)scale;
+    const double v = std::floor((double)tau * s * s * 64.0);
+    const int kb = (Ns * Ns * Ns <= 2048) ? 11 : 12;
+    const double lim = std::ldexp(1.0, 32 - kb) - 2.0;
+    if (!(v <= lim))
+        return fail(B4D_ERR_UNSUPPORTED,
+                    "tau*sigma^2*64 = " + std::to_string(v) + " exceeds the 32-bit match key (" +
+                        std::to_string(lim) + "); lower sigma or tau");
+    *out = (uint32_t)v;
+    return 0;
+}
+
+struct Plan {
+    int D, H, W, nvol;
+    std::vector<int> rz1, rz2, ry, rx;
+};
+
+void fill_geom(const Plan &pl, const std::vector<int> &rz, const int *d_refs, B4dGeom *g) {
+    g->D = pl.D;
+    g->H = pl.H;
+    g->W = pl.W;
+    g->nvol = pl.nvol;
+    g->nrz = (int)rz.size();
+    g->nry = (int)pl.ry.size();
+    g->nrx = (int)pl.rx.size();
+    g->tz = (g->nrz + 3) / 4;
+    g->ty = (g->nry + 3) / 4;
+    g->tx = (g->nrx + 3) / 4;
+    g->refz = d_refs;
+    g->refy = d_refs + rz.size();
+    g->refx = d_refs + rz.size() + pl.ry.size();
+    g->vol_stride = (long long)pl.D * pl.H * pl.W;
+    g->refs_per_vol = (long long)g->nrz * g->nry * g->nrx;
+}
+
+// One stage boundary timing: we record an event after each kernel family and
+// resolve all of them after the final synchronise.
+struct StageClock {
+    b4d_handle *h;
+    std::vector<cudaEvent_t> evs;
+    std::vector<std::pair<int, int>> tags;  // (slot, launches) for interval i -> i+1
+    explicit StageClock(b4d_handle *hh) : h(hh) {}
+    void mark(int slot, int launches) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, h->stream);
+        evs.push_back(e);
+        tags.push_back({slot, launches});
+    }
+    void resolve() {
+        for (size_t i = 1; i < evs.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, evs[i - 1], evs[i]);
+            const int slot = tags[i].first;
+            if (slot >= 0 && slot < B4D_T_COUNT) {
+                h->t_ms[slot] += ms;
+                h->launches[slot] += tags[i].second;
+            }
+        }
+        for (auto e : evs) cudaEventDestroy(e);
+        evs.clear();
+        tags.clear();
+    }
+};
+
+// The two-stage pipeline on device-resident inputs.
+//   d_zf   float32 noisy volumes            [nvol*V]
+//   d_u    uint16 matching image (stage 1)  [nvol*V]   (overwritten by stage 2)
+//   d_out  float32 result                   [nvol*V]
+int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u, const MatchMap &mm, float sigma,
+                 float *d_out, StageClock &clk) {
+    const b4d_profile &p = h->prof;
+    const long long V = (long long)pl.D * pl.H * pl.W, TV = V * pl.nvol;
+    cudaStream_t s = h->stream;
+
+    uint32_t tau1 = 0, tau2 = 0;
+    B4D_TRY(tau_for(p.tau_ht, sigma, mm.scale, p.search_ht, &tau1));
+    if (p.stages == 2) B4D_TRY(tau_for(p.tau_wie, sigma, mm.scale, p.search_wie, &tau2));
+
+    // reference-origin lists: [rz1 | ry | rx | rz2 | ry | rx]
+    std::vector<int> refs;
+    refs.insert(refs.end(), pl.rz1.begin(), pl.rz1.end());
+    refs.insert(refs.end(), pl.ry.begin(), pl.ry.end());
+    refs.insert(refs.end(), pl.rx.begin(), pl.rx.end());
+    const size_t off2 = refs.size();
+    refs.insert(refs.end(), pl.rz2.begin(), pl.rz2.end());
+    refs.insert(refs.end(), pl.ry.begin(), pl.ry.end());
+    refs.insert(refs.end(), pl.rx.begin(), pl.rx.end());
+    B4D_TRY(h->refs.ensure(refs.size() * sizeof(int)));
+    CU_TRY(cudaMemcpyAsync(h->refs.p, refs.data(), refs.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));  // `refs` is a stack vector
+
+    B4dGeom g1, g2;
+    fill_geom(pl, pl.rz1, h->refs.as<int>(), &g1);
+    fill_geom(pl, pl.rz2, h->refs.as<int>() + off2, &g2);
+    const long long R1 = g1.refs_per_vol * pl.nvol, R2 = g2.refs_per_vol * pl.nvol;
+    if ((long long)pl.nvol * g1.tz * g1.ty * g1.tx > 2147483647ll || (R1 + 3) / 4 > 2147483647ll ||
+        (R2 + 3) / 4 > 2147483647ll)
+        return fail(B4D_ERR_TOO_LARGE, "too many reference blocks for one launch");
+    const int Kmax = std::max(p.k_ht, p.k_wie);
+    B4D_TRY(h->widx.ensure((size_t)std::max(R1, R2) * Kmax * sizeof(uint16_t)));
+    B4D_TRY(h->cnt.ensure((size_t)std::max(R1, R2)));
+    B4D_TRY(h->basic.ensure((size_t)TV * sizeof(float)));
+    B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
+    const bool det = p.deterministic != 0;
+    if (det) {
+        B4D_TRY(h->numq.ensure((size_t)TV * sizeof(long long)));
+        B4D_TRY(h->denq.ensure((size_t)TV * sizeof(long long)));
+    } else {
+        B4D_TRY(h->acc.ensure((size_t)TV * sizeof(float2)));
+    }
+    const B4dTables tab = make_tables(p, sigma);
+    b4d_upload_tables(tab, s);
+    CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
+
+    auto zero_acc = [&]() -> int {
+        if (det) {
+            CU_TRY(cudaMemsetAsync(h->numq.p, 0, (size_t)TV * sizeof(long long), s));
+            CU_TRY(cudaMemsetAsync(h->denq.p, 0, (size_t)TV * sizeof(long long), s));
+        } else {
+            CU_TRY(cudaMemsetAsync(h->acc.p, 0, (size_t)TV * sizeof(float2), s));
+        }
+        return 0;
+    };
+    auto normalise = [&](const float *fb, float *dst) {
+        if (det) b4d_launch_normalise_det(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, TV, s);
+        else b4d_launch_normalise(h->acc.as<float2>(), fb, dst, TV, s);
+    };
+
+    float *d_basic = (p.stages == 1) ? d_out : h->basic.as<float>();
+
+    // ---- stage 1: hard thresholding
+    B4D_TRY(zero_acc());
+    clk.mark(B4D_T_PREP, 1);
+    MatchParams mp;
+    mp.g = g1;
+    mp.u = d_u;
+    mp.tau = tau1;
+    mp.K = p.k_ht;
+    mp.widx = h->widx.as<uint16_t>();
+    mp.cnt = h->cnt.as<uint8_t>();
+    mp.ssd_out = nullptr;
+    mp.stats = h->stats.as<unsigned long long>();
+    if (R1 > 0) b4d_launch_match(mp, p.search_ht, s);
+    clk.mark(B4D_T_MATCH1, 1);
+    FilterParams fp;
+    fp.g = g1;
+    fp.zf = d_zf;
+    fp.basic = nullptr;
+    fp.widx = mp.widx;
+    fp.cnt = mp.cnt;
+    fp.K = p.k_ht;
+    fp.Ns = p.search_ht;
+    fp.acc = h->acc.as<float2>();
+    fp.numq = h->numq.as<long long>();
+    fp.denq = h->denq.as<long long>();
+    if (R1 > 0) b4d_launch_filter(fp, false, det, s);
+    clk.mark(B4D_T_FILTER1, 1);
+    normalise(d_zf, d_basic);
+    clk.mark(B4D_T_NORM1, 1);
+    CU_TRY(cudaGetLastError());
+    if (p.stages == 1) return 0;
+
+    // ---- stage 2: Wiener, matching on the basic estimate
+    b4d_launch_to_match(d_basic, d_u, TV, mm.shift, mm.scale, s);
+    B4D_TRY(zero_acc());
+    clk.mark(B4D_T_PREP, 2);
+    mp.g = g2;
+    mp.tau = tau2;
+    mp.K = p.k_wie;
+    if (R2 > 0) b4d_launch_match(mp, p.search_wie, s);
+    clk.mark(B4D_T_MATCH2, 1);
+    fp.g = g2;
+    fp.basic = d_basic;
+    fp.K = p.k_wie;
+    fp.Ns = p.search_wie;
+    if (R2 > 0) b4d_launch_filter(fp, true, det, s);
+    clk.mark(B4D_T_FILTER2, 1);
+    normalise(d_basic, d_out);
+    clk.mark(B4D_T_NORM2, 1);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// float32 input -> matching map (shift, scale); mirrors oracle derive_match_map.
+int derive_match_map(b4d_handle *h, const float *d_in, long long n, float sigma, MatchMap *mm) {
+    cudaStream_t s = h->stream;
+    float z0 = 0.f;
+    CU_TRY(cudaMemcpyAsync(&z0, d_in, sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    const double c = std::rint((double)z0) - (double)z0;
+    const int nb = b4d_analyze_blocks();
+    B4D_TRY(h->partial.ensure((size_t)nb * 6 * sizeof(double)));
+    b4d_launch_analyze(d_in, n, c, h->partial.as<double>(), s);
+    std::vector<double> part((size_t)nb * 6);
+    CU_TRY(cudaMemcpyAsync(part.data(), h->partial.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    double dev = 0, lo = 1e300, hi = -1e300, zlo = 1e300, zhi = -1e300;
+    for (int b = 0; b < nb; ++b) {
+        dev = std::max(dev, part[b * 6 + 0]);
+        lo = std::min(lo, part[b * 6 + 1]);
+        hi = std::max(hi, part[b * 6 + 2]);
+        zlo = std::min(zlo, part[b * 6 + 3]);
+        zhi = std::max(zhi, part[b * 6 + 4]);
+    }
+    if (!(std::isfinite(zlo) && std::isfinite(zhi))) return fail(B4D_ERR_INVALID, "input contains non-finite values");
+    if (dev <= 1.0 / 64.0 && hi - lo <= 65535.0) {
+        mm->integral = 1;
+        mm->scale = 1.0f;
+        mm->shift = (float)(c - lo + std::floor((65535.0 - (hi - lo)) * 0.5));  // centred: no clamping
+        return 0;
+    }
+    const double range = std::max(zhi - zlo, 1e-30);
+    const int e_range = (int)std::floor(std::log2(65535.0 / range));
+    const int e_sigma = (int)std::floor(std::log2(64.0 / (double)sigma));
+    mm->integral = 0;
+    mm->scale = (float)std::ldexp(1.0, std::min(e_range, e_sigma));
+    mm->shift = (float)(-zlo + std::floor((65535.0 - range * (double)mm->scale) * 0.5) / (double)mm->scale);
+    return 0;
+}
+
+int common_checks(b4d_handle *h, const void *in, const void *out, const int64_t shape[3], float sigma) {
+    if (!h || !in || !out || !shape) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!(sigma > 0) || !std::isfinite(sigma)) return fail(B4D_ERR_INVALID, "sigma must be positive and finite");
+    B4D_TRY(check_shape(shape));
+    CU_TRY(cudaSetDevice(h->device));
+    return 0;
+}
+
+void reset_timings(b4d_handle *h) {
+    for (int i = 0; i < B4D_T_COUNT; ++i) {
+        h->t_ms[i] = 0.f;
+        h->launches[i] = 0;
+    }
+}
+
+// Batched denoise, chunked so scratch stays bounded.
+template <class T>
+int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3], float sigma, float *out,
+                  int in_dev, int out_dev) {
+    B4D_TRY(common_checks(h, in, out, shape, sigma));
+    if (n < 1) return fail(B4D_ERR_INVALID, "n must be >= 1");
+    reset_timings(h);
+    const long long V = shape[0] * shape[1] * shape[2];
+    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, CHUNK_VOXELS / V));
+    cudaStream_t s = h->stream;
+    Plan pl;
+    pl.D = (int)shape[0];
+    pl.H = (int)shape[1];
+    pl.W = (int)shape[2];
+    pl.rz1 = pl.rz2 = ref_origins(shape[0]);
+    pl.ry = ref_origins(shape[1]);
+    pl.rx = ref_origins(shape[2]);
+    StageClock clk(h);
+    for (int64_t i0 = 0; i0 < n; i0 += per) {
+        const int64_t nb = std::min<int64_t>(per, n - i0);
+        const long long TV = V * nb;
+        pl.nvol = (int)nb;
+        // input -> device (always into an aligned scratch copy)
+        B4D_TRY(h->in.ensure((size_t)TV * sizeof(T)));
+        CU_TRY(cudaMemcpyAsync(h->in.p, in + i0 * V, (size_t)TV * sizeof(T),
+                               in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        B4D_TRY(h->u16.ensure((size_t)TV * sizeof(uint16_t) + 16));
+        float *d_out = nullptr;
+        if (out_dev && (reinterpret_cast<uintptr_t>(out + i0 * V) & 15) == 0) {
+            d_out = out + i0 * V;
+        } else {
+            B4D_TRY(h->out.ensure((size_t)TV * sizeof(float)));
+            d_out = h->out.as<float>();
+        }
+        MatchMap mm;
+        const float *d_zf = nullptr;
+        uint16_t *d_u = h->u16.as<uint16_t>();
+        clk.mark(-1, 0);
+        if (sizeof(T) == 2) {
+            B4D_TRY(h->zf.ensure((size_t)TV * sizeof(float)));
+            b4d_launch_u16_to_f32(h->in.as<uint16_t>(), h->zf.as<float>(), TV, s);
+            d_zf = h->zf.as<float>();
+            d_u = h->in.as<uint16_t>();  // the staged copy doubles as the matching image
+        } else {
+            B4D_TRY(derive_match_map(h, h->in.as<float>(), TV, sigma, &mm));
+            b4d_launch_to_match(h->in.as<float>(), h->u16.as<uint16_t>(), TV, mm.shift, mm.scale, s);
+            d_zf = h->in.as<float>();
+        }
+        clk.mark(B4D_T_PREP, 2);
+        B4D_TRY(run_pipeline(h, pl, d_zf, d_u, mm, sigma, d_out, clk));
+        if (d_out != out + i0 * V)
+            CU_TRY(cudaMemcpyAsync(out + i0 * V, d_out, (size_t)TV * sizeof(float),
+                                   out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        clk.resolve();
+    }
+    CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================ C ABI =====
+extern "C" {
+
+int b4d_version(void) { return B4D_ABI_VERSION; }
+const char *b4d_last_error(void) { return g_err.c_str(); }
+void b4d_default_profile(b4d_profile *p) {
+    if (p) default_profile(p);
+}
+
+int b4d_create(int device, const b4d_profile *profile, b4d_handle **out) {
+    if (!out) return fail(B4D_ERR_INVALID, "out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B4D_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                      " (libb4d has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(B4D_ERR_INVALID, "device index out of range");
+    b4d_profile prof;
+    default_profile(&prof);
+    if (profile) {
+        prof = *profile;
+        B4D_TRY(check_profile(prof));
+    }
+    CU_TRY(cudaSetDevice(device));
+    b4d_handle *h = new b4d_handle();
+    h->device = device;
+    h->prof = prof;
+    cudaError_t es = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (es != cudaSuccess) {
+        delete h;
+        return fail(B4D_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(es));
+    }
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    reset_timings(h);
+    std::memset(h->match_stats, 0, sizeof(h->match_stats));
+    *out = h;
+    return 0;
+}
+
+void b4d_destroy(b4d_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->acc, &h->numq, &h->denq, &h->basic, &h->out, &h->widx, &h->cnt,
+                      &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats})
+        b->release();
+    for (auto &ev : h->ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int b4d_set_profile(b4d_handle *h, const b4d_profile *profile) {
+    if (!h || !profile) return fail(B4D_ERR_INVALID, "NULL argument");
+    B4D_TRY(check_profile(*profile));
+    h->prof = *profile;
+    return 0;
+}
+
+int64_t b4d_num_refs(const int64_t shape[3]) {
+    if (!shape || check_shape(shape)) return -1;
+    return (int64_t)ref_origins(shape[0]).size() * (int64_t)ref_origins(shape[1]).size() *
+           (int64_t)ref_origins(shape[2]).size();
+}
+
+int b4d_denoise_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t shape[3], float sigma, float *out,
+                    int in_on_device, int out_on_device) {
+    return denoise_batch<uint16_t>(h, in, n, shape, sigma, out, in_on_device, out_on_device);
+}
+int b4d_denoise_f32(b4d_handle *h, const float *in, int64_t n, const int64_t shape[3], float sigma, float *out,
+                    int in_on_device, int out_on_device) {
+    return denoise_batch<float>(h, in, n, shape, sigma, out, in_on_device, out_on_device);
+}
+
+int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
+                         int64_t z_total, int64_t own_begin, int64_t own_end, float sigma, float *out,
+                         int in_on_device, int out_on_device) {
+    B4D_TRY(common_checks(h, in, out, shape, sigma));
+    if (z_begin < 0 || z_begin + shape[0] > z_total || own_begin < z_begin || own_end > z_begin + shape[0] ||
+        own_begin >= own_end)
+        return fail(B4D_ERR_INVALID, "slab / owned range inconsistent");
+    reset_timings(h);
+    cudaStream_t s = h->stream;
+    const long long V = shape[0] * shape[1] * shape[2], P = shape[1] * shape[2];
+    Plan pl;
+    pl.D = (int)shape[0];
+    pl.H = (int)shape[1];
+    pl.W = (int)shape[2];
+    pl.nvol = 1;
+    pl.rz1 = slab_origins(z_total, z_begin, shape[0], h->prof.search_ht / 2);
+    pl.rz2 = slab_origins(z_total, z_begin, shape[0], h->prof.search_wie / 2);
+    pl.ry = ref_origins(shape[1]);
+    pl.rx = ref_origins(shape[2]);
+    B4D_TRY(h->in.ensure((size_t)V * sizeof(uint16_t)));
+    B4D_TRY(h->u16.ensure((size_t)V * sizeof(uint16_t) + 16));
+    B4D_TRY(h->zf.ensure((size_t)V * sizeof(float)));
+    B4D_TRY(h->out.ensure((size_t)V * sizeof(float)));
+    StageClock clk(h);
+    CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)V * sizeof(uint16_t),
+                           in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    clk.mark(-1, 0);
+    b4d_launch_u16_to_f32(h->in.as<uint16_t>(), h->zf.as<float>(), V, s);
+    clk.mark(B4D_T_PREP, 1);
+    MatchMap mm;
+    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk));
+    CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - z_begin) * P,
+                           (size_t)(own_end - own_begin) * P * sizeof(float),
+                           out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    clk.resolve();
+    CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], float sigma, int32_t *idx,
+                     uint64_t *ssd, int32_t *count) {
+    if (!idx || !ssd || !count) return fail(B4D_ERR_INVALID, "NULL argument");
+    B4D_TRY(common_checks(h, in, idx, shape, sigma));
+    const int64_t Dc = shape[0] - L + 1, Hc = shape[1] - L + 1, Wc = shape[2] - L + 1;
+    if (Dc * Hc * Wc > INT32_MAX) return fail(B4D_ERR_TOO_LARGE, "candidate index space exceeds int32");
+    const b4d_profile &p = h->prof;
+    cudaStream_t s = h->stream;
+    reset_timings(h);
+    Plan pl;
+    pl.D = (int)shape[0];
+    pl.H = (int)shape[1];
+    pl.W = (int)shape[2];
+    pl.nvol = 1;
+    pl.rz1 = pl.rz2 = ref_origins(shape[0]);
+    pl.ry = ref_origins(shape[1]);
+    pl.rx = ref_origins(shape[2]);
+    std::vector<int> refs;
+    refs.insert(refs.end(), pl.rz1.begin(), pl.rz1.end());
+    refs.insert(refs.end(), pl.ry.begin(), pl.ry.end());
+    refs.insert(refs.end(), pl.rx.begin(), pl.rx.end());
+    const long long V = shape[0] * shape[1] * shape[2];
+    B4D_TRY(h->refs.ensure(refs.size() * sizeof(int)));
+    B4D_TRY(h->u16.ensure((size_t)V * sizeof(uint16_t) + 16));
+    CU_TRY(cudaMemcpyAsync(h->refs.p, refs.data(), refs.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(h->u16.p, in, (size_t)V * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    B4dGeom g;
+    fill_geom(pl, pl.rz1, h->refs.as<int>(), &g);
+    const long long R = g.refs_per_vol;
+    const int K = p.k_ht, Ns = p.search_ht, r = Ns / 2;
+    B4D_TRY(h->widx.ensure((size_t)R * std::max(p.k_ht, p.k_wie) * sizeof(uint16_t)));
+    B4D_TRY(h->cnt.ensure((size_t)R));
+    B4D_TRY(h->ssd.ensure((size_t)R * K * sizeof(uint32_t)));
+    B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
+    CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
+    MatchParams mp;
+    mp.g = g;
+    mp.u = h->u16.as<uint16_t>();
+    B4D_TRY(tau_for(p.tau_ht, sigma, 1.0f, Ns, &mp.tau));
+    mp.K = K;
+    mp.widx = h->widx.as<uint16_t>();
+    mp.cnt = h->cnt.as<uint8_t>();
+    mp.ssd_out = h->ssd.as<uint32_t>();
+    mp.stats = h->stats.as<unsigned long long>();
+    StageClock clk(h);
+    clk.mark(-1, 0);
+    b4d_launch_match(mp, Ns, s);
+    clk.mark(B4D_T_MATCH1, 1);
+    CU_TRY(cudaGetLastError());
+    std::vector<uint16_t> hw((size_t)R * K);
+    std::vector<uint32_t> hs((size_t)R * K);
+    std::vector<uint8_t> hc((size_t)R);
+    CU_TRY(cudaMemcpyAsync(hw.data(), mp.widx, hw.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(hs.data(), mp.ssd_out, hs.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(hc.data(), mp.cnt, hc.size(), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    clk.resolve();
+    const int nry = g.nry, nrx = g.nrx;
+    for (long long ri = 0; ri < R; ++ri) {
+        const int oz = pl.rz1[ri / ((long long)nry * nrx)], oy = pl.ry[(ri / nrx) % nry], ox = pl.rx[ri % nrx];
+        count[ri] = hc[ri];
+        for (int k = 0; k < K; ++k) {
+            if (k < hc[ri]) {
+                const int wi = hw[ri * K + k];
+                const int cz = oz - r + wi / (Ns * Ns), cy = oy - r + (wi / Ns) % Ns, cx = ox - r + wi % Ns;
+                idx[ri * K + k] = (int32_t)(((int64_t)cz * Hc + cy) * Wc + cx);
+                ssd[ri * K + k] = hs[ri * K + k];
+            } else {
+                idx[ri * K + k] = -1;
+                ssd[ri * K + k] = UINT64_MAX;
+            }
+        }
+    }
+    return 0;
+}
+
+int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub, float offset_add, float step,
+                     uint16_t *out, int in_on_device, int out_on_device) {
+    if (!h || !in || !out || n < 0) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!(step >= 1.0f)) return fail(B4D_ERR_INVALID, "step must be >= 1");
+    CU_TRY(cudaSetDevice(h->device));
+    if (n == 0) return 0;
+    cudaStream_t s = h->stream;
+    const float *d_in = in;
+    uint16_t *d_out = out;
+    if (!in_on_device || (reinterpret_cast<uintptr_t>(in) & 15)) {
+        B4D_TRY(h->in.ensure((size_t)n * sizeof(float)));
+        CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)n * sizeof(float),
+                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        d_in = h->in.as<float>();
+    }
+    if (!out_on_device || (reinterpret_cast<uintptr_t>(out) & 15)) {
+        B4D_TRY(h->u16.ensure((size_t)n * sizeof(uint16_t) + 16));
+        d_out = h->u16.as<uint16_t>();
+    }
+    b4d_launch_quantize(d_in, d_out, n, offset_sub, offset_add, step, s);
+    CU_TRY(cudaGetLastError());
+    if (d_out != out)
+        CU_TRY(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(uint16_t),
+                               out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Exact NumPy-2 semantics on float32 data (float32 virtual index, float32 lerp):
+//   q = float32(pct) / float32(100); vi = float32(n - 1) * q;  lerp in float32.
+static float percentile_f32(const std::vector<unsigned long long> &hist, int first_bin, long long n, double pct) {
+    auto order_stat = [&](long long k) -> float {  // k-th smallest (0-based) among bins >= first_bin
+        long long c = 0;
+        for (int v = first_bin; v < 65536; ++v) {
+            c += (long long)hist[v];
+            if (k < c) return (float)v;
+        }
+        return 65535.0f;
+    };
+    volatile float q = (float)pct / 100.0f;
+    volatile float vi = (float)(n - 1) * q;
+    long long pi, ni;
+    const float prev = std::floor(vi);
+    if (vi >= (float)(n - 1)) {
+        pi = ni = n - 1;
+    } else if (vi < 0) {
+        pi = ni = 0;
+    } else {
+        pi = (long long)prev;
+        ni = pi + 1;
+    }
+    volatile float g = vi - prev;
+    const float a = order_stat(pi), b = order_stat(ni);
+    volatile float d = b - a;
+    volatile float dg = d * g;
+    volatile float r = a + dg;
+    if (g >= 0.5f) {
+        volatile float omg = 1.0f - g;
+        volatile float t = d * omg;
+        r = b - t;
+    }
+    return r;
+}
+
+int b4d_tile_stats(b4d_handle *h, const uint16_t *in, int64_t n, double pct, b4d_stats *out, int64_t *hist_out,
+                   int in_on_device) {
+    if (!h || !in || !out || n < 1) return fail(B4D_ERR_INVALID, "NULL argument or empty tile");
+    if (!(pct >= 0.0 && pct <= 100.0)) return fail(B4D_ERR_INVALID, "percentile must be in [0, 100]");
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const uint16_t *d_in = in;
+    if (!in_on_device || (reinterpret_cast<uintptr_t>(in) & 15)) {
+        B4D_TRY(h->in.ensure((size_t)n * sizeof(uint16_t)));
+        CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)n * sizeof(uint16_t),
+                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        d_in = h->in.as<uint16_t>();
+    }
+    B4D_TRY(h->hist.ensure(65536 * sizeof(unsigned long long)));
+    CU_TRY(cudaMemsetAsync(h->hist.p, 0, 65536 * sizeof(unsigned long long), s));
+    b4d_launch_hist(d_in, n, h->hist.as<unsigned long long>(), s);
+    CU_TRY(cudaGetLastError());
+    std::vector<unsigned long long> hist(65536);
+    CU_TRY(cudaMemcpyAsync(hist.data(), h->hist.p, 65536 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (hist_out)
+        for (int v = 0; v < 65536; ++v) hist_out[v] = (int64_t)hist[v];
+
+    std::memset(out, 0, sizeof(*out));
+    out->n = n;
+    out->n_nonzero = n - (int64_t)hist[0];
+    int vmin = 65535, vmax = 0;
+    for (int v = 0; v < 65536; ++v)
+        if (hist[v]) {
+            vmin = std::min(vmin, v);
+            vmax = std::max(vmax, v);
+        }
+    out->vmin = vmin;
+    out->vmax = vmax;
+    // transforms.py:433-438: zeros are ignored unless every voxel is zero
+    if (out->n_nonzero > 0) out->offset = (double)percentile_f32(hist, 1, out->n_nonzero, pct);
+    else out->offset = (double)percentile_f32(hist, 0, n, pct);
+    // metrics.py:55-57 in float32
+    auto kth = [&](const std::vector<unsigned long long> &hh, long long k) -> long long {
+        long long c = 0;
+        for (size_t v = 0; v < hh.size(); ++v) {
+            c += (long long)hh[v];
+            if (k < c) return (long long)v;
+        }
+        return (long long)hh.size() - 1;
+    };
+    // median: mean of the two middle order statistics (equal when n is odd)
+    const long long m_lo = kth(hist, (n - 1) / 2), m_hi = kth(hist, n / 2);
+    const float med = ((float)m_lo + (float)m_hi) * 0.5f;  // exact: integers < 2^17
+    // |x - med| in half-counts: t = |2x - (m_lo + m_hi)|
+    const long long m2 = m_lo + m_hi;
+    std::vector<unsigned long long> h2(131072, 0ull);
+    for (int v = 0; v < 65536; ++v)
+        if (hist[v]) h2[(size_t)std::llabs(2ll * v - m2)] += hist[v];
+    const long long a_lo = kth(h2, (n - 1) / 2), a_hi = kth(h2, n / 2);
+    const float mad_med = ((float)a_lo * 0.5f + (float)a_hi * 0.5f) * 0.5f;  // exact (quarter counts)
+    volatile float mad = mad_med + 1e-6f;
+    volatile float sig = 1.4826f * mad;
+    out->median = med;
+    out->mad = mad;
+    out->sigma = sig;
+    return 0;
+}
+
+int b4d_last_timings(b4d_handle *h, float ms[B4D_T_COUNT], int64_t launches[B4D_T_COUNT]) {
+    if (!h || !ms) return fail(B4D_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < B4D_T_COUNT; ++i) {
+        ms[i] = h->t_ms[i];
+        if (launches) launches[i] = h->launches[i];
+    }
+    return 0;
+}
+
+// oracle-free diagnostics: [0] survivor-list fallbacks, [1] wide (uint64) tiles
+int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]) {
+    if (!h || !out) return fail(B4D_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < 4; ++i) out[i] = h->match_stats[i];
+    return 0;
+}
+
+int b4d_measure_pipe_peaks(b4d_handle *h, double out[4]) {
+    if (!h || !out) return fail(B4D_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(h->device));
+    B4D_TRY(h->sink.ensure(64));
+    cudaStream_t s = h->stream;
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreate(&a));
+    CU_TRY(cudaEventCreate(&b));
+    for (int which = 0; which < 4; ++which) {
+        double best = 0.0;
+        for (int rep = 0; rep < 4; ++rep) {
+            const int iters = rep == 0 ? 64 : 2048;
+            cudaEventRecord(a, s);
+            const double ops = b4d_launch_pipe_bench(which, iters, h->sink.as<unsigned>(), s);
+            cudaEventRecord(b, s);
+            CU_TRY(cudaEventSynchronize(b));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, a, b);
+            if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3));
+        }
+        out[which] = best;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

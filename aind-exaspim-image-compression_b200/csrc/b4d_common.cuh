@@ -1,0 +1,75 @@
+// b4d_common.cuh — shared definitions for the sm_100a BM4D kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b4d.h"
+
+#define B4D_L 4
+#define B4D_LV 64
+#define B4D_INVALID_KEY 0xFFFFFFFFu
+#define B4D_FULL 0xFFFFFFFFu
+
+// Geometry of one launch: `nvol` equal-shape volumes, reference-block origin
+// lists per axis (device pointers).  All volumes share the lists.
+struct B4dGeom {
+    int D, H, W;
+    int nvol;
+    int nrz, nry, nrx;       // reference blocks per axis
+    int tz, ty, tx;          // 4x4x4-reference tiles per axis
+    const int *refz, *refy, *refx;
+    long long vol_stride;    // voxels per volume
+    long long refs_per_vol;
+};
+
+// Tables shared by the filter kernels; built on the host in float64 and rounded
+// once, exactly as oracle/b4d_oracle.cpp make_tables() does.
+struct B4dTables {
+    float win[B4D_LV];   // (w[z]*w[y])*w[x], float32 products
+    float tht[16];       // lambda*sigma*2^(m/2)
+    float gs[8];         // 2^(-l/2)
+    float c1, c3;        // DCT-II-4
+    float sigma2;
+};
+
+struct MatchParams {
+    B4dGeom g;
+    const uint16_t *u;   // matching image [nvol][D][H][W]
+    uint32_t tau;        // acceptance threshold (SSD <= tau)
+    int K;               // max group size
+    uint16_t *widx;      // [R][K] window index of each match
+    uint8_t *cnt;        // [R] group size (power of two)
+    uint32_t *ssd_out;   // optional [R][K] exact SSDs (instrumented matcher)
+    unsigned long long *stats;  // optional: [0] fallback refs, [1] wide tiles
+};
+
+struct FilterParams {
+    B4dGeom g;
+    const float *zf;     // noisy volume (float32)
+    const float *basic;  // basic estimate (Wiener stage only)
+    const uint16_t *widx;
+    const uint8_t *cnt;
+    int K;
+    int Ns;
+    float2 *acc;                 // fast mode: (num, den) per voxel
+    long long *numq, *denq;      // deterministic mode: 2^32 fixed point
+};
+
+void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s);
+void b4d_launch_filter(const FilterParams &p, bool wiener, bool deterministic, cudaStream_t s);
+void b4d_upload_tables(const B4dTables &t, cudaStream_t s);
+
+// misc kernels (b4d_misc.cu)
+void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, cudaStream_t s);
+void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float shift, float scale, cudaStream_t s);
+void b4d_launch_normalise(const float2 *acc, const float *fallback, float *out, long long n, cudaStream_t s);
+void b4d_launch_normalise_det(const long long *numq, const long long *denq, const float *fallback, float *out,
+                              long long n, cudaStream_t s);
+void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
+                         float step, cudaStream_t s);
+void b4d_launch_hist(const uint16_t *in, long long n, unsigned long long *hist, cudaStream_t s);
+// analysis of a float32 volume for the matching map: partial[6*blocks] doubles
+int b4d_analyze_blocks();
+void b4d_launch_analyze(const float *in, long long n, double c, double *partial, cudaStream_t s);
+// issue-rate microbenchmarks: returns lane-ops executed
+double b4d_launch_pipe_bench(int which, int iters, unsigned *sink, cudaStream_t s);

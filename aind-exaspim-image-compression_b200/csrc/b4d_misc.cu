@@ -1,0 +1,290 @@
+// b4d_misc.cu — the HBM-bound kernels around the two stages (K3/K6 normalise,
+// K7 quantize, K8 histogram, dtype preparation) and the issue-rate
+// microbenchmarks that give the INT32 / FP32 roofline denominators.
+//
+// All elementwise kernels are grid-stride over 16-byte vectors with the grid
+// sized to a multiple of the SM count; the tail is handled scalar.
+#include "b4d_common.cuh"
+
+namespace {
+
+int g_sms = 0;
+int sm_count() {
+    if (!g_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sms <= 0) g_sms = 148;
+    }
+    return g_sms;
+}
+unsigned grid_for(long long nvec, int threads, int per_sm) {
+    long long want = (nvec + threads - 1) / threads;
+    long long cap = (long long)sm_count() * per_sm;
+    if (want < 1) want = 1;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+// ------------------------------------------------------------ u16 -> f32 ----
+__global__ void __launch_bounds__(256) k_u16_to_f32(const uint16_t *__restrict__ in, float *__restrict__ out,
+                                                    long long n) {
+    const long long nv = n >> 3;  // 8 voxels: 16 B in, 32 B out
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(in) + i);
+        float4 a, b;
+        a.x = (float)(v.x & 0xFFFFu);
+        a.y = (float)(v.x >> 16);
+        a.z = (float)(v.y & 0xFFFFu);
+        a.w = (float)(v.y >> 16);
+        b.x = (float)(v.z & 0xFFFFu);
+        b.y = (float)(v.z >> 16);
+        b.z = (float)(v.w & 0xFFFFu);
+        b.w = (float)(v.w >> 16);
+        reinterpret_cast<float4 *>(out)[2 * i] = a;
+        reinterpret_cast<float4 *>(out)[2 * i + 1] = b;
+    }
+    for (long long i = (nv << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (float)in[i];
+}
+
+// ---------------------------------------------- f32 -> matching image (u16) --
+__device__ __forceinline__ uint32_t to_match(float v, float shift, float scale) {
+    float q = rintf((v + shift) * scale);
+    q = fminf(fmaxf(q, 0.0f), 65535.0f);
+    return (uint32_t)q;
+}
+__global__ void __launch_bounds__(256) k_to_match(const float *__restrict__ in, uint16_t *__restrict__ out,
+                                                  long long n, float shift, float scale) {
+    const long long nv = n >> 3;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const float4 a = reinterpret_cast<const float4 *>(in)[2 * i];
+        const float4 b = reinterpret_cast<const float4 *>(in)[2 * i + 1];
+        uint4 o;
+        o.x = to_match(a.x, shift, scale) | (to_match(a.y, shift, scale) << 16);
+        o.y = to_match(a.z, shift, scale) | (to_match(a.w, shift, scale) << 16);
+        o.z = to_match(b.x, shift, scale) | (to_match(b.y, shift, scale) << 16);
+        o.w = to_match(b.z, shift, scale) | (to_match(b.w, shift, scale) << 16);
+        reinterpret_cast<uint4 *>(out)[i] = o;
+    }
+    for (long long i = (nv << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (uint16_t)to_match(in[i], shift, scale);
+}
+
+// ------------------------------------------------------------- normalise ----
+// K3 / K6: out = num / den (den > 0), else the fallback value.  12 B/voxel.
+__global__ void __launch_bounds__(256) k_normalise(const float2 *__restrict__ acc, const float *__restrict__ fb,
+                                                   float *__restrict__ out, long long n) {
+    const long long nv = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const float4 p0 = __ldcs(reinterpret_cast<const float4 *>(acc) + 2 * i);
+        const float4 p1 = __ldcs(reinterpret_cast<const float4 *>(acc) + 2 * i + 1);
+        const float4 f = reinterpret_cast<const float4 *>(fb)[i];
+        float4 o;
+        o.x = p0.y > 0.0f ? p0.x / p0.y : f.x;
+        o.y = p0.w > 0.0f ? p0.z / p0.w : f.y;
+        o.z = p1.y > 0.0f ? p1.x / p1.y : f.z;
+        o.w = p1.w > 0.0f ? p1.z / p1.w : f.w;
+        reinterpret_cast<float4 *>(out)[i] = o;
+    }
+    for (long long i = (nv << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float2 p = acc[i];
+        out[i] = p.y > 0.0f ? p.x / p.y : fb[i];
+    }
+}
+__global__ void __launch_bounds__(256) k_normalise_det(const long long *__restrict__ numq,
+                                                       const long long *__restrict__ denq,
+                                                       const float *__restrict__ fb, float *__restrict__ out,
+                                                       long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long d = denq[i];
+        out[i] = d > 0 ? (float)((double)numq[i] / (double)d) : fb[i];
+    }
+}
+
+// -------------------------------------------------------------- quantize ----
+// K7: q = rint(clip((x - offset_sub + offset_add) / step, 0, 65535/step)).
+// float32, clip BEFORE round, round-half-to-even: transforms.py:403-411.
+__device__ __forceinline__ uint32_t quant1(float x, float osub, float oadd, float step, float hi, bool unit) {
+    float v = __fadd_rn(__fsub_rn(x, osub), oadd);
+    if (!unit) v = __fdiv_rn(v, step);
+    v = fminf(fmaxf(v, 0.0f), hi);
+    return (uint32_t)__float2int_rn(v);
+}
+__global__ void __launch_bounds__(256) k_quantize(const float *__restrict__ in, uint16_t *__restrict__ out,
+                                                  long long n, float osub, float oadd, float step) {
+    const bool unit = (step == 1.0f);
+    const float hi = __fdiv_rn(65535.0f, step);
+    const long long nv = n >> 3;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const float4 a = __ldcs(reinterpret_cast<const float4 *>(in) + 2 * i);
+        const float4 b = __ldcs(reinterpret_cast<const float4 *>(in) + 2 * i + 1);
+        uint4 o;
+        o.x = quant1(a.x, osub, oadd, step, hi, unit) | (quant1(a.y, osub, oadd, step, hi, unit) << 16);
+        o.y = quant1(a.z, osub, oadd, step, hi, unit) | (quant1(a.w, osub, oadd, step, hi, unit) << 16);
+        o.z = quant1(b.x, osub, oadd, step, hi, unit) | (quant1(b.y, osub, oadd, step, hi, unit) << 16);
+        o.w = quant1(b.z, osub, oadd, step, hi, unit) | (quant1(b.w, osub, oadd, step, hi, unit) << 16);
+        __stcs(reinterpret_cast<uint4 *>(out) + i, o);
+    }
+    for (long long i = (nv << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (uint16_t)quant1(in[i], osub, oadd, step, hi, unit);
+}
+
+// ------------------------------------------------------------- histogram ----
+// K8: exact 65536-bin histogram of a uint16 tile.  Bins below HOT live in a
+// per-CTA shared-memory histogram (ExaSPIM background sits there), the rest go
+// straight to global atomics; the shared part is flushed once per CTA.
+constexpr int HOT = 12288;
+__global__ void __launch_bounds__(512) k_hist(const uint16_t *__restrict__ in, long long n,
+                                              unsigned long long *__restrict__ hist) {
+    __shared__ unsigned int sh[HOT];
+    for (int i = threadIdx.x; i < HOT; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    const long long nv = n >> 3;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto add = [&](uint32_t v) {
+        if (v < HOT) atomicAdd(&sh[v], 1u);
+        else atomicAdd(&hist[v], 1ull);
+    };
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(in) + i);
+        add(v.x & 0xFFFFu);
+        add(v.x >> 16);
+        add(v.y & 0xFFFFu);
+        add(v.y >> 16);
+        add(v.z & 0xFFFFu);
+        add(v.z >> 16);
+        add(v.w & 0xFFFFu);
+        add(v.w >> 16);
+    }
+    for (long long i = (nv << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) add(in[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < HOT; i += blockDim.x) {
+        const unsigned int c = sh[i];
+        if (c) atomicAdd(&hist[i], (unsigned long long)c);
+    }
+}
+
+// -------------------------------------------- float32 analysis (match map) --
+// per-block partials: {max |frac dev|, min rint, max rint, min z, max z, unused}
+constexpr int AN_BLOCKS = 592;
+__global__ void __launch_bounds__(256) k_analyze(const float *__restrict__ in, long long n, double c,
+                                                 double *__restrict__ partial) {
+    double dev = 0.0, lo = 1e300, hi = -1e300, zlo = 1e300, zhi = -1e300;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double z = (double)in[i];
+        const double v = z + c, rv = rint(v);
+        dev = fmax(dev, fabs(v - rv));
+        lo = fmin(lo, rv);
+        hi = fmax(hi, rv);
+        zlo = fmin(zlo, z);
+        zhi = fmax(zhi, z);
+    }
+    __shared__ double sh[5][8];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        dev = fmax(dev, __shfl_xor_sync(B4D_FULL, dev, m));
+        lo = fmin(lo, __shfl_xor_sync(B4D_FULL, lo, m));
+        hi = fmax(hi, __shfl_xor_sync(B4D_FULL, hi, m));
+        zlo = fmin(zlo, __shfl_xor_sync(B4D_FULL, zlo, m));
+        zhi = fmax(zhi, __shfl_xor_sync(B4D_FULL, zhi, m));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sh[0][warp] = dev;
+        sh[1][warp] = lo;
+        sh[2][warp] = hi;
+        sh[3][warp] = zlo;
+        sh[4][warp] = zhi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            sh[0][0] = fmax(sh[0][0], sh[0][w]);
+            sh[1][0] = fmin(sh[1][0], sh[1][w]);
+            sh[2][0] = fmax(sh[2][0], sh[2][w]);
+            sh[3][0] = fmin(sh[3][0], sh[3][w]);
+            sh[4][0] = fmax(sh[4][0], sh[4][w]);
+        }
+        for (int q = 0; q < 5; ++q) partial[blockIdx.x * 6 + q] = sh[q][0];
+        partial[blockIdx.x * 6 + 5] = 0.0;
+    }
+}
+
+// ------------------------------------------------- issue-rate microbenchmarks
+// which: 0 IMAD, 1 IADD3, 2 dependent (sub, mad) pairs, 3 FFMA.  8 independent
+// chains per thread; 1024 threads per CTA, 2 CTAs per SM.
+template <int WHICH>
+__global__ void __launch_bounds__(1024) k_pipe(int iters, unsigned *sink) {
+    unsigned a[8];
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = threadIdx.x * 2654435761u + i;
+        f[i] = (float)(threadIdx.x + i) * 1e-3f;
+    }
+    const unsigned m = threadIdx.x | 1u, c = blockIdx.x + 3u;
+    const float fm = 1.0f + (float)threadIdx.x * 1e-9f, fc = (float)blockIdx.x * 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (WHICH == 0) a[i] = a[i] * m + c;
+                if (WHICH == 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(c));
+                if (WHICH == 2) {
+                    const int d = (int)a[i] - (int)c;       // sub
+                    a[i] = (unsigned)(d * d) + a[i];        // mad
+                }
+                if (WHICH == 3) f[i] = __fmaf_rn(f[i], fm, fc);
+            }
+        }
+    }
+    unsigned r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= a[i] ^ __float_as_uint(f[i]);
+    if (r == 0x12345678u) sink[0] = r;
+}
+
+}  // namespace
+
+void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, cudaStream_t s) {
+    k_u16_to_f32<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n);
+}
+void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float shift, float scale, cudaStream_t s) {
+    k_to_match<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, shift, scale);
+}
+void b4d_launch_normalise(const float2 *acc, const float *fallback, float *out, long long n, cudaStream_t s) {
+    k_normalise<<<grid_for(n >> 2, 256, 8), 256, 0, s>>>(acc, fallback, out, n);
+}
+void b4d_launch_normalise_det(const long long *numq, const long long *denq, const float *fallback, float *out,
+                              long long n, cudaStream_t s) {
+    k_normalise_det<<<grid_for(n, 256, 8), 256, 0, s>>>(numq, denq, fallback, out, n);
+}
+void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
+                         float step, cudaStream_t s) {
+    k_quantize<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, offset_sub, offset_add, step);
+}
+void b4d_launch_hist(const uint16_t *in, long long n, unsigned long long *hist, cudaStream_t s) {
+    k_hist<<<grid_for(n >> 3, 512, 2), 512, 0, s>>>(in, n, hist);
+}
+int b4d_analyze_blocks() { return AN_BLOCKS; }
+void b4d_launch_analyze(const float *in, long long n, double c, double *partial, cudaStream_t s) {
+    k_analyze<<<AN_BLOCKS, 256, 0, s>>>(in, n, c, partial);
+}
+double b4d_launch_pipe_bench(int which, int iters, unsigned *sink, cudaStream_t s) {
+    const int blocks = sm_count() * 2;
+    switch (which) {
+        case 0: k_pipe<0><<<blocks, 1024, 0, s>>>(iters, sink); break;
+        case 1: k_pipe<1><<<blocks, 1024, 0, s>>>(iters, sink); break;
+        case 2: k_pipe<2><<<blocks, 1024, 0, s>>>(iters, sink); break;
+        default: k_pipe<3><<<blocks, 1024, 0, s>>>(iters, sink); break;
+    }
+    const double per_iter = (which == 2) ? 2.0 : 1.0;
+    return (double)blocks * 1024.0 * (double)iters * 16.0 * 8.0 * per_iter;
+}

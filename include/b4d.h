@@ -1,0 +1,168 @@
+/*
+ * b4d.h — C ABI of the B200-native BM4D denoise path (libb4d.so).
+ *
+ * What this boundary replaces in the reference (paths under /root/reference):
+ *
+ *   - `from bm4d import bm4d`           machine_learning/data_handling.py:12, evaluate.py:11
+ *   - `teacher = bm4d(raw, sigma)`      machine_learning/data_handling.py:332, :926
+ *   - `bm4d(noise, 10)`                 evaluate.py:202            (uint16 view in)
+ *   - offset subtract before the call   machine_learning/data_handling.py:353-354
+ *   - clip after the call               machine_learning/data_handling.py:333, :927
+ *   - clip + rint + uint16              machine_learning/transforms.py:150-152, :409-411
+ *   - low percentile of non-zero voxels machine_learning/transforms.py:433-438
+ *   - median / MAD noise statistic      machine_learning/metrics.py:54-58
+ *
+ * The reference has no FFI of its own for this path: the arithmetic lives in
+ * the closed third-party wheel bm4d==4.2.5 (uv.lock:387-400), bound by name at
+ * import time.  The entry points below are what a ctypes binding for that call
+ * needs; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative b4d_status;
+ *     b4d_last_error() returns a thread-local message for the last failure;
+ *   - the caller owns every data buffer, the handle owns scratch and a stream;
+ *   - pointers are host pointers unless the matching *_on_device flag is set;
+ *   - volumes are C-order (z, y, x), x fastest, shape = {D, H, W};
+ *   - one handle per (process, device); a handle is not thread-safe;
+ *   - calls are synchronous: results are complete when the call returns.
+ *
+ * The same ABI is implemented by the CPU oracle (oracle/liboracle.so, test
+ * infrastructure only) so one harness drives both.
+ */
+#ifndef B4D_H_
+#define B4D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B4D_ABI_VERSION 1
+
+typedef enum b4d_status {
+    B4D_OK = 0,
+    B4D_ERR_INVALID = -1,     /* bad argument (shape, dtype contract, profile) */
+    B4D_ERR_CUDA = -2,        /* a CUDA call failed; message names the call     */
+    B4D_ERR_NOMEM = -3,       /* host or device allocation failed               */
+    B4D_ERR_UNSUPPORTED = -4, /* valid request this build does not implement    */
+    B4D_ERR_TOO_LARGE = -5    /* index space exceeds the ABI's integer width    */
+} b4d_status;
+
+/* Algorithm profile.  Defaults are SURVEY.md Appendix A; every constant the
+ * closed bm4d binary may choose differently is a field here. */
+typedef struct b4d_profile {
+    int32_t abi;            /* B4D_ABI_VERSION                                         */
+    int32_t block;          /* block side L; only 4 is implemented                     */
+    int32_t step;           /* reference-block stride; only 3 is implemented           */
+    int32_t search_ht;      /* search window side Ns (odd, 3..15), stage 1             */
+    int32_t search_wie;     /* search window side Ns (odd, 3..15), stage 2             */
+    int32_t k_ht;           /* max group size, stage 1 (power of two, <= 32)           */
+    int32_t k_wie;          /* max group size, stage 2 (power of two, <= 32)           */
+    int32_t stages;         /* 1 = hard-threshold stage only, 2 = + Wiener stage       */
+    int32_t deterministic;  /* 1 = order-independent fixed-point aggregation           */
+    int32_t reserved0;
+    float tau_ht;           /* match acceptance: SSD <= floor(tau*sigma^2*L^3)         */
+    float tau_wie;
+    float lambda_ht;        /* hard threshold: zero |c| < lambda*sigma                 */
+    float kaiser_beta;      /* aggregation window; <= 0 selects an all-ones window     */
+} b4d_profile;
+
+/* Per-tile statistics (K8).  Semantics are exact: every field is what NumPy 2.x
+ * returns on the same uint16 data cast to float32 (float32 virtual index and
+ * interpolation included), widened to double. */
+typedef struct b4d_stats {
+    int64_t n;              /* voxels seen                                             */
+    int64_t n_nonzero;      /* voxels > 0                                              */
+    double offset;          /* percentile(x[x > 0], pct)       transforms.py:433-438   */
+    double median;          /* median(x)                       metrics.py:55           */
+    double mad;             /* median(|x - median|) + 1e-6     metrics.py:56           */
+    double sigma;           /* 1.4826 * mad                    metrics.py:57           */
+    double vmin;
+    double vmax;
+} b4d_stats;
+
+typedef struct b4d_handle b4d_handle;
+
+int b4d_version(void);
+const char *b4d_last_error(void);
+void b4d_default_profile(b4d_profile *p);
+
+/* Create / destroy a handle bound to CUDA device `device` (ignored by the
+ * oracle build).  `profile` may be NULL for the defaults. */
+int b4d_create(int device, const b4d_profile *profile, b4d_handle **out);
+void b4d_destroy(b4d_handle *h);
+int b4d_set_profile(b4d_handle *h, const b4d_profile *profile);
+
+/* Full BM4D denoise of `n` independent equal-shape volumes (n = 1 for one
+ * patch).  Replaces bm4d.bm4d(z, sigma) at data_handling.py:332/:926 and
+ * evaluate.py:202.  Output is float32, unclipped, same shape.
+ *
+ * u16: the filter runs on float(in); matching runs on the integers.
+ * f32: the filter runs on `in`; matching runs on the integer image recovered
+ *      from it (uint16 counts minus one scalar offset, data_handling.py:353-354)
+ *      or, for non-integral data, on a 16-bit quantisation of it.            */
+int b4d_denoise_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t shape[3],
+                    float sigma, float *out, int in_on_device, int out_on_device);
+int b4d_denoise_f32(b4d_handle *h, const float *in, int64_t n, const int64_t shape[3],
+                    float sigma, float *out, int in_on_device, int out_on_device);
+
+/* One z-slab of a larger volume.  `in` holds global planes
+ * [z_begin, z_begin + shape[0]) of a volume with `z_total` planes; reference
+ * blocks sit on the GLOBAL grid and only those whose search window lies inside
+ * the slab are processed.  `out` receives planes [own_begin, own_end) (global
+ * numbering), own_end - own_begin planes of H*W floats.  Exact (equal to the
+ * whole-volume result) when the slab extends 2*(Ns-1+L-1) planes beyond the
+ * owned range on each interior face. */
+int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3],
+                         int64_t z_begin, int64_t z_total, int64_t own_begin, int64_t own_end,
+                         float sigma, float *out, int in_on_device, int out_on_device);
+
+/* Instrumented stage-1 matcher (bit-exactness test, BASELINE config 3).
+ * R = number of reference blocks, K = profile.k_ht.  Host pointers.
+ *   idx[R*K]   linear candidate origin (z*H' + y)*W' + x, H' = H-L+1, W' = W-L+1; -1 = unused
+ *   ssd[R*K]   exact integer SSD; UINT64_MAX = unused
+ *   count[R]   group size actually used (power of two)                        */
+int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], float sigma,
+                     int32_t *idx, uint64_t *ssd, int32_t *count);
+int64_t b4d_num_refs(const int64_t shape[3]);
+
+/* Fused offset-subtract + clip + (noise-scaled) quantize, K7:
+ *   q = rint(clip((x - offset_sub + offset_add) / step, 0, 65535 / step)) -> uint16
+ * At step = 1, offset_sub = 0 this is transforms.py:403-411 bit for bit. */
+int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub,
+                     float offset_add, float step, uint16_t *out, int in_on_device,
+                     int out_on_device);
+
+/* Per-tile statistics, K8.  Also returns the exact 65536-bin histogram when
+ * `hist` is non-NULL (host pointer, 65536 x int64) — that histogram is the
+ * payload ranks allgather to agree on a global offset / sigma. */
+int b4d_tile_stats(b4d_handle *h, const uint16_t *in, int64_t n, double pct, b4d_stats *out,
+                   int64_t *hist, int in_on_device);
+
+/* Device time of the last denoise call, per kernel family, in milliseconds
+ * (CUDA events on the handle's stream).  names: see B4D_T_* below. */
+#define B4D_T_PREP 0
+#define B4D_T_MATCH1 1
+#define B4D_T_FILTER1 2
+#define B4D_T_NORM1 3
+#define B4D_T_MATCH2 4
+#define B4D_T_FILTER2 5
+#define B4D_T_NORM2 6
+#define B4D_T_COUNT 8
+int b4d_last_timings(b4d_handle *h, float ms[B4D_T_COUNT], int64_t launches[B4D_T_COUNT]);
+
+/* Diagnostics of the last matching launch(es): out[0] = reference blocks that
+ * took the survivor-list overflow fallback, out[1] = tiles on the uint64 path. */
+int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]);
+
+/* Measured issue-rate peaks on this device (shipped microbenchmark):
+ *   out[0] = IMAD lane-ops/s, out[1] = IADD3 lane-ops/s,
+ *   out[2] = dependent (sub, mad) pair stream in lane-ops/s (2 per pair),
+ *   out[3] = FFMA lane-ops/s.                                                */
+int b4d_measure_pipe_peaks(b4d_handle *h, double out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B4D_H_ */

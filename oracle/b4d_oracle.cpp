@@ -1,0 +1,854 @@
+// b4d_oracle.cpp — CPU ORACLE for the BM4D denoise path.  TEST INFRASTRUCTURE ONLY.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may load this library.  The product (libb4d.so) never does.
+//
+// PARITY UNPINNED.  The reference calls the closed third-party wheel
+// bm4d==4.2.5 (uv.lock:387-400; call sites data_handling.py:332, :926 and
+// evaluate.py:202).  It is absent from /root/reference, from this image and
+// from the GPU box, and no reference test holds a single BM4D output value,
+// so this file restates the PUBLISHED algorithm (Maggioni, Katkovnik,
+// Egiazarian, Foi, IEEE TIP 2013) under the contract of SURVEY.md Appendix A /
+// DESIGN.md §3.  Steps that DO exist in the reference tree are followed line
+// by line in oracle/np_oracle.py and pinned against the imported reference
+// (tests/golden/).
+//
+// Two independent arithmetic paths are provided on purpose:
+//
+//   arith = "f64"    plain restatement: dense orthonormal matrices (Haar-4 =
+//                    periodised bior1.5 at L = 4, DCT-II-4, Haar-K), float64
+//                    everywhere, float64 accumulators.  This is the oracle the
+//                    tolerance test (max-abs 0.5, rel-L2 1e-3) is stated against.
+//   arith = "mirror" the same algorithm in float32 with the operation order the
+//                    CUDA kernels use (unnormalised butterflies, power-of-two
+//                    rescale, fixed-point int64 aggregation).  With the
+//                    profile's deterministic flag the CUDA path must equal this
+//                    BIT FOR BIT — a much sharper regression check.
+//
+// Compile with -ffp-contract=off (oracle/Makefile does): the mirror path relies
+// on every float operation being rounded exactly once, and uses fmaf() where
+// the kernels use an explicit FMA.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../include/b4d.h"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+constexpr int L = 4;
+constexpr int LV = 64;
+
+struct b4d_handle_impl {
+    b4d_profile prof;
+    int arith;  // 0 = mirror (float32, CUDA op order), 1 = f64 plain restatement
+    int threads;
+};
+
+// ---------------------------------------------------------------- profile ---
+void default_profile(b4d_profile *p) {
+    std::memset(p, 0, sizeof(*p));
+    p->abi = B4D_ABI_VERSION;
+    p->block = 4;
+    p->step = 3;
+    p->search_ht = 11;
+    p->search_wie = 11;
+    p->k_ht = 16;
+    p->k_wie = 32;
+    p->stages = 2;
+    p->deterministic = 0;
+    p->tau_ht = 2.9527f;
+    p->tau_wie = 0.7693f;
+    p->lambda_ht = 2.7f;
+    p->kaiser_beta = 2.0f;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int check_profile(const b4d_profile &p) {
+    if (p.abi != B4D_ABI_VERSION) return fail(B4D_ERR_INVALID, "profile.abi mismatch");
+    if (p.block != 4 || p.step != 3)
+        return fail(B4D_ERR_UNSUPPORTED, "only block = 4, step = 3 are implemented");
+    for (int ns : {p.search_ht, p.search_wie})
+        if (ns < 3 || ns > 15 || (ns & 1) == 0)
+            return fail(B4D_ERR_INVALID, "search window side must be odd in [3, 15]");
+    for (int k : {p.k_ht, p.k_wie})
+        if (!is_pow2(k) || k > 32) return fail(B4D_ERR_INVALID, "group size must be a power of two <= 32");
+    if (p.stages != 1 && p.stages != 2) return fail(B4D_ERR_INVALID, "stages must be 1 or 2");
+    if (!(p.tau_ht > 0) || !(p.tau_wie > 0) || !(p.lambda_ht >= 0))
+        return fail(B4D_ERR_INVALID, "tau / lambda must be positive");
+    return 0;
+}
+
+// ------------------------------------------------------------------- grid ---
+// Reference-block origins along one axis: 0, 3, 6, ... plus a final flush
+// origin N - L when (N - L) is not on the grid.
+std::vector<int> ref_origins(int64_t n) {
+    std::vector<int> o;
+    for (int64_t v = 0; v + L <= n; v += 3) o.push_back((int)v);
+    if ((n - L) % 3 != 0) o.push_back((int)(n - L));
+    return o;
+}
+
+// z origins of one slab: global grid, kept when the whole search window lies
+// inside the slab; returned in slab-local coordinates.
+std::vector<int> slab_origins(int64_t z_total, int64_t z_begin, int64_t depth, int r) {
+    std::vector<int> o;
+    for (int g : ref_origins(z_total)) {
+        int64_t lo = std::max<int64_t>(0, g - r);
+        int64_t hi = std::min<int64_t>(z_total - L, g + r) + (L - 1);
+        if (lo >= z_begin && hi < z_begin + depth) o.push_back((int)(g - z_begin));
+    }
+    return o;
+}
+
+struct Geom {
+    int D, H, W;
+    std::vector<int> rz, ry, rx;
+    int64_t nrefs() const { return (int64_t)rz.size() * ry.size() * rx.size(); }
+};
+
+// -------------------------------------------------------------- matching ---
+// Exact integer SSD over 4x4x4 blocks of a uint16 image; candidates are every
+// origin of the Ns^3 window clipped to [0, N - L]; accepted when SSD <= tau;
+// ordered by (SSD, window index (dz*Ns + dy)*Ns + dx); truncated to the largest
+// power of two <= min(K, accepted).
+struct Matches {
+    int K;
+    std::vector<uint16_t> widx;  // [R*K] window index
+    std::vector<uint64_t> ssd;   // [R*K]
+    std::vector<uint8_t> cnt;    // [R]
+};
+
+void match_all(const uint16_t *u, const Geom &g, int Ns, int K, uint64_t tau, Matches &m) {
+    const int r = Ns / 2;
+    const int64_t R = g.nrefs();
+    m.K = K;
+    m.widx.assign(R * K, 0xFFFF);
+    m.ssd.assign(R * K, UINT64_MAX);
+    m.cnt.assign(R, 0);
+    const int nry = (int)g.ry.size(), nrx = (int)g.rx.size();
+    const int64_t sy = g.W, sz = (int64_t)g.W * g.H;
+#pragma omp parallel
+    {
+        std::vector<std::pair<uint64_t, uint32_t>> acc;
+        acc.reserve(Ns * Ns * Ns);
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t ri = 0; ri < R; ++ri) {
+            const int oz = g.rz[ri / ((int64_t)nry * nrx)];
+            const int oy = g.ry[(ri / nrx) % nry];
+            const int ox = g.rx[ri % nrx];
+            int32_t ref[LV];
+            for (int z = 0; z < L; ++z)
+                for (int y = 0; y < L; ++y)
+                    for (int x = 0; x < L; ++x)
+                        ref[(z * L + y) * L + x] = u[(oz + z) * sz + (oy + y) * sy + ox + x];
+            acc.clear();
+            const int z0 = std::max(0, oz - r), z1 = std::min(g.D - L, oz + r);
+            const int y0 = std::max(0, oy - r), y1 = std::min(g.H - L, oy + r);
+            const int x0 = std::max(0, ox - r), x1 = std::min(g.W - L, ox + r);
+            for (int cz = z0; cz <= z1; ++cz)
+                for (int cy = y0; cy <= y1; ++cy)
+                    for (int cx = x0; cx <= x1; ++cx) {
+                        uint64_t s = 0;
+                        const uint16_t *c = u + cz * sz + cy * sy + cx;
+                        for (int z = 0; z < L; ++z)
+                            for (int y = 0; y < L; ++y) {
+                                const uint16_t *row = c + z * sz + y * sy;
+                                const int32_t *rr = ref + (z * L + y) * L;
+                                for (int x = 0; x < L; ++x) {
+                                    int64_t d = (int64_t)row[x] - rr[x];
+                                    s += (uint64_t)(d * d);
+                                }
+                            }
+                        if (s <= tau) {
+                            uint32_t wi = (uint32_t)(((cz - (oz - r)) * Ns + (cy - (oy - r))) * Ns +
+                                                     (cx - (ox - r)));
+                            acc.emplace_back(s, wi);
+                        }
+                    }
+            std::sort(acc.begin(), acc.end());
+            int n = (int)std::min<size_t>(acc.size(), (size_t)K);
+            int kp = 1;
+            while (kp * 2 <= n) kp *= 2;
+            if (n == 0) kp = 0;  // cannot happen: the reference block matches itself with SSD 0
+            m.cnt[ri] = (uint8_t)kp;
+            for (int k = 0; k < kp; ++k) {
+                m.ssd[ri * K + k] = acc[k].first;
+                m.widx[ri * K + k] = (uint16_t)acc[k].second;
+            }
+        }
+    }
+}
+
+inline void widx_to_origin(int wi, int Ns, int r, int oz, int oy, int ox, int &cz, int &cy, int &cx) {
+    cz = oz - r + wi / (Ns * Ns);
+    cy = oy - r + (wi / Ns) % Ns;
+    cx = ox - r + wi % Ns;
+}
+
+// ---------------------------------------------------------------- window ---
+double bessel_i0(double x) {
+    double s = 1.0, t = 1.0;
+    for (int k = 1; k < 64; ++k) {
+        t *= (x / (2.0 * k)) * (x / (2.0 * k));
+        s += t;
+        if (t < 1e-18 * s) break;
+    }
+    return s;
+}
+void kaiser4(double beta, double w[4]) {
+    for (int n = 0; n < 4; ++n) {
+        if (beta <= 0) {
+            w[n] = 1.0;
+            continue;
+        }
+        double a = 2.0 * n / 3.0 - 1.0;
+        w[n] = bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - a * a))) / bessel_i0(beta);
+    }
+}
+
+// =====================================================================
+//  Path 1: plain float64 restatement with dense orthonormal matrices
+// =====================================================================
+struct Mats {
+    double haar4[4][4], dct4[4][4];
+};
+Mats make_mats() {
+    Mats m{};
+    const double h = 0.5, q = 1.0 / std::sqrt(2.0);
+    // Periodised bior1.5 analysis matrix at length 4, full decomposition,
+    // row-normalised, equals the orthonormal Haar matrix.
+    const double hh[4][4] = {{h, h, h, h}, {h, h, -h, -h}, {q, -q, 0, 0}, {0, 0, q, -q}};
+    std::memcpy(m.haar4, hh, sizeof(hh));
+    for (int k = 0; k < 4; ++k)
+        for (int n = 0; n < 4; ++n) {
+            double c = (k == 0) ? 0.5 : std::sqrt(0.5);
+            m.dct4[k][n] = c * std::cos(M_PI * (2 * n + 1) * k / 8.0);
+        }
+    return m;
+}
+// Orthonormal Haar matrix of size K (power of two), full dyadic decomposition.
+// Row layout: row 0 = scaling function; the detail of level l (l = 1 finest)
+// covering samples [i, i + 2^l) sits at row i + 2^(l-1) — the same placement the
+// in-place butterflies of the mirror path produce.
+std::vector<double> haar_matrix(int K) {
+    std::vector<double> m((size_t)K * K, 0.0);
+    for (int j = 0; j < K; ++j) m[j] = 1.0 / std::sqrt((double)K);
+    for (int s = 1; s < K; s *= 2)
+        for (int i = 0; i < K; i += 2 * s) {
+            double a = 1.0 / std::sqrt(2.0 * s);
+            for (int j = 0; j < s; ++j) {
+                m[(size_t)(i + s) * K + i + j] = a;
+                m[(size_t)(i + s) * K + i + s + j] = -a;
+            }
+        }
+    return m;
+}
+
+void sep3(const double T[4][4], bool transpose, const double *in, double *out) {
+    double a[LV], b[LV];
+    auto t = [&](int k, int n) { return transpose ? T[n][k] : T[k][n]; };
+    for (int z = 0; z < 4; ++z)
+        for (int y = 0; y < 4; ++y)
+            for (int k = 0; k < 4; ++k) {
+                double s = 0;
+                for (int n = 0; n < 4; ++n) s += t(k, n) * in[(z * 4 + y) * 4 + n];
+                a[(z * 4 + y) * 4 + k] = s;
+            }
+    for (int z = 0; z < 4; ++z)
+        for (int x = 0; x < 4; ++x)
+            for (int k = 0; k < 4; ++k) {
+                double s = 0;
+                for (int n = 0; n < 4; ++n) s += t(k, n) * a[(z * 4 + n) * 4 + x];
+                b[(z * 4 + k) * 4 + x] = s;
+            }
+    for (int y = 0; y < 4; ++y)
+        for (int x = 0; x < 4; ++x)
+            for (int k = 0; k < 4; ++k) {
+                double s = 0;
+                for (int n = 0; n < 4; ++n) s += t(k, n) * b[(n * 4 + y) * 4 + x];
+                out[(k * 4 + y) * 4 + x] = s;
+            }
+}
+
+void group_xf(const std::vector<double> &G, int K, bool transpose, std::vector<double> &stack) {
+    std::vector<double> tmp((size_t)K * LV);
+    for (int k = 0; k < K; ++k)
+        for (int v = 0; v < LV; ++v) {
+            double s = 0;
+            for (int j = 0; j < K; ++j)
+                s += (transpose ? G[(size_t)j * K + k] : G[(size_t)k * K + j]) * stack[(size_t)j * LV + v];
+            tmp[(size_t)k * LV + v] = s;
+        }
+    stack.swap(tmp);
+}
+
+template <bool WIENER>
+void filter_f64(const float *zf, const double *basic, const Geom &g, const Matches &m, int Ns,
+                double sigma, const b4d_profile &p, std::vector<double> &num,
+                std::vector<double> &den) {
+    const Mats mats = make_mats();
+    const int r = Ns / 2;
+    double kw[4], win[LV];
+    kaiser4(p.kaiser_beta, kw);
+    for (int z = 0; z < 4; ++z)
+        for (int y = 0; y < 4; ++y)
+            for (int x = 0; x < 4; ++x) win[(z * 4 + y) * 4 + x] = kw[z] * kw[y] * kw[x];
+    std::vector<std::vector<double>> hm(6);
+    for (int l = 0; l <= 5; ++l) hm[l] = haar_matrix(1 << l);
+    const int nry = (int)g.ry.size(), nrx = (int)g.rx.size();
+    const int64_t sy = g.W, sz = (int64_t)g.W * g.H;
+    const int64_t R = g.nrefs();
+    const double thr = (double)p.lambda_ht * sigma;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t ri = 0; ri < R; ++ri) {
+        const int kp = m.cnt[ri];
+        if (kp == 0) continue;
+        int lg = 0;
+        while ((1 << lg) < kp) ++lg;
+        const int oz = g.rz[ri / ((int64_t)nry * nrx)];
+        const int oy = g.ry[(ri / nrx) % nry];
+        const int ox = g.rx[ri % nrx];
+        int cz[32], cy[32], cx[32];
+        std::vector<double> noisy((size_t)kp * LV), est((size_t)kp * LV);
+        double blk[LV];
+        for (int k = 0; k < kp; ++k) {
+            widx_to_origin(m.widx[ri * m.K + k], Ns, r, oz, oy, ox, cz[k], cy[k], cx[k]);
+            for (int z = 0; z < 4; ++z)
+                for (int y = 0; y < 4; ++y)
+                    for (int x = 0; x < 4; ++x)
+                        blk[(z * 4 + y) * 4 + x] = zf[(cz[k] + z) * sz + (cy[k] + y) * sy + cx[k] + x];
+            sep3(WIENER ? mats.dct4 : mats.haar4, false, blk, &noisy[(size_t)k * LV]);
+            if (WIENER) {
+                for (int z = 0; z < 4; ++z)
+                    for (int y = 0; y < 4; ++y)
+                        for (int x = 0; x < 4; ++x)
+                            blk[(z * 4 + y) * 4 + x] =
+                                basic[(cz[k] + z) * sz + (cy[k] + y) * sy + cx[k] + x];
+                sep3(mats.dct4, false, blk, &est[(size_t)k * LV]);
+            }
+        }
+        group_xf(hm[lg], kp, false, noisy);
+        double weight;
+        if (!WIENER) {
+            int64_t kept = 0;
+            for (auto &c : noisy) {
+                if (std::fabs(c) < thr)
+                    c = 0.0;
+                else
+                    ++kept;
+            }
+            weight = 1.0 / (double)std::max<int64_t>(kept, 1);  // sigma^-2 cancels in num/den
+        } else {
+            group_xf(hm[lg], kp, false, est);
+            double sw2 = 0;
+            for (size_t i = 0; i < noisy.size(); ++i) {
+                double y2 = est[i] * est[i];
+                double w = y2 / (y2 + sigma * sigma);
+                noisy[i] *= w;
+                sw2 += w * w;
+            }
+            weight = 1.0 / std::max(sw2, 1.0);
+        }
+        group_xf(hm[lg], kp, true, noisy);
+        for (int k = 0; k < kp; ++k) {
+            sep3(WIENER ? mats.dct4 : mats.haar4, true, &noisy[(size_t)k * LV], blk);
+            for (int z = 0; z < 4; ++z)
+                for (int y = 0; y < 4; ++y)
+                    for (int x = 0; x < 4; ++x) {
+                        const int v = (z * 4 + y) * 4 + x;
+                        const int64_t a = (cz[k] + z) * sz + (cy[k] + y) * sy + cx[k] + x;
+                        const double ww = weight * win[v];
+#pragma omp atomic
+                        num[a] += ww * blk[v];
+#pragma omp atomic
+                        den[a] += ww;
+                    }
+        }
+    }
+}
+
+// =====================================================================
+//  Path 2: float32 mirror of the CUDA kernels' operation order
+// =====================================================================
+struct MirrorTables {
+    float win[LV];       // (w[z]*w[y])*w[x] in float32
+    float tht[16];       // tht[m] = float(lambda*sigma*2^(m/2)), m = 6 - n + l
+    float gs[6];         // gs[l] = float(2^(-l/2)): group normalisation
+    float c1, c3;        // DCT-II-4 constants
+    float sigma2;        // float(sigma)*float(sigma)
+};
+MirrorTables make_tables(const b4d_profile &p, float sigma) {
+    MirrorTables t{};
+    double kw[4];
+    kaiser4(p.kaiser_beta, kw);
+    float kf[4];
+    for (int i = 0; i < 4; ++i) kf[i] = (float)kw[i];
+    for (int z = 0; z < 4; ++z)
+        for (int y = 0; y < 4; ++y)
+            for (int x = 0; x < 4; ++x) t.win[(z * 4 + y) * 4 + x] = (kf[z] * kf[y]) * kf[x];
+    for (int m = 0; m < 16; ++m) {
+        double s = std::ldexp(1.0, m / 2) * ((m & 1) ? M_SQRT2 : 1.0);
+        t.tht[m] = (float)((double)p.lambda_ht * (double)sigma * s);
+    }
+    for (int l = 0; l < 6; ++l) t.gs[l] = (float)(std::ldexp(1.0, -(l / 2)) * ((l & 1) ? M_SQRT1_2 : 1.0));
+    t.c1 = (float)(std::cos(M_PI / 8.0) * M_SQRT1_2);
+    t.c3 = (float)(std::cos(3.0 * M_PI / 8.0) * M_SQRT1_2);
+    t.sigma2 = sigma * sigma;
+    return t;
+}
+
+// unnormalised Haar-4 butterflies, in place on 4 strided values
+inline void haar4_fwd(float *v, int s) {
+    float a = v[0] + v[s], b = v[2 * s] + v[3 * s], c = v[0] - v[s], d = v[2 * s] - v[3 * s];
+    v[0] = a + b;
+    v[s] = a - b;
+    v[2 * s] = c;
+    v[3 * s] = d;
+}
+inline void haar4_inv(float *v, int s) {
+    float pp = v[0] + v[s], q = v[0] - v[s], y2 = v[2 * s], y3 = v[3 * s];
+    v[0] = pp + y2;
+    v[s] = pp - y2;
+    v[2 * s] = q + y3;
+    v[3 * s] = q - y3;
+}
+inline void dct4_fwd(float *v, int s, float c1, float c3) {
+    float a = v[0] + v[3 * s], b = v[s] + v[2 * s], c = v[0] - v[3 * s], d = v[s] - v[2 * s];
+    v[0] = (a + b) * 0.5f;
+    v[2 * s] = (a - b) * 0.5f;
+    v[s] = fmaf(c1, c, c3 * d);
+    v[3 * s] = fmaf(c3, c, -(c1 * d));
+}
+inline void dct4_inv(float *v, int s, float c1, float c3) {
+    float a = (v[0] + v[2 * s]) * 0.5f, b = (v[0] - v[2 * s]) * 0.5f;
+    float c = fmaf(c1, v[s], c3 * v[3 * s]), d = fmaf(c3, v[s], -(c1 * v[3 * s]));
+    v[0] = a + c;
+    v[3 * s] = a - c;
+    v[s] = b + d;
+    v[2 * s] = b - d;
+}
+template <bool DCT>
+inline void xf3_fwd(float *b, const MirrorTables &t) {
+    for (int i = 0; i < 16; ++i) DCT ? dct4_fwd(b + 4 * i, 1, t.c1, t.c3) : haar4_fwd(b + 4 * i, 1);
+    for (int z = 0; z < 4; ++z)
+        for (int x = 0; x < 4; ++x)
+            DCT ? dct4_fwd(b + 16 * z + x, 4, t.c1, t.c3) : haar4_fwd(b + 16 * z + x, 4);
+    for (int i = 0; i < 16; ++i) DCT ? dct4_fwd(b + i, 16, t.c1, t.c3) : haar4_fwd(b + i, 16);
+}
+template <bool DCT>
+inline void xf3_inv(float *b, const MirrorTables &t) {
+    for (int i = 0; i < 16; ++i) DCT ? dct4_inv(b + i, 16, t.c1, t.c3) : haar4_inv(b + i, 16);
+    for (int z = 0; z < 4; ++z)
+        for (int x = 0; x < 4; ++x)
+            DCT ? dct4_inv(b + 16 * z + x, 4, t.c1, t.c3) : haar4_inv(b + 16 * z + x, 4);
+    for (int i = 0; i < 16; ++i) DCT ? dct4_inv(b + 4 * i, 1, t.c1, t.c3) : haar4_inv(b + 4 * i, 1);
+}
+// in-place unnormalised Haar along the group, element k of block-major stack
+inline void ghaar_fwd(float *st, int kp) {
+    for (int s = 1; s < kp; s *= 2)
+        for (int i = 0; i < kp; i += 2 * s)
+            for (int v = 0; v < LV; ++v) {
+                float a = st[i * LV + v], b = st[(i + s) * LV + v];
+                st[i * LV + v] = a + b;
+                st[(i + s) * LV + v] = a - b;
+            }
+}
+inline void ghaar_inv(float *st, int kp) {
+    for (int s = kp / 2; s >= 1; s /= 2)
+        for (int i = 0; i < kp; i += 2 * s)
+            for (int v = 0; v < LV; ++v) {
+                float a = st[i * LV + v], b = st[(i + s) * LV + v];
+                st[i * LV + v] = a + b;
+                st[(i + s) * LV + v] = a - b;
+            }
+}
+// detail level of group slot k: l = 1 + log2(lowest set bit); slot 0 -> log2(kp)
+inline int group_level(int k, int lg) { return k == 0 ? lg : 1 + __builtin_ctz((unsigned)k); }
+inline int spatial_class(int v) { return ((v & 3) >= 2) + (((v >> 2) & 3) >= 2) + ((v >> 4) >= 2); }
+
+constexpr float FIX_SCALE = 4294967296.0f;  // 2^32
+
+template <bool WIENER>
+void filter_mirror(const float *zf, const float *basic, const Geom &g, const Matches &m, int Ns,
+                   const MirrorTables &t, std::vector<int64_t> &numq, std::vector<int64_t> &denq) {
+    const int r = Ns / 2;
+    const int nry = (int)g.ry.size(), nrx = (int)g.rx.size();
+    const int64_t sy = g.W, sz = (int64_t)g.W * g.H;
+    const int64_t R = g.nrefs();
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t ri = 0; ri < R; ++ri) {
+        const int kp = m.cnt[ri];
+        if (kp == 0) continue;
+        int lg = 0;
+        while ((1 << lg) < kp) ++lg;
+        const int oz = g.rz[ri / ((int64_t)nry * nrx)];
+        const int oy = g.ry[(ri / nrx) % nry];
+        const int ox = g.rx[ri % nrx];
+        int cz[32], cy[32], cx[32];
+        float noisy[32 * LV], est[32 * LV];
+        for (int k = 0; k < kp; ++k) {
+            widx_to_origin(m.widx[ri * m.K + k], Ns, r, oz, oy, ox, cz[k], cy[k], cx[k]);
+            for (int z = 0; z < 4; ++z)
+                for (int y = 0; y < 4; ++y)
+                    for (int x = 0; x < 4; ++x) {
+                        const int64_t a = (cz[k] + z) * sz + (cy[k] + y) * sy + cx[k] + x;
+                        noisy[k * LV + (z * 4 + y) * 4 + x] = zf[a];
+                        if (WIENER) est[k * LV + (z * 4 + y) * 4 + x] = basic[a];
+                    }
+        }
+        float weight;
+        if (!WIENER) {
+            for (int k = 0; k < kp; ++k) xf3_fwd<false>(noisy + k * LV, t);
+            ghaar_fwd(noisy, kp);
+            int kept = 0;
+            for (int k = 0; k < kp; ++k) {
+                const int l = group_level(k, lg);
+                for (int v = 0; v < LV; ++v) {
+                    const int n = spatial_class(v);
+                    float c = noisy[k * LV + v];
+                    if (fabsf(c) < t.tht[6 - n + l]) {
+                        c = 0.0f;
+                    } else {
+                        ++kept;
+                        c = ldexpf(c, -(6 - n + l));  // exact: squared normalisation 2^(-6+n-l)
+                    }
+                    noisy[k * LV + v] = c;
+                }
+            }
+            weight = 1.0f / (float)std::max(kept, 1);
+            ghaar_inv(noisy, kp);
+            for (int k = 0; k < kp; ++k) xf3_inv<false>(noisy + k * LV, t);
+        } else {
+            // basic-estimate stack first (gives the Wiener attenuation), then the noisy stack
+            for (int k = 0; k < kp; ++k) xf3_fwd<true>(est + k * LV, t);
+            ghaar_fwd(est, kp);
+            for (int k = 0; k < kp; ++k) xf3_fwd<true>(noisy + k * LV, t);
+            ghaar_fwd(noisy, kp);
+            float part[32];
+            for (int k = 0; k < 32; ++k) part[k] = 0.0f;
+            for (int k = 0; k < kp; ++k) {
+                const int l = group_level(k, lg);
+                float acc = 0.0f;
+                for (int v = 0; v < LV; ++v) {
+                    const float yn = est[k * LV + v] * t.gs[l];
+                    const float y2 = yn * yn;
+                    const float w = y2 / (y2 + t.sigma2);
+                    acc = fmaf(w, w, acc);
+                    noisy[k * LV + v] = ldexpf(noisy[k * LV + v] * w, -l);
+                }
+                part[k] = acc;
+            }
+            for (int mm = 16; mm >= 1; mm >>= 1) {  // xor-butterfly reduction, as __shfl_xor does
+                float nx[32];
+                for (int k = 0; k < 32; ++k) nx[k] = part[k] + part[k ^ mm];
+                std::memcpy(part, nx, sizeof(nx));
+            }
+            weight = 1.0f / fmaxf(part[0], 1.0f);
+            ghaar_inv(noisy, kp);
+            for (int k = 0; k < kp; ++k) xf3_inv<true>(noisy + k * LV, t);
+        }
+        for (int k = 0; k < kp; ++k)
+            for (int z = 0; z < 4; ++z)
+                for (int y = 0; y < 4; ++y)
+                    for (int x = 0; x < 4; ++x) {
+                        const int v = (z * 4 + y) * 4 + x;
+                        const int64_t a = (cz[k] + z) * sz + (cy[k] + y) * sy + cx[k] + x;
+                        const float ww = weight * t.win[v];
+                        const int64_t qn = llrintf((ww * noisy[k * LV + v]) * FIX_SCALE);
+                        const int64_t qd = llrintf(ww * FIX_SCALE);
+#pragma omp atomic
+                        numq[a] += qn;
+#pragma omp atomic
+                        denq[a] += qd;
+                    }
+    }
+}
+
+// ----------------------------------------------------- matching image ------
+// Matching runs on a uint16 image: u = clamp(rint((z + shift) * scale), 0, 65535).
+//  * uint16 input: shift 0, scale 1 (the data itself).
+//  * float32 input that is uint16 counts minus one scalar (data_handling.py:
+//    353-354): shift restores the integers, scale 1 — matching is then exactly
+//    the matching on the original counts (offset invariance).
+//  * any other float32 input: a power-of-two scale puts sigma at 32..64 steps
+//    (bounded by the 16-bit range).
+struct MatchMap {
+    float shift, scale;
+    int integral;
+};
+MatchMap derive_match_map(const float *z, int64_t n, float sigma) {
+    double c = std::rint((double)z[0]) - (double)z[0];
+    double dev = 0, lo = 1e300, hi = -1e300, zlo = 1e300, zhi = -1e300;
+#pragma omp parallel for reduction(max : dev, hi, zhi) reduction(min : lo, zlo)
+    for (int64_t i = 0; i < n; ++i) {
+        double v = (double)z[i] + c, rv = std::rint(v);
+        dev = std::max(dev, std::fabs(v - rv));
+        lo = std::min(lo, rv);
+        hi = std::max(hi, rv);
+        zlo = std::min(zlo, (double)z[i]);
+        zhi = std::max(zhi, (double)z[i]);
+    }
+    MatchMap mm{};
+    if (dev <= 1.0 / 64.0 && hi - lo <= 65535.0) {
+        mm.integral = 1;
+        mm.scale = 1.0f;
+        mm.shift = (float)(c - lo + std::floor((65535.0 - (hi - lo)) * 0.5));  // centred: no clamping
+        return mm;
+    }
+    double range = std::max(zhi - zlo, 1e-30);
+    int e_range = (int)std::floor(std::log2(65535.0 / range));
+    int e_sigma = (int)std::floor(std::log2(64.0 / (double)sigma));
+    int e = std::min(e_range, e_sigma);
+    mm.integral = 0;
+    mm.scale = (float)std::ldexp(1.0, e);
+    mm.shift = (float)(-zlo + std::floor((65535.0 - range * (double)mm.scale) * 0.5) / (double)mm.scale);
+    return mm;
+}
+inline uint16_t to_match_u16(float v, const MatchMap &mm) {
+    float q = rintf((v + mm.shift) * mm.scale);
+    q = fminf(fmaxf(q, 0.0f), 65535.0f);
+    return (uint16_t)q;
+}
+
+uint64_t tau_int(float tau, float sigma, float scale) {
+    double s = (double)sigma * (double)scale;
+    return (uint64_t)std::floor((double)tau * s * s * 64.0);
+}
+
+// ----------------------------------------------------------- full pipeline --
+int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *in_f32, const Geom &g1,
+                const Geom &g2, float sigma, float *out) {
+    const b4d_profile &p = h->prof;
+    const int64_t V = (int64_t)g1.D * g1.H * g1.W;
+    std::vector<float> zf(V);
+    std::vector<uint16_t> u(V);
+    MatchMap mm{0.0f, 1.0f, 1};
+    if (in_u16) {
+        for (int64_t i = 0; i < V; ++i) {
+            zf[i] = (float)in_u16[i];
+            u[i] = in_u16[i];
+        }
+    } else {
+        mm = derive_match_map(in_f32, V, sigma);
+        for (int64_t i = 0; i < V; ++i) {
+            zf[i] = in_f32[i];
+            u[i] = to_match_u16(in_f32[i], mm);
+        }
+    }
+    Matches m;
+    match_all(u.data(), g1, p.search_ht, p.k_ht, tau_int(p.tau_ht, sigma, mm.scale), m);
+    if (h->arith == 1) {
+        std::vector<double> num(V, 0.0), den(V, 0.0), basic(V);
+        filter_f64<false>(zf.data(), nullptr, g1, m, p.search_ht, (double)sigma, p, num, den);
+        for (int64_t i = 0; i < V; ++i) basic[i] = den[i] > 0 ? num[i] / den[i] : (double)zf[i];
+        if (p.stages == 1) {
+            for (int64_t i = 0; i < V; ++i) out[i] = (float)basic[i];
+            return 0;
+        }
+        for (int64_t i = 0; i < V; ++i) u[i] = to_match_u16((float)basic[i], mm);
+        match_all(u.data(), g2, p.search_wie, p.k_wie, tau_int(p.tau_wie, sigma, mm.scale), m);
+        std::fill(num.begin(), num.end(), 0.0);
+        std::fill(den.begin(), den.end(), 0.0);
+        filter_f64<true>(zf.data(), basic.data(), g2, m, p.search_wie, (double)sigma, p, num, den);
+        for (int64_t i = 0; i < V; ++i) out[i] = (float)(den[i] > 0 ? num[i] / den[i] : basic[i]);
+        return 0;
+    }
+    const MirrorTables t = make_tables(p, sigma);
+    std::vector<int64_t> numq(V, 0), denq(V, 0);
+    std::vector<float> basic(V);
+    filter_mirror<false>(zf.data(), nullptr, g1, m, p.search_ht, t, numq, denq);
+    for (int64_t i = 0; i < V; ++i)
+        basic[i] = denq[i] > 0 ? (float)((double)numq[i] / (double)denq[i]) : zf[i];
+    if (p.stages == 1) {
+        std::memcpy(out, basic.data(), V * sizeof(float));
+        return 0;
+    }
+    for (int64_t i = 0; i < V; ++i) u[i] = to_match_u16(basic[i], mm);
+    match_all(u.data(), g2, p.search_wie, p.k_wie, tau_int(p.tau_wie, sigma, mm.scale), m);
+    std::fill(numq.begin(), numq.end(), 0);
+    std::fill(denq.begin(), denq.end(), 0);
+    filter_mirror<true>(zf.data(), basic.data(), g2, m, p.search_wie, t, numq, denq);
+    for (int64_t i = 0; i < V; ++i)
+        out[i] = denq[i] > 0 ? (float)((double)numq[i] / (double)denq[i]) : basic[i];
+    return 0;
+}
+
+int check_shape(const int64_t shape[3]) {
+    for (int i = 0; i < 3; ++i)
+        if (shape[i] < L || shape[i] > 65535)
+            return fail(B4D_ERR_INVALID, "every dimension must be in [4, 65535]");
+    return 0;
+}
+Geom whole_geom(const int64_t shape[3]) {
+    Geom g;
+    g.D = (int)shape[0];
+    g.H = (int)shape[1];
+    g.W = (int)shape[2];
+    g.rz = ref_origins(shape[0]);
+    g.ry = ref_origins(shape[1]);
+    g.rx = ref_origins(shape[2]);
+    return g;
+}
+
+}  // namespace
+
+// =============================================================== C ABI =====
+extern "C" {
+
+int b4d_version(void) { return B4D_ABI_VERSION; }
+const char *b4d_last_error(void) { return g_err.c_str(); }
+void b4d_default_profile(b4d_profile *p) { default_profile(p); }
+
+int b4d_create(int device, const b4d_profile *profile, b4d_handle **out) {
+    (void)device;
+    if (!out) return fail(B4D_ERR_INVALID, "out is NULL");
+    auto *h = new b4d_handle_impl();
+    default_profile(&h->prof);
+    h->arith = 1;
+    h->threads = 0;
+    if (profile) {
+        h->prof = *profile;
+        if (int e = check_profile(h->prof)) {
+            delete h;
+            return e;
+        }
+    }
+    *out = reinterpret_cast<b4d_handle *>(h);
+    return 0;
+}
+void b4d_destroy(b4d_handle *h) { delete reinterpret_cast<b4d_handle_impl *>(h); }
+int b4d_set_profile(b4d_handle *hh, const b4d_profile *profile) {
+    auto *h = reinterpret_cast<b4d_handle_impl *>(hh);
+    if (!h || !profile) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (int e = check_profile(*profile)) return e;
+    h->prof = *profile;
+    return 0;
+}
+// oracle-only: choose the arithmetic path (0 = float32 mirror, 1 = float64 plain)
+int b4d_oracle_set_arith(b4d_handle *hh, int arith) {
+    auto *h = reinterpret_cast<b4d_handle_impl *>(hh);
+    if (!h || (arith != 0 && arith != 1)) return fail(B4D_ERR_INVALID, "arith must be 0 or 1");
+    h->arith = arith;
+    return 0;
+}
+
+int64_t b4d_num_refs(const int64_t shape[3]) {
+    if (check_shape(shape)) return -1;
+    return whole_geom(shape).nrefs();
+}
+
+int b4d_denoise_u16(b4d_handle *hh, const uint16_t *in, int64_t n, const int64_t shape[3], float sigma,
+                    float *out, int, int) {
+    auto *h = reinterpret_cast<b4d_handle_impl *>(hh);
+    if (!h || !in || !out || n < 1) return fail(B4D_ERR_INVALID, "NULL argument or n < 1");
+    if (!(sigma > 0)) return fail(B4D_ERR_INVALID, "sigma must be positive");
+    if (int e = check_shape(shape)) return e;
+    const Geom g = whole_geom(shape);
+    const int64_t V = shape[0] * shape[1] * shape[2];
+    for (int64_t i = 0; i < n; ++i)
+        if (int e = denoise_one(h, in + i * V, nullptr, g, g, sigma, out + i * V)) return e;
+    return 0;
+}
+int b4d_denoise_f32(b4d_handle *hh, const float *in, int64_t n, const int64_t shape[3], float sigma,
+                    float *out, int, int) {
+    auto *h = reinterpret_cast<b4d_handle_impl *>(hh);
+    if (!h || !in || !out || n < 1) return fail(B4D_ERR_INVALID, "NULL argument or n < 1");
+    if (!(sigma > 0)) return fail(B4D_ERR_INVALID, "sigma must be positive");
+    if (int e = check_shape(shape)) return e;
+    const Geom g = whole_geom(shape);
+    const int64_t V = shape[0] * shape[1] * shape[2];
+    for (int64_t i = 0; i < n; ++i)
+        if (int e = denoise_one(h, nullptr, in + i * V, g, g, sigma, out + i * V)) return e;
+    return 0;
+}
+
+int b4d_denoise_slab_u16(b4d_handle *hh, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
+                         int64_t z_total, int64_t own_begin, int64_t own_end, float sigma, float *out,
+                         int, int) {
+    auto *h = reinterpret_cast<b4d_handle_impl *>(hh);
+    if (!h || !in || !out) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!(sigma > 0)) return fail(B4D_ERR_INVALID, "sigma must be positive");
+    if (int e = check_shape(shape)) return e;
+    if (z_begin < 0 || z_begin + shape[0] > z_total || own_begin < z_begin || own_end > z_begin + shape[0] ||
+        own_begin >= own_end)
+        return fail(B4D_ERR_INVALID, "slab / owned range inconsistent");
+    Geom g1 = whole_geom(shape), g2 = g1;
+    g1.rz = slab_origins(z_total, z_begin, shape[0], h->prof.search_ht / 2);
+    g2.rz = slab_origins(z_total, z_begin, shape[0], h->prof.search_wie / 2);
+    const int64_t V = shape[0] * shape[1] * shape[2], P = shape[1] * shape[2];
+    std::vector<float> full(V);
+    if (int e = denoise_one(h, in, nullptr, g1, g2, sigma, full.data())) return e;
+    std::memcpy(out, full.data() + (own_begin - z_begin) * P, (own_end - own_begin) * P * sizeof(float));
+    return 0;
+}
+
+int b4d_match_stage1(b4d_handle *hh, const uint16_t *in, const int64_t shape[3], float sigma, int32_t *idx,
+                     uint64_t *ssd, int32_t *count) {
+    auto *h = reinterpret_cast<b4d_handle_impl *>(hh);
+    if (!h || !in || !idx || !ssd || !count) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (int e = check_shape(shape)) return e;
+    const Geom g = whole_geom(shape);
+    const int64_t Hc = g.H - L + 1, Wc = g.W - L + 1, Dc = g.D - L + 1;
+    if (Dc * Hc * Wc > INT32_MAX) return fail(B4D_ERR_TOO_LARGE, "candidate index space exceeds int32");
+    const b4d_profile &p = h->prof;
+    Matches m;
+    match_all(in, g, p.search_ht, p.k_ht, tau_int(p.tau_ht, sigma, 1.0f), m);
+    const int Ns = p.search_ht, r = Ns / 2, K = p.k_ht;
+    const int nry = (int)g.ry.size(), nrx = (int)g.rx.size();
+    const int64_t R = g.nrefs();
+    for (int64_t ri = 0; ri < R; ++ri) {
+        const int oz = g.rz[ri / ((int64_t)nry * nrx)], oy = g.ry[(ri / nrx) % nry], ox = g.rx[ri % nrx];
+        count[ri] = m.cnt[ri];
+        for (int k = 0; k < K; ++k) {
+            if (k < m.cnt[ri]) {
+                int cz, cy, cx;
+                widx_to_origin(m.widx[ri * K + k], Ns, r, oz, oy, ox, cz, cy, cx);
+                idx[ri * K + k] = (int32_t)(((int64_t)cz * Hc + cy) * Wc + cx);
+                ssd[ri * K + k] = m.ssd[ri * K + k];
+            } else {
+                idx[ri * K + k] = -1;
+                ssd[ri * K + k] = UINT64_MAX;
+            }
+        }
+    }
+    return 0;
+}
+
+// K7 restated in C (float32, clip before round, half-to-even): transforms.py:403-411.
+int b4d_quantize_u16(b4d_handle *, const float *in, int64_t n, float offset_sub, float offset_add, float step,
+                     uint16_t *out, int, int) {
+    if (!in || !out || n < 0) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!(step >= 1.0f)) return fail(B4D_ERR_INVALID, "step must be >= 1");
+    const float hi = 65535.0f / step;
+    for (int64_t i = 0; i < n; ++i) {
+        float v = (in[i] - offset_sub) + offset_add;
+        if (step != 1.0f) v = v / step;
+        v = fminf(fmaxf(v, 0.0f), hi);
+        out[i] = (uint16_t)rintf(v);
+    }
+    return 0;
+}
+
+int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *, int64_t *, int) {
+    return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
+}
+int b4d_last_timings(b4d_handle *, float *, int64_t *) {
+    return fail(B4D_ERR_UNSUPPORTED, "no device timings in the oracle");
+}
+int b4d_measure_pipe_peaks(b4d_handle *, double *) {
+    return fail(B4D_ERR_UNSUPPORTED, "no device in the oracle");
+}
+
+}  // extern "C"
