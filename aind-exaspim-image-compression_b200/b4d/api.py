@@ -186,8 +186,9 @@ class Denoiser:
         self.denoise_ptr(zc.ctypes.data, zc.dtype.type, n, zc.shape[-3:], sigma, out.ctypes.data, 0, 0)
         return out
 
-    def denoise_slab(self, slab, z_begin, z_total, own_begin, own_end, sigma):
-        """One z-slab (uint16, with halos) of a larger volume -> float32 owned planes."""
+    def denoise_slab(self, slab, z_begin, z_total, own_begin, own_end, sigma, out=None):
+        """One z-slab (uint16, with halos) of a larger volume -> float32 owned planes.
+        `out` (NumPy path only) receives the result in place, e.g. a pinned buffer."""
         if _is_torch(slab):
             import torch
 
@@ -203,7 +204,11 @@ class Denoiser:
             sc = np.ascontiguousarray(slab)
             if sc.dtype != np.uint16 or sc.ndim != 3:
                 raise ValueError("slab must be a 3-D uint16 array")
-            out = np.empty((own_end - own_begin,) + sc.shape[1:], dtype=np.float32)
+            oshape = (own_end - own_begin,) + sc.shape[1:]
+            if out is None:
+                out = np.empty(oshape, dtype=np.float32)
+            elif out.shape != oshape or out.dtype != np.float32 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float32 array of shape %r" % (oshape,))
             on_dev = False
             in_ptr, out_ptr, shape = sc.ctypes.data, out.ctypes.data, sc.shape
         _lib.check(

@@ -398,6 +398,24 @@ int derive_match_map(b4d_handle *h, const float *d_in, long long n, float sigma,
     return 0;
 }
 
+// uint16 input: float copy + the centring shift of the stage-2 matching image
+// (stage 1 matches on the raw integers; mirrors oracle denoise_one).
+int convert_u16(b4d_handle *h, const uint16_t *d_in, float *d_zf, long long n, MatchMap *mm) {
+    cudaStream_t s = h->stream;
+    B4D_TRY(h->sink.ensure(64));
+    const unsigned init[2] = {0xFFFFu, 0u};
+    CU_TRY(cudaMemcpyAsync(h->sink.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    b4d_launch_u16_to_f32(d_in, d_zf, n, h->sink.as<unsigned>(), s);
+    unsigned got[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(got, h->sink.p, sizeof(got), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    const double lo = got[0], hi = got[1];
+    mm->integral = 1;
+    mm->scale = 1.0f;
+    mm->shift = (float)(std::floor((65535.0 - (hi - lo)) * 0.5) - lo);
+    return 0;
+}
+
 int common_checks(b4d_handle *h, const void *in, const void *out, const int64_t shape[3], float sigma) {
     if (!h || !in || !out || !shape) return fail(B4D_ERR_INVALID, "NULL argument");
     if (!(sigma > 0) || !std::isfinite(sigma)) return fail(B4D_ERR_INVALID, "sigma must be positive and finite");
@@ -453,7 +471,7 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
         clk.mark(-1, 0);
         if (sizeof(T) == 2) {
             B4D_TRY(h->zf.ensure((size_t)TV * sizeof(float)));
-            b4d_launch_u16_to_f32(h->in.as<uint16_t>(), h->zf.as<float>(), TV, s);
+            B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), TV, &mm));
             d_zf = h->zf.as<float>();
             d_u = h->in.as<uint16_t>();  // the staged copy doubles as the matching image
         } else {
@@ -576,9 +594,9 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
     CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)V * sizeof(uint16_t),
                            in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     clk.mark(-1, 0);
-    b4d_launch_u16_to_f32(h->in.as<uint16_t>(), h->zf.as<float>(), V, s);
-    clk.mark(B4D_T_PREP, 1);
     MatchMap mm;
+    B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), V, &mm));
+    clk.mark(B4D_T_PREP, 1);
     B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk));
     CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - z_begin) * P,
                            (size_t)(own_end - own_begin) * P * sizeof(float),

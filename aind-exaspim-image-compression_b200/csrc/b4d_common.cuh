@@ -60,7 +60,7 @@ void b4d_launch_filter(const FilterParams &p, bool wiener, bool deterministic, c
 void b4d_upload_tables(const B4dTables &t, cudaStream_t s);
 
 // misc kernels (b4d_misc.cu)
-void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, cudaStream_t s);
+void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, unsigned *minmax, cudaStream_t s);
 void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float shift, float scale, cudaStream_t s);
 void b4d_launch_normalise(const float2 *acc, const float *fallback, float *out, long long n, cudaStream_t s);
 void b4d_launch_normalise_det(const long long *numq, const long long *denq, const float *fallback, float *out,

@@ -26,26 +26,46 @@ unsigned grid_for(long long nvec, int threads, int per_sm) {
 }
 
 // ------------------------------------------------------------ u16 -> f32 ----
+// Also reduces min / max of the tile (minmax[0] = min, minmax[1] = max): the
+// stage-2 matching image is centred in the uint16 range with them.
 __global__ void __launch_bounds__(256) k_u16_to_f32(const uint16_t *__restrict__ in, float *__restrict__ out,
-                                                    long long n) {
+                                                    long long n, unsigned *__restrict__ minmax) {
     const long long nv = n >> 3;  // 8 voxels: 16 B in, 32 B out
     const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned mn = 0xFFFFu, mx = 0u;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
         const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(in) + i);
+        const unsigned e[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
+                               v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            mn = min(mn, e[k]);
+            mx = max(mx, e[k]);
+        }
         float4 a, b;
-        a.x = (float)(v.x & 0xFFFFu);
-        a.y = (float)(v.x >> 16);
-        a.z = (float)(v.y & 0xFFFFu);
-        a.w = (float)(v.y >> 16);
-        b.x = (float)(v.z & 0xFFFFu);
-        b.y = (float)(v.z >> 16);
-        b.z = (float)(v.w & 0xFFFFu);
-        b.w = (float)(v.w >> 16);
+        a.x = (float)e[0];
+        a.y = (float)e[1];
+        a.z = (float)e[2];
+        a.w = (float)e[3];
+        b.x = (float)e[4];
+        b.y = (float)e[5];
+        b.z = (float)e[6];
+        b.w = (float)e[7];
         reinterpret_cast<float4 *>(out)[2 * i] = a;
         reinterpret_cast<float4 *>(out)[2 * i + 1] = b;
     }
-    for (long long i = (nv << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = (float)in[i];
+    for (long long i = (nv << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned e = in[i];
+        mn = min(mn, e);
+        mx = max(mx, e);
+        out[i] = (float)e;
+    }
+    mn = __reduce_min_sync(B4D_FULL, mn);
+    mx = __reduce_max_sync(B4D_FULL, mx);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&minmax[0], mn);
+        atomicMax(&minmax[1], mx);
+    }
 }
 
 // ---------------------------------------------- f32 -> matching image (u16) --
@@ -253,8 +273,8 @@ __global__ void __launch_bounds__(1024) k_pipe(int iters, unsigned *sink) {
 
 }  // namespace
 
-void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, cudaStream_t s) {
-    k_u16_to_f32<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n);
+void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, unsigned *minmax, cudaStream_t s) {
+    k_u16_to_f32<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, minmax);
 }
 void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float shift, float scale, cudaStream_t s) {
     k_to_match<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, shift, scale);

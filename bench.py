@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — BM4D denoise voxels/s on a synthetic uint16 1024^3 ExaSPIM-like
+volume, z-slab sharded over N B200s (BASELINE.json metric, configs[3]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S]
+
+One step = one full two-stage BM4D denoise (hard threshold + Wiener) of the
+whole volume: every rank denoises its z-slab (+ halos on the global grid, no
+volume data crosses GPUs), after the path's only collective — the all-gather of
+per-slab uint16 histograms for the global offset / sigma statistics.
+
+  value   voxels/s with the slab already resident in HBM (device in, device out)
+  e2e     voxels/s through the public API with HOST buffers (pinned): H2D of the
+          slab and D2H of the owned planes inside the timed region
+  roofline  the matching kernel (dominant): algorithmic integer ops
+          2*Ns^3*L^3*R per launch / its CUDA-event duration, against the
+          (sub, mad) issue-rate peak measured live by the shipped microbenchmark
+  cpu_baseline  the CPU oracle (float32 path, OpenMP, all host cores) on a
+          bounded sub-volume of the same data — "port", not the closed bm4d wheel
+
+--impl reference times the reference arm: the reference's BM4D is the closed
+third-party wheel bm4d==4.2.5 (absent from this image and un-installable, no
+network), so the arm runs this repo's CPU restatement (oracle/) — labelled as such.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "aind-exaspim-image-compression_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+SIGMA = 24.0  # scripts/precompute.py:284
+SEED = 4
+NS, LBLK, K_HT, K_WIE = 11, 4, 16, 32
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------- data ------
+def make_slab_device(size, zb, ze, device):
+    """uint16 planes [zb, ze) of the seeded size^3 volume, generated on the GPU:
+    the clean 128^3 tile of b4d.synth repeated periodically + white Gaussian
+    noise (sigma 24) seeded per 128-plane chunk, so any rank can regenerate any
+    plane without materialising the whole volume."""
+    import torch
+
+    from b4d import synth
+
+    clean = torch.from_numpy(synth.clean_tile(SEED)).to(device)  # (128,128,128) float32
+    T = clean.shape[0]
+    reps = (size + T - 1) // T
+    plane_tile = clean.repeat(1, reps, reps)[:, :size, :size]  # (128, size, size)
+    out = torch.empty((ze - zb, size, size), dtype=torch.uint16, device=device)
+    for c in range(zb // T, (ze - 1) // T + 1):
+        a, b = max(zb, c * T), min(ze, (c + 1) * T)
+        g = torch.Generator(device=device)
+        g.manual_seed(SEED * 1000003 + c)
+        noise = torch.randn((T, size, size), generator=g, device=device, dtype=torch.float32) * SIGMA
+        v = (plane_tile + noise)[a - c * T : b - c * T]
+        out[a - zb : b - zb] = torch.clamp(torch.round(v), 0, 65535).to(torch.int32).to(torch.uint16)
+        del noise, v
+    return out
+
+
+def make_sample_host(shape):
+    from b4d import synth
+
+    return synth.vol(shape[0], shape[1], shape[2], seed=SEED, sigma=SIGMA)
+
+
+# --------------------------------------------------------------- clocks ------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------- reference -----
+def probe_real_bm4d():
+    """Version of an importable closed `bm4d` wheel (plain, then baseline/_ref), or
+    None.  This repo's own import-name shim does not count."""
+    saved = list(sys.path)
+    try:
+        sys.path[:] = [p for p in saved if "aind-exaspim-image-compression_b200" not in p]
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        sys.modules.pop("bm4d", None)
+        import bm4d as real
+
+        v = getattr(real, "__version__", "?")
+        return None if "b4d" in str(v) else str(v)
+    except Exception:
+        return None
+    finally:
+        sys.modules.pop("bm4d", None)
+        sys.path[:] = saved
+
+
+def workload_config(S, halo):
+    return {
+        "workload": "BM4D HT+Wiener denoise of one uint16 %d^3 volume (BASELINE configs[3]), z-slabs + halo %d" % (S, halo),
+        "sigma": SIGMA, "Ns": NS, "K_ht": K_HT, "K_wiener": K_WIE,
+    }
+
+
+def cpu_port_throughput(sample_shape, repeats=1):
+    """voxels/s of the CPU oracle (float32 path, OpenMP over all host cores)."""
+    from oracle import np_oracle
+
+    vol = make_sample_host(sample_shape)
+    o = np_oracle.Oracle("mirror")
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        o.denoise(vol, SIGMA)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return vol.size / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    shape = (96, 128, 128)
+    cores = os.cpu_count() or 1
+    real = probe_real_bm4d()
+    from oracle import np_oracle
+
+    vol = make_sample_host(shape)
+    o = np_oracle.Oracle("mirror")
+    for _ in range(args.warmup):
+        o.denoise(vol, SIGMA)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        o.denoise(vol, SIGMA)
+    dt = (time.perf_counter() - t) / args.steps
+    val = vol.size / dt
+    sample = "%dx%dx%d sub-volume of the seeded 1024^3 volume per step (CPU restatement oracle/, float32 path, OpenMP)" % shape
+    line = {
+        "impl": "reference",
+        "metric": "bm4d_denoise_voxels_per_s",
+        "value": val,
+        "unit": "voxels/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt * 1e3,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": dict(workload_config(args.size, 2 * (NS - 1 + LBLK - 1)), sample=sample),
+        "cpu_baseline": {"value": val, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference bm4d==4.2.5 (closed wheel) absent -> parity vs closed binary NOT measured; "
+        "this arm times the repo's CPU restatement" + ("" if real is None else " (an importable bm4d %s was found but is not used here)" % real),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------ main -----
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b4d", choices=["b4d", "reference"])
+    ap.add_argument("--size", type=int, default=1024, help="volume side (default 1024: the metric's config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import b4d
+    from b4d.sharding import halo_planes, merge_histograms, slab_plan, stats_from_hist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        log("bench.py: --gpus %d needs torchrun with WORLD_SIZE=%d (got %d)" % (args.gpus, args.gpus, world))
+        return 2
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.size
+    halo = halo_planes(NS, NS, 2)
+    own_b, own_e, zb, ze = slab_plan(S, world, rank, halo)
+    dn = b4d.Denoiser(local)
+    t0 = time.perf_counter()
+    slab_dev = make_slab_device(S, zb, ze, dev)
+    torch.cuda.synchronize()
+    slab_pin = torch.empty(slab_dev.shape, dtype=torch.uint16, pin_memory=True)
+    slab_pin.copy_(slab_dev)
+    out_pin = torch.empty((own_e - own_b, S, S), dtype=torch.float32, pin_memory=True)
+    torch.cuda.synchronize()
+    if rank == 0:
+        log("data: slab %s generated in %.1fs" % (tuple(slab_dev.shape), time.perf_counter() - t0))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def stats_step():
+        # the path's only collective: all-gather of per-slab histograms
+        st, hist = dn.tile_stats(slab_dev[own_b - zb : own_e - zb], 0.1, return_hist=True)
+        if world > 1:
+            total = merge_histograms(torch.from_numpy(hist).to(dev))
+            return stats_from_hist(total.cpu().numpy(), 0.1)
+        return st
+
+    def step_resident():
+        st = stats_step()
+        y = dn.denoise_slab(slab_dev, zb, S, own_b, own_e, SIGMA)
+        return st, y
+
+    def step_e2e():
+        # host in -> host out through the public API; H2D and D2H happen inside the call
+        dn.denoise_slab(slab_pin.numpy(), zb, S, own_b, own_e, SIGMA, out=out_pin.numpy())
+
+    # ---- warm-up (also sizes the scratch buffers)
+    stats = None
+    for _ in range(max(args.warmup, 3)):
+        stats, y = step_resident()
+        del y
+    barrier()
+
+    # ---- timed: resident inputs
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    fam = {}
+    launches = 0
+    barrier()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        stats, y = step_resident()
+        del y
+        tm = dn.last_timings()
+        for k, (ms, nl) in tm.items():
+            fam[k] = fam.get(k, 0.0) + ms
+            launches += nl
+        launches += 1  # histogram kernel
+    barrier()
+    dt = time.perf_counter() - t
+    clocks = sampler.stop() if rank == 0 else None
+    mstats = dn.last_match_stats()
+
+    # ---- timed: end to end with host buffers
+    step_e2e()
+    barrier()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    dt_e2e = time.perf_counter() - t
+
+    times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dt, dt_e2e = float(times[0]), float(times[1])
+    h2d = torch.tensor([slab_pin.numel() * 2, out_pin.numel() * 4, launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        V = float(S) ** 3
+        # reference blocks this rank processed per stage (slab grid), for the roofline
+        from b4d.api import _lib as L
+
+        peaks = dn.measure_pipe_peaks()
+        r_slab = dn.lib.b4d_num_refs(L.shape3((ze - zb, S, S)))
+        ops_per_launch = 2.0 * NS ** 3 * LBLK ** 3 * r_slab  # upper bound: slab-edge refs are skipped
+        t_match = (fam.get("match1", 0.0) + fam.get("match2", 0.0)) / (2.0 * args.steps) * 1e-3
+        achieved = ops_per_launch / t_match if t_match > 0 else 0.0
+        hbm_peak = 6553.9
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        t_norm = (fam.get("norm1", 0.0) + fam.get("norm2", 0.0)) / (2.0 * args.steps) * 1e-3
+        slab_vox = float(ze - zb) * S * S
+        kernels = {
+            "match": {"bound": "int32", "achieved": achieved / 1e12, "peak": peaks["sub_mad"] / 1e12, "unit": "TOP/s",
+                      "frac": achieved / peaks["sub_mad"] if peaks["sub_mad"] else None,
+                      "ms_per_launch": t_match * 1e3},
+            "normalise": {"bound": "hbm", "achieved": 12.0 * slab_vox / t_norm / 1e9 if t_norm > 0 else None,
+                          "peak": hbm_peak, "unit": "GB/s",
+                          "frac": 12.0 * slab_vox / t_norm / 1e9 / hbm_peak if t_norm > 0 else None,
+                          "ms_per_launch": t_norm * 1e3},
+            "filter_ht_ms": fam.get("filter1", 0.0) / args.steps,
+            "filter_wiener_ms": fam.get("filter2", 0.0) / args.steps,
+        }
+        line = {
+            "metric": "bm4d_denoise_voxels_per_s",
+            "value": V * args.steps / dt,
+            "unit": "voxels/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "int32 matching + f32 filtering",
+            "data": "synthetic",
+            "config": dict(
+                workload_config(S, halo),
+                l2="inputs larger than L2 (%.2f GiB slab per rank)" % (slab_pin.numel() * 2 / 2 ** 30),
+                timing="wall clock around synchronous C-ABI calls between cuda synchronize + barrier, max over ranks",
+            ),
+            "e2e": {"value": V * args.steps / dt_e2e, "unit": "voxels/s",
+                    "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1])},
+            "gpu_launches": int(h2d[2]),
+            "clocks": clocks,
+            "roofline": {"bound": "int32", "achieved": achieved / 1e12, "peak": peaks["sub_mad"] / 1e12,
+                         "unit": "TOP/s", "frac": achieved / peaks["sub_mad"] if peaks["sub_mad"] else None,
+                         "traffic": None,
+                         "kernel": "k_match<11> (stage-1 and stage-2 launches averaged)",
+                         "peak_source": "shipped microbenchmark, dependent (sub, mad) pairs, measured in this run"},
+            "roofline_kernels": kernels,
+            "device_ms_per_step": {k: v / args.steps for k, v in fam.items()},
+            "pipe_peaks_ops_per_s": peaks,
+            "match_stats": mstats,
+            "tile_stats": stats,
+        }
+        if not args.no_cpu_baseline:
+            shape = (96, 128, 128)
+            v, secs = cpu_port_throughput(shape)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "voxels/s", "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": "%dx%dx%d sub-volume of the same seeded volume, one pass (%.1f s); CPU restatement, not the closed bm4d binary" % (shape + (secs,)),
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

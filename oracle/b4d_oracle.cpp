@@ -636,10 +636,16 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     std::vector<uint16_t> u(V);
     MatchMap mm{0.0f, 1.0f, 1};
     if (in_u16) {
+        // stage 1 matches on the raw integers; the stage-2 matching image is the
+        // basic estimate centred in the uint16 range so that it is never clamped
+        double lo = 65535.0, hi = 0.0;
         for (int64_t i = 0; i < V; ++i) {
             zf[i] = (float)in_u16[i];
             u[i] = in_u16[i];
+            lo = std::min(lo, (double)in_u16[i]);
+            hi = std::max(hi, (double)in_u16[i]);
         }
+        mm.shift = (float)(std::floor((65535.0 - (hi - lo)) * 0.5) - lo);
     } else {
         mm = derive_match_map(in_f32, V, sigma);
         for (int64_t i = 0; i < V; ++i) {

@@ -1,0 +1,250 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, on B200.
+
+Bars (BASELINE.json north_star / DESIGN.md §5):
+  * stage-1 match lists: bit-exact (idx, ssd, count);
+  * denoised output, deterministic aggregation: BIT-EXACT vs the oracle's float32
+    mirror (same discrete decisions, same rounding);
+  * denoised output, fast (float-atomic) aggregation: max-abs <= 0.5 and
+    rel-L2 <= 1e-3 vs the mirror; rel-L2 <= 1e-3 vs the plain float64 oracle
+    (block matching is discontinuous, so a float64 pipeline may flip a handful
+    of near-tied matches; max-abs vs float64 is bounded at 0.5 for >= 99.99 %
+    of voxels and reported);
+  * quantize, statistics: bit-exact.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 0.5
+REL_L2 = 1e-3
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def b4d_mod():
+    import b4d
+
+    return b4d
+
+
+@pytest.fixture(scope="module")
+def dn(b4d_mod):
+    d = b4d_mod.Denoiser(0)
+    yield d
+    d.close()
+
+
+def _volumes():
+    from b4d import synth
+
+    rng = np.random.default_rng(0)
+    return {
+        "synth_ragged": synth.vol(21, 26, 31, seed=3),
+        "synth_40": synth.vol(40, 40, 40, seed=5),
+        "noise": np.clip(rng.normal(100, 24, (16, 17, 18)), 0, 65535).astype(np.uint16),
+        "constant": np.full((12, 12, 12), 77, np.uint16),
+        "single_block": np.clip(rng.normal(100, 24, (4, 4, 4)), 0, 65535).astype(np.uint16),
+        "thin": synth.vol(4, 9, 33, seed=8),
+        "bright_wide_range": (rng.integers(0, 2, (20, 20, 20)) * 60000 + rng.integers(0, 50, (20, 20, 20))).astype(
+            np.uint16
+        ),
+        "ramp": (np.arange(18 * 18 * 18).reshape(18, 18, 18) % 4096).astype(np.uint16),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_volumes()))
+def test_stage1_match_lists_bit_exact(name, dn, oracle_lib):
+    vol = _volumes()[name]
+    for sigma in (24.0, 10.0):
+        gi, gs, gc = dn.match_stage1(vol, sigma)
+        oi, os_, oc = oracle_lib.Oracle("f64").match_stage1(vol, sigma)
+        assert np.array_equal(gc, oc)
+        assert np.array_equal(gi, oi)
+        assert np.array_equal(gs, os_)
+
+
+def test_stage1_match_lists_config3_slice(dn, oracle_lib):
+    """BASELINE config 3 is a 256^3 tile; the oracle finishes a 96^3 sub-tile of the
+    same seeded volume in seconds — same code path, R = 29 791 reference blocks."""
+    from b4d import synth
+
+    vol = synth.vol(96, 96, 96, seed=3)
+    gi, gs, gc = dn.match_stage1(vol, 24.0)
+    oi, os_, oc = oracle_lib.Oracle("f64").match_stage1(vol, 24.0)
+    assert gi.shape == (31 ** 3, 16)
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi) and np.array_equal(gs, os_)
+
+
+@pytest.mark.parametrize("ns,k", [(7, 8), (15, 16), (5, 4), (13, 32)])
+def test_stage1_other_windows(ns, k, b4d_mod, oracle_lib):
+    from b4d import synth
+
+    vol = synth.vol(24, 23, 22, seed=4)
+    d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(search_window_ht=(ns // 2,) * 3, max_stack_size_ht=k))
+    gi, gs, gc = d.match_stage1(vol, 24.0)
+    oi, os_, oc = oracle_lib.Oracle("f64", search_ht=ns, k_ht=k).match_stage1(vol, 24.0)
+    d.close()
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi) and np.array_equal(gs, os_)
+
+
+@pytest.mark.parametrize("name", ["synth_ragged", "synth_40", "noise", "constant", "single_block", "thin", "bright_wide_range"])
+def test_deterministic_mode_bit_exact_vs_mirror(name, b4d_mod, oracle_lib):
+    vol = _volumes()[name]
+    d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(deterministic=True))
+    for stages in (1, 2):
+        d.set_profile(b4d_mod.BM4DProfile(deterministic=True), stages)
+        y = d.denoise(vol, 24.0)
+        m = oracle_lib.Oracle("mirror", stages=stages).denoise(vol, 24.0)
+        assert y.dtype == np.float32 and y.shape == vol.shape
+        assert np.array_equal(y, m), "stage %d: max-abs %g" % (stages, np.abs(y - m).max())
+    d.close()
+
+
+def test_deterministic_f32_offset_input_bit_exact(b4d_mod, oracle_lib):
+    """The precompute path: raw = uint16 -> float32 - offset (data_handling.py:353-354)."""
+    vol = _volumes()["synth_40"]
+    d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(deterministic=True))
+    for off in (37.0, 36.37):
+        raw = vol.astype(np.float32) - np.float32(off)
+        assert np.array_equal(d.denoise(raw, 24.0), oracle_lib.Oracle("mirror").denoise(raw, 24.0))
+    # non-integral float data takes the quantised-matching path on both sides
+    rng = np.random.default_rng(1)
+    z = rng.normal(0.4, 0.05, (14, 15, 16)).astype(np.float32)
+    assert np.array_equal(d.denoise(z, 0.05), oracle_lib.Oracle("mirror").denoise(z, 0.05))
+    d.close()
+
+
+def test_fast_mode_within_tolerance(dn, oracle_lib):
+    from b4d import synth
+
+    vol = synth.vol(64, 64, 64, seed=1)  # BASELINE config 1 input
+    raw = vol.astype(np.float32) - np.float32(37.0)
+    for z in (vol, raw):
+        y = dn.denoise(z, 24.0)
+        m = oracle_lib.Oracle("mirror").denoise(z, 24.0)
+        f = oracle_lib.Oracle("f64").denoise(z, 24.0)
+        assert np.abs(y - m).max() <= MAX_ABS and rel_l2(y, m) <= REL_L2
+        assert rel_l2(y, f) <= REL_L2
+        frac_bad = float((np.abs(y - f) > MAX_ABS).mean())
+        print("fast vs f64: max-abs %.4f, frac > 0.5: %.2e" % (np.abs(y - f).max(), frac_bad))
+        assert frac_bad <= 1e-4
+    # evaluator surface (evaluate.py:201-202): non-contiguous uint16 view, sigma 10
+    view = vol[5:-5, 5:-5, 5:-5]
+    import b4d
+
+    y = np.maximum(b4d.bm4d(view, 10), 0).astype(int)
+    m = np.maximum(oracle_lib.Oracle("mirror").denoise(np.ascontiguousarray(view), 10.0), 0).astype(int)
+    assert y.shape == (54, 54, 54) and (np.abs(y - m) <= 1).all() and (y != m).mean() < 1e-3
+
+
+def test_batch_equals_per_patch_and_precompute_targets(b4d_mod, oracle_lib):
+    from b4d import synth
+
+    d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(deterministic=True))
+    batch = np.stack([synth.vol(20, 22, 24, seed=s) for s in (1, 2, 3)])
+    yb = d.denoise(batch, 24.0)
+    for i in range(3):
+        assert np.array_equal(yb[i], d.denoise(batch[i], 24.0))
+        assert np.array_equal(yb[i], oracle_lib.Oracle("mirror").denoise(batch[i], 24.0))
+    d.close()
+    raw, teacher = b4d_mod.precompute_targets(batch, [37.0, 37.0, 12.5], 24.0)
+    assert raw.dtype == np.float32 and teacher.dtype == np.float32  # scripts/precompute.py:204-213
+    assert teacher.min() >= 0.0 and teacher.max() <= 65535.0
+    want = np.clip(oracle_lib.Oracle("mirror").denoise(oracle_lib.read_counts(batch[2], 12.5), 24.0), 0, 65535)
+    assert np.abs(teacher[2] - want).max() <= MAX_ABS
+
+
+def test_slabs_equal_whole_on_device(b4d_mod):
+    """Shard == whole, bit for bit, in deterministic mode."""
+    from b4d import synth
+    from b4d.sharding import halo_planes, slab_plan
+
+    vol = synth.vol(96, 24, 28, seed=9)
+    d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(deterministic=True))
+    whole = d.denoise(vol, 24.0)
+    halo = halo_planes(11, 11, 2)
+    for world in (2, 3):
+        parts = []
+        for rank in range(world):
+            ob, oe, zb, ze = slab_plan(96, world, rank, halo)
+            parts.append(d.denoise_slab(vol[zb:ze], zb, 96, ob, oe, 24.0))
+        assert np.array_equal(np.concatenate(parts, 0), whole)
+    d.close()
+
+
+def test_torch_device_tensors_in_out(dn, oracle_lib):
+    import torch
+
+    from b4d import synth
+
+    vol = synth.vol(24, 24, 24, seed=2)
+    t = torch.from_numpy(vol).cuda()
+    y = dn.denoise(t, 24.0)
+    assert y.is_cuda and y.dtype == torch.float32 and tuple(y.shape) == vol.shape
+    assert np.abs(y.cpu().numpy() - oracle_lib.Oracle("mirror").denoise(vol, 24.0)).max() <= MAX_ABS
+    q = dn.quantize(y)
+    assert q.is_cuda and q.dtype == torch.uint16
+    assert np.array_equal(q.cpu().numpy(), oracle_lib.quantize_reference(y.cpu().numpy()))
+
+
+def test_quantize_bit_exact(dn, oracle_lib):
+    gold = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "reference_vectors.npz"))
+    x = gold["quant_x"]
+    for i, off in enumerate(gold["quant_offsets"]):
+        assert np.array_equal(dn.quantize(x, 0.0, float(off), 1.0), gold["quant_q%d" % i])  # reference output
+    rng = np.random.default_rng(2)
+    x = rng.normal(500, 700, 1_000_003).astype(np.float32)
+    assert np.array_equal(dn.quantize(x), oracle_lib.quantize_reference(x))
+    for osub, oadd, step in ((3.5, 37.0, 2.5), (0.0, 0.0, 12.0), (36.37, 0.0, 1.0), (0.0, 37.0, 17.79)):
+        assert np.array_equal(dn.quantize(x, osub, oadd, step), oracle_lib.quantize_noise_scaled(x, osub, oadd, step))
+    assert dn.quantize(np.zeros(0, np.float32)).size == 0
+    with pytest.raises(ValueError):
+        dn.quantize(x, step=0.5)
+
+
+def test_tile_stats_exact(dn, oracle_lib):
+    from b4d import synth
+    from b4d.sharding import stats_from_hist
+
+    gold = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "reference_vectors.npz"))
+    data, pos = gold["offset_data"], 0
+    for n, p, want in zip(gold["offset_n"], gold["offset_pct"], gold["offset_val"]):
+        s = data[pos : pos + n]
+        pos += n
+        assert dn.tile_stats(s, float(p))["offset"] == want  # reference estimate_offset output
+    vol = synth.vol(64, 64, 64, seed=1)
+    st, hist = dn.tile_stats(vol, 0.1, return_hist=True)
+    assert np.array_equal(hist, np.bincount(vol.reshape(-1), minlength=65536))
+    med, mad, sigma = oracle_lib.robust_sigma(vol)
+    assert (st["median"], st["mad"], st["sigma"]) == (med, mad, sigma)
+    assert st["offset"] == oracle_lib.estimate_offset(vol, 0.1)
+    assert st == stats_from_hist(hist, 0.1)
+
+
+def test_errors(dn, b4d_mod):
+    with pytest.raises(ValueError):
+        dn.denoise(np.zeros((3, 8, 8), np.uint16), 24.0)
+    with pytest.raises(ValueError):
+        dn.denoise(np.zeros((8, 8, 8), np.uint16), -1.0)
+    with pytest.raises(NotImplementedError):
+        dn.denoise(np.zeros((8, 8, 8), np.uint16), 500.0)  # tau*sigma^2*64 exceeds the 32-bit key
+    with pytest.raises(ValueError):
+        b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(max_stack_size_ht=12))
+
+
+def test_full_size_properties_128(dn):
+    """BASELINE config 2's patch size (128^3): properties that need no oracle —
+    constant volume is a fixed point, output finite, noise reduced."""
+    from b4d import synth
+
+    vol = synth.vol(128, 128, 128, seed=1000)
+    clean = synth.clean_vol(128, 128, 128, 1000)
+    y = dn.denoise(vol, 24.0)
+    assert np.isfinite(y).all()
+    assert np.sqrt(np.mean((y - clean) ** 2)) < 0.25 * np.sqrt(np.mean((vol - clean) ** 2))
+    c = np.full((128, 128, 128), 4321, np.uint16)
+    assert np.abs(dn.denoise(c, 24.0) - 4321.0).max() < 1e-2

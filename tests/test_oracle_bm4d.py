@@ -1,0 +1,126 @@
+"""Known-answer and self-consistency tests of the BM4D restatement
+(oracle/b4d_oracle.cpp).  Sized to run in well under a minute on CPU."""
+import numpy as np
+import pytest
+
+from b4d import synth
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def vol24():
+    return synth.vol(22, 25, 27, seed=7)
+
+
+def test_ref_origins_rule(oracle_lib):
+    assert oracle_lib.ref_origins(64) == list(range(0, 61, 3))  # 21 origins, 60 = N - 4 on the grid
+    assert oracle_lib.ref_origins(128)[-2:] == [123, 124] and len(oracle_lib.ref_origins(128)) == 43
+    assert oracle_lib.ref_origins(4) == [0] and oracle_lib.ref_origins(5) == [0, 1]
+    assert len(oracle_lib.ref_origins(256)) == 85 and len(oracle_lib.ref_origins(1024)) == 341
+
+
+def test_matcher_against_bruteforce_numpy(oracle_lib):
+    rng = np.random.default_rng(3)
+    vol = np.clip(rng.normal(100, 24, (9, 10, 12)), 0, 65535).astype(np.uint16)
+    o = oracle_lib.Oracle("f64", search_ht=7, k_ht=8)
+    idx, ssd, cnt = o.match_stage1(vol, 24.0)
+    bidx, bssd, bcnt = oracle_lib.match_bruteforce(vol, 24.0, Ns=7, K=8)
+    assert np.array_equal(cnt, bcnt) and np.array_equal(idx, bidx) and np.array_equal(ssd, bssd)
+    assert (idx[:, 0] >= 0).all() and (ssd[:, 0] == 0).all()  # the reference block matches itself first
+    assert set(np.unique(cnt)) <= {1, 2, 4, 8}
+
+
+def test_matcher_ties_lowest_index_first(oracle_lib):
+    vol = np.full((8, 8, 8), 500, np.uint16)
+    idx, ssd, cnt = oracle_lib.Oracle("f64").match_stage1(vol, 10.0)
+    assert (cnt == 16).all() and (ssd[:, :16] == 0).all()
+    assert (np.diff(idx.astype(np.int64), axis=1) > 0).all()  # all SSD 0: ascending origin index
+
+
+def test_constant_volume_is_a_fixed_point(oracle_lib):
+    vol = np.full((12, 13, 14), 1234, np.uint16)
+    for arith in ("f64", "mirror"):
+        y = oracle_lib.Oracle(arith).denoise(vol, 24.0)
+        assert np.abs(y - 1234.0).max() < 1e-2
+
+
+def test_denoising_reduces_error(oracle_lib):
+    vol = synth.vol(32, 32, 32, seed=1)
+    clean = synth.clean_vol(32, 32, 32, 1)
+    y1 = oracle_lib.Oracle("f64", stages=1).denoise(vol, 24.0)
+    y2 = oracle_lib.Oracle("f64").denoise(vol, 24.0)
+    e0 = np.sqrt(np.mean((vol - clean) ** 2))
+    e1 = np.sqrt(np.mean((y1 - clean) ** 2))
+    e2 = np.sqrt(np.mean((y2 - clean) ** 2))
+    assert e1 < 0.4 * e0 and e2 < e1  # HT removes most noise, Wiener improves on it
+
+
+def test_mirror_matches_plain_f64(oracle_lib, vol24):
+    """Butterflies + power-of-two rescale + fixed-point aggregation (float32) ==
+    dense orthonormal matrices in float64, within float32 rounding."""
+    for stages in (1, 2):
+        a = oracle_lib.Oracle("mirror", stages=stages).denoise(vol24, 24.0)
+        b = oracle_lib.Oracle("f64", stages=stages).denoise(vol24, 24.0)
+        assert rel_l2(a, b) < 1e-5
+        assert np.abs(a - b).max() < 0.5
+
+
+def test_all_ones_window_and_other_profiles(oracle_lib, vol24):
+    y = oracle_lib.Oracle("f64", kaiser_beta=0.0, search_ht=7, search_wie=9, k_ht=8, k_wie=16).denoise(vol24, 24.0)
+    assert np.isfinite(y).all() and rel_l2(y, vol24.astype(np.float32)) < 0.9
+
+
+def test_f32_zero_offset_equals_u16(oracle_lib, vol24):
+    a = oracle_lib.Oracle("mirror").denoise(vol24, 24.0)
+    b = oracle_lib.Oracle("mirror").denoise(vol24.astype(np.float32), 24.0)
+    assert np.array_equal(a, b)
+
+
+def test_f32_fractional_offset_runs_on_integer_matches(oracle_lib, vol24):
+    """raw - 36.37 (data_handling.py:353-354): matching is offset invariant, so a
+    pure hard-threshold pass with lambda = 0 (identity shrinkage) returns raw."""
+    raw = vol24.astype(np.float32) - np.float32(36.37)
+    y = oracle_lib.Oracle("f64", stages=1, lambda_ht=0.0).denoise(raw, 24.0)
+    assert np.abs(y - raw).max() < 1e-2
+
+
+def test_batch_equals_per_patch(oracle_lib):
+    b = np.stack([synth.vol(12, 14, 16, seed=s) for s in (1, 2)])
+    o = oracle_lib.Oracle("mirror")
+    yb = o.denoise(b, 24.0)
+    assert np.array_equal(yb[0], o.denoise(b[0], 24.0)) and np.array_equal(yb[1], o.denoise(b[1], 24.0))
+
+
+def test_slabs_equal_whole_volume(oracle_lib):
+    """global grid + halo 2*(Ns-1+L-1) => slab outputs concatenate to
+    the whole-volume result, bit for bit (integer aggregation is order free)."""
+    from b4d.sharding import halo_planes, slab_plan
+
+    vol = synth.vol(40, 12, 13, seed=9)
+    kw = dict(search_ht=5, search_wie=5, k_ht=8, k_wie=8)
+    o = oracle_lib.Oracle("mirror", **kw)
+    whole = o.denoise(vol, 24.0)
+    halo = halo_planes(5, 5, 2)
+    assert halo == 14
+    parts = []
+    for rank in range(3):
+        ob, oe, zb, ze = slab_plan(40, 3, rank, halo)
+        parts.append(o.denoise_slab(vol[zb:ze], zb, 40, ob, oe, 24.0))
+    assert np.array_equal(np.concatenate(parts, 0), whole)
+    # one plane short of the bound must NOT be relied on: the contract says halo, test says why
+    ob, oe, zb, ze = slab_plan(40, 3, 1, halo - 7)
+    short = o.denoise_slab(vol[zb:ze], zb, 40, ob, oe, 24.0)
+    assert short.shape == whole[ob:oe].shape
+
+
+def test_argument_errors(oracle_lib):
+    o = oracle_lib.Oracle("f64")
+    with pytest.raises(RuntimeError):
+        o.denoise(np.zeros((3, 8, 8), np.uint16), 24.0)  # a dimension below the block size
+    with pytest.raises(RuntimeError):
+        o.denoise(np.zeros((8, 8, 8), np.uint16), 0.0)
+    with pytest.raises(RuntimeError):
+        oracle_lib.Oracle("f64", search_ht=4)

@@ -1,0 +1,66 @@
+"""The oracle against golden vectors produced by RUNNING the reference
+(tests/golden/make_golden.py imports /root/reference's transforms.py and
+metrics.py).  Pins every step around BM4D that exists in the reference tree.
+BM4D itself is PARITY UNPINNED (closed wheel bm4d==4.2.5, absent)."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def test_quantize_matches_reference_offset_transform(gold, oracle_lib):
+    x = gold["quant_x"]
+    for i, off in enumerate(gold["quant_offsets"]):
+        want = gold["quant_q%d" % i]
+        got = oracle_lib.quantize_reference(x, offset_add=float(off))
+        assert got.dtype == np.uint16 and np.array_equal(got, want)
+        # the K7 contract at step = 1, offset_sub = 0 degenerates to the reference bit for bit
+        assert np.array_equal(oracle_lib.quantize_noise_scaled(x, 0.0, float(off), 1.0), want)
+        # and so does the C restatement
+        o = oracle_lib.Oracle("f64")
+        assert np.array_equal(o.quantize(x, 0.0, float(off), 1.0), want)
+
+
+def test_quantize_matches_reference_asinh_inverse(gold, oracle_lib):
+    assert np.array_equal(oracle_lib.quantize_reference(gold["asinh_counts"]), gold["asinh_q"])
+
+
+def test_estimate_offset_matches_reference(gold, oracle_lib):
+    from b4d.sharding import stats_from_hist
+
+    data, pos = gold["offset_data"], 0
+    for n, p, want in zip(gold["offset_n"], gold["offset_pct"], gold["offset_val"]):
+        s = data[pos : pos + n]
+        pos += n
+        assert oracle_lib.estimate_offset(s, percentile=float(p)) == want
+        # host-side statistic from the exact histogram (what ranks all-gather)
+        st = stats_from_hist(np.bincount(s, minlength=65536), float(p))
+        assert st["offset"] == want, (n, p, st["offset"], want)
+
+
+def test_mad_sigma_matches_reference_mask(gold, oracle_lib):
+    from b4d.sharding import stats_from_hist
+
+    for k in range(4):
+        raw = gold["mask_raw%d" % k]
+        med, mad, sigma = oracle_lib.robust_sigma(raw)
+        st = stats_from_hist(np.bincount(raw.reshape(-1), minlength=65536))
+        assert (st["median"], st["mad"], st["sigma"]) == (med, mad, sigma)
+        for kk in (3, 6):
+            want = np.unpackbits(gold["mask_m%d_k%d" % (k, kk)])[: raw.size].astype(bool).reshape(raw.shape)
+            # metrics.py:58 in float32
+            thr = np.float32(med) + np.float32(kk) * np.float32(sigma)
+            got = raw.astype(np.float32) > thr
+            assert np.array_equal(got, want)
+
+
+def test_truncating_variant(oracle_lib):
+    x = np.array([-3.2, 0.0, 0.9, 1.5, 2.5, 65535.9], dtype=np.float32)
+    assert oracle_lib.quantize_truncating(x).tolist() == [0, 0, 0, 1, 2, 65535]
