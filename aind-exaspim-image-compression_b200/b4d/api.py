@@ -328,7 +328,7 @@ class Denoiser:
     def last_match_stats(self):
         out = (ctypes.c_uint64 * 4)()
         _lib.check(self.lib.b4d_last_match_stats(self._h, out))
-        return {"fallback_refs": int(out[0]), "wide_tiles": int(out[1])}
+        return {"retry_refs": int(out[0]), "wide_tiles": int(out[1]), "slow_refs": int(out[2])}
 
     def measure_pipe_peaks(self):
         out = (ctypes.c_double * 4)()

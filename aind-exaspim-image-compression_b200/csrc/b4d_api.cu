@@ -68,7 +68,7 @@ struct b4d_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     b4d_profile prof;
-    DevBuf in, u16, zf, acc, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats;
+    DevBuf in, u16, zf, acc, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2;
     cudaEvent_t ev[B4D_T_COUNT + 1];
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
@@ -171,10 +171,13 @@ B4dTables make_tables(const b4d_profile &p, float sigma) {
     return t;
 }
 
+// u = clamp(int(rint((z + cf) * scale)) + ishift, 0, 65535); see oracle MatchMap.
 struct MatchMap {
-    float shift = 0.0f, scale = 1.0f;
+    float cf = 0.0f, scale = 1.0f;
+    int ishift = 0;
     int integral = 1;
 };
+int centre_shift(double lo, double hi) { return (int)(std::floor((65535.0 - (hi - lo)) * 0.5) - lo); }
 
 int tau_for(float tau, float sigma, float scale, int Ns, uint32_t *out) {
     const double s = (double)sigma * (double)scale;
@@ -280,19 +283,23 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     B4D_TRY(h->widx.ensure((size_t)std::max(R1, R2) * Kmax * sizeof(uint16_t)));
     B4D_TRY(h->cnt.ensure((size_t)std::max(R1, R2)));
     B4D_TRY(h->basic.ensure((size_t)TV * sizeof(float)));
+    B4D_TRY(h->s2.ensure((size_t)TV * sizeof(uint32_t)));
     B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
+    // Stage 1 ALWAYS aggregates in order-independent fixed point: the basic estimate feeds a
+    // discontinuous decision (quantise -> match), so it must not depend on atomic ordering.
+    // `deterministic` only selects the aggregation of the last stage.
     const bool det = p.deterministic != 0;
-    if (det) {
+    const bool det1 = true, det2 = det;
+    if (det1 || det2) {
         B4D_TRY(h->numq.ensure((size_t)TV * sizeof(long long)));
         B4D_TRY(h->denq.ensure((size_t)TV * sizeof(long long)));
-    } else {
-        B4D_TRY(h->acc.ensure((size_t)TV * sizeof(float2)));
     }
+    if (!det1 || (p.stages == 2 && !det2)) B4D_TRY(h->acc.ensure((size_t)TV * sizeof(float2)));
     const B4dTables tab = make_tables(p, sigma);
     b4d_upload_tables(tab, s);
     CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
 
-    auto zero_acc = [&]() -> int {
+    auto zero_acc = [&](bool det) -> int {
         if (det) {
             CU_TRY(cudaMemsetAsync(h->numq.p, 0, (size_t)TV * sizeof(long long), s));
             CU_TRY(cudaMemsetAsync(h->denq.p, 0, (size_t)TV * sizeof(long long), s));
@@ -301,7 +308,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         }
         return 0;
     };
-    auto normalise = [&](const float *fb, float *dst) {
+    auto normalise = [&](bool det, const float *fb, float *dst) {
         if (det) b4d_launch_normalise_det(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, TV, s);
         else b4d_launch_normalise(h->acc.as<float2>(), fb, dst, TV, s);
     };
@@ -309,11 +316,13 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     float *d_basic = (p.stages == 1) ? d_out : h->basic.as<float>();
 
     // ---- stage 1: hard thresholding
-    B4D_TRY(zero_acc());
-    clk.mark(B4D_T_PREP, 1);
+    B4D_TRY(zero_acc(det1));
+    b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
+    clk.mark(B4D_T_PREP, 2);
     MatchParams mp;
     mp.g = g1;
     mp.u = d_u;
+    mp.s2 = h->s2.as<uint32_t>();
     mp.tau = tau1;
     mp.K = p.k_ht;
     mp.widx = h->widx.as<uint16_t>();
@@ -333,17 +342,18 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.acc = h->acc.as<float2>();
     fp.numq = h->numq.as<long long>();
     fp.denq = h->denq.as<long long>();
-    if (R1 > 0) b4d_launch_filter(fp, false, det, s);
+    if (R1 > 0) b4d_launch_filter(fp, false, det1, s);
     clk.mark(B4D_T_FILTER1, 1);
-    normalise(d_zf, d_basic);
+    normalise(det1, d_zf, d_basic);
     clk.mark(B4D_T_NORM1, 1);
     CU_TRY(cudaGetLastError());
     if (p.stages == 1) return 0;
 
     // ---- stage 2: Wiener, matching on the basic estimate
-    b4d_launch_to_match(d_basic, d_u, TV, mm.shift, mm.scale, s);
-    B4D_TRY(zero_acc());
-    clk.mark(B4D_T_PREP, 2);
+    b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
+    B4D_TRY(zero_acc(det2));
+    b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
+    clk.mark(B4D_T_PREP, 3);
     mp.g = g2;
     mp.tau = tau2;
     mp.K = p.k_wie;
@@ -353,9 +363,9 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.basic = d_basic;
     fp.K = p.k_wie;
     fp.Ns = p.search_wie;
-    if (R2 > 0) b4d_launch_filter(fp, true, det, s);
+    if (R2 > 0) b4d_launch_filter(fp, true, det2, s);
     clk.mark(B4D_T_FILTER2, 1);
-    normalise(d_basic, d_out);
+    normalise(det2, d_basic, d_out);
     clk.mark(B4D_T_NORM2, 1);
     CU_TRY(cudaGetLastError());
     return 0;
@@ -386,7 +396,8 @@ int derive_match_map(b4d_handle *h, const float *d_in, long long n, float sigma,
     if (dev <= 1.0 / 64.0 && hi - lo <= 65535.0) {
         mm->integral = 1;
         mm->scale = 1.0f;
-        mm->shift = (float)(c - lo + std::floor((65535.0 - (hi - lo)) * 0.5));  // centred: no clamping
+        mm->cf = (float)c;
+        mm->ishift = centre_shift(lo, hi);
         return 0;
     }
     const double range = std::max(zhi - zlo, 1e-30);
@@ -394,7 +405,8 @@ int derive_match_map(b4d_handle *h, const float *d_in, long long n, float sigma,
     const int e_sigma = (int)std::floor(std::log2(64.0 / (double)sigma));
     mm->integral = 0;
     mm->scale = (float)std::ldexp(1.0, std::min(e_range, e_sigma));
-    mm->shift = (float)(-zlo + std::floor((65535.0 - range * (double)mm->scale) * 0.5) / (double)mm->scale);
+    mm->cf = 0.0f;
+    mm->ishift = centre_shift(std::floor(zlo * (double)mm->scale), std::ceil(zhi * (double)mm->scale));
     return 0;
 }
 
@@ -412,7 +424,8 @@ int convert_u16(b4d_handle *h, const uint16_t *d_in, float *d_zf, long long n, M
     const double lo = got[0], hi = got[1];
     mm->integral = 1;
     mm->scale = 1.0f;
-    mm->shift = (float)(std::floor((65535.0 - (hi - lo)) * 0.5) - lo);
+    mm->cf = 0.0f;
+    mm->ishift = centre_shift(lo, hi);
     return 0;
 }
 
@@ -476,7 +489,7 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
             d_u = h->in.as<uint16_t>();  // the staged copy doubles as the matching image
         } else {
             B4D_TRY(derive_match_map(h, h->in.as<float>(), TV, sigma, &mm));
-            b4d_launch_to_match(h->in.as<float>(), h->u16.as<uint16_t>(), TV, mm.shift, mm.scale, s);
+            b4d_launch_to_match(h->in.as<float>(), h->u16.as<uint16_t>(), TV, mm.cf, mm.scale, mm.ishift, s);
             d_zf = h->in.as<float>();
         }
         clk.mark(B4D_T_PREP, 2);
@@ -538,7 +551,7 @@ void b4d_destroy(b4d_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->acc, &h->numq, &h->denq, &h->basic, &h->out, &h->widx, &h->cnt,
-                      &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats})
+                      &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2})
         b->release();
     for (auto &ev : h->ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -642,9 +655,12 @@ int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], 
     B4D_TRY(h->ssd.ensure((size_t)R * K * sizeof(uint32_t)));
     B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
     CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
+    B4D_TRY(h->s2.ensure((size_t)V * sizeof(uint32_t)));
+    b4d_launch_block_energy(h->u16.as<uint16_t>(), h->s2.as<uint32_t>(), pl.D, pl.H, pl.W, 1, s);
     MatchParams mp;
     mp.g = g;
     mp.u = h->u16.as<uint16_t>();
+    mp.s2 = h->s2.as<uint32_t>();
     B4D_TRY(tau_for(p.tau_ht, sigma, 1.0f, Ns, &mp.tau));
     mp.K = K;
     mp.widx = h->widx.as<uint16_t>();

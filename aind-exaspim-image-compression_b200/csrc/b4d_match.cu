@@ -1,4 +1,5 @@
-// b4d_match.cu — K1 / K4: exact-integer block matching on a uint16 image.
+// b4d_match.cu — K0 (block energies) and K1 / K4 (exact-integer block matching)
+// on a uint16 image.
 //
 // Contract: for every reference block
 // (4x4x4, origins on the step-3 grid plus the flush origin N-4) compute the
@@ -6,29 +7,127 @@
 // accept SSD <= tau, order by (SSD, window index), keep the first
 // K' = 2^floor(log2(min(K, accepted))).
 //
-// Mapping: one CTA per 4x4x4 tile of reference blocks; the (Ns+12)^3 voxel
-// neighbourhood of the tile is staged once in shared memory (zero filled outside
-// the volume) and serves all 64 reference blocks.  One warp per reference
-// block.  A lane owns one (dz, dy) row of the window at a time and slides along
-// dx with Ns accumulators in registers: each shared-memory row of Ns+3 values
-// feeds 4*Ns (sub, mad) pairs, the reference block lives in 64 registers.
-// SSDs are uint32 when the tile's value range allows (64*(range)^2 < 2^32,
-// checked per tile while staging), else uint64.
+// Arithmetic.  SSD(a, b) = S2(a) + S2(b) - 2 * sum(a*b), with S2 the block energy
+// sum(v^2).  Everything is evaluated modulo 2^32: K0 writes S2 mod 2^32 for every
+// block origin once per stage, the matcher accumulates the cross term with one
+// IMAD per voxel pair (no subtract), and the modular result equals the true SSD
+// whenever the true SSD < 2^32 — guaranteed per tile by a range check made while
+// staging (64 * range^2 < 2^32).  Tiles that fail the check (bright structures
+// more than 8191 counts above their surroundings) take a direct 64-bit path.
+//
+// Mapping.  One CTA per 4x4x4 tile of reference blocks; the (Ns+12)^3 voxel
+// neighbourhood and the (Ns+9)^3 block energies are staged once in shared memory
+// and serve all 64 reference blocks.  One warp per reference block.  A lane owns
+// one (dz, dy) row of the window at a time and slides along dx with Ns
+// accumulators in registers: each shared-memory row of Ns+3 values feeds 4*Ns
+// IMADs, the reference block lives in 64 registers.  Shared-memory strides are
+// padded so that the 32 rows a warp reads at once fall in 32 distinct banks
+// (bank = B * (Ns*dz + dy) mod 32 with B odd).
 //
 // Selection is exact and deterministic: key = SSD << KB | window index (unique),
-// rejected candidates get 0xFFFFFFFF.  A running per-lane minimum (second
-// minimum for K = 32) gives, through one 32-lane bitonic sort per iteration, an
-// upper bound B with at least K keys <= B; only keys <= B are appended to a small
-// per-warp survivor list, which is rank-sorted at the end.  If the list
-// overflows (adversarial key order) the warp falls back to K rounds of
-// "smallest key greater than the previous one", recomputing the SSDs.
+// rejected candidates get 0xFFFFFFFF.  Rows are visited centre-out so the good
+// matches arrive first; a running per-lane minimum (second minimum for K = 32)
+// gives, through one 32-lane bitonic sort, an upper bound B with at least K keys
+// <= B; only keys <= B are appended to a small per-warp survivor list, which is
+// rank-sorted at the end.  If the list overflows (adversarial key order) the warp
+// falls back to K rounds of "smallest key greater than the previous one".
 #include "b4d_common.cuh"
 
 namespace {
 
 constexpr int WARPS = 8;
-constexpr int CAP = 256;  // survivor list entries per warp
+constexpr int CAP = 512;  // survivor list entries per warp
 
+// ---- shared-memory geometry (all constexpr in NS) ---------------------------
+template <int NS>
+struct Geo {
+    static constexpr int R = NS / 2;
+    static constexpr int E = NS + 12;   // staged voxels per axis
+    static constexpr int EC = NS + 9;   // staged block origins per axis (E - 3)
+    static constexpr int UNITS = NS * NS;
+    static constexpr int ITERS = (UNITS + 31) / 32;
+    static constexpr int KB = (NS * NS * NS <= 2048) ? 11 : 12;
+    // uint16 window: row stride 2*BW elements (BW odd words), plane stride 2*AW
+    static constexpr int BW = ((E + 1) / 2) | 1;
+    static constexpr int AW0 = E * BW;
+    static constexpr int AW = AW0 + (((NS * BW) % 32 - AW0 % 32) + 32) % 32;
+    static constexpr int SY = 2 * BW, SZ = 2 * AW;
+    static constexpr int WIN_ELEMS = E * SZ;
+    // uint32 energies: row stride BC (odd words), plane stride AC
+    static constexpr int BC = EC | 1;
+    static constexpr int AC0 = EC * BC;
+    static constexpr int AC = AC0 + (((NS * BC) % 32 - AC0 % 32) + 32) % 32;
+    static constexpr int S2_WORDS = EC * AC;
+    static constexpr size_t SMEM = (((size_t)WIN_ELEMS * 2 + 15) & ~(size_t)15) + (size_t)S2_WORDS * 4;
+    // centre-out visiting order of the 32-unit groups: mc, mc+1, mc-1, mc+2, ...
+    // packed 4 bits per entry so the device reads it with a shift and a mask
+    static constexpr int order_at(int it) {
+        const int mc = (UNITS / 2) / 32;
+        int count = 0;
+        for (int k = 0; k < 2 * ITERS + 2; ++k) {
+            const int off = (k + 1) / 2;
+            const int m = (k & 1) ? mc + off : mc - off;
+            if (m < 0 || m >= ITERS) continue;
+            if (count == it) return m;
+            ++count;
+        }
+        return 0;
+    }
+    static constexpr unsigned long long order_pack() {
+        unsigned long long v = 0;
+        for (int it = 0; it < ITERS; ++it) v |= (unsigned long long)order_at(it) << (4 * it);
+        return v;
+    }
+    static constexpr unsigned long long ORDER = order_pack();
+};
+
+// ------------------------------------------------------------------ K0 ------
+// S2[z][y][x] = sum over the 4x4x4 block at origin (z,y,x) of u^2, modulo 2^32,
+// for every origin with z <= D-4, y <= H-4, x <= W-4 (others are left untouched).
+// One thread per (z, y, 4 consecutive x): 16 rows of 7 values from L1/L2.
+__global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict__ u, uint32_t *__restrict__ s2,
+                                                      int D, int H, int W, int nvol) {
+    const int xq = (W - 3 + 3) / 4;
+    const long long per_vol = (long long)(D - 3) * (H - 3) * xq;
+    const long long total = per_vol * nvol;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int vol = (int)(i / per_vol);
+        long long r = i - (long long)vol * per_vol;
+        const int x0 = (int)(r % xq) * 4;
+        r /= xq;
+        const int y = (int)(r % (H - 3)), z = (int)(r / (H - 3));
+        const uint16_t *p = u + (long long)vol * D * H * W + ((long long)z * H + y) * W + x0;
+        uint32_t s[4] = {0u, 0u, 0u, 0u};
+        const int nx = min(7, W - x0);
+#pragma unroll
+        for (int dz = 0; dz < 4; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 4; ++dy) {
+                const uint16_t *row = p + ((long long)dz * H + dy) * W;
+                uint32_t q[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const uint32_t v = (k < nx) ? (uint32_t)__ldg(row + k) : 0u;
+                    q[k] = v * v;
+                }
+                const uint32_t w0 = q[0] + q[1] + q[2] + q[3];
+                const uint32_t w1 = w0 - q[0] + q[4];
+                const uint32_t w2 = w1 - q[1] + q[5];
+                const uint32_t w3 = w2 - q[2] + q[6];
+                s[0] += w0;
+                s[1] += w1;
+                s[2] += w2;
+                s[3] += w3;
+            }
+        uint32_t *o = s2 + (long long)vol * D * H * W + ((long long)z * H + y) * W + x0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x0 + k <= W - 4) o[k] = s[k];
+    }
+}
+
+// ------------------------------------------------------------ helpers -------
 __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) { return __reduce_min_sync(B4D_FULL, v); }
 
 // K-th smallest (0-based index kth) of one value per lane: 32-lane bitonic sort.
@@ -38,7 +137,7 @@ __device__ __forceinline__ uint32_t kth_smallest32(uint32_t v, int kth, int lane
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
             const uint32_t o = __shfl_xor_sync(B4D_FULL, v, j);
-            const bool up = (lane & k) == 0;      // ascending half (k == 32: all ascending)
+            const bool up = (lane & k) == 0;  // ascending half (k == 32: all ascending)
             const bool lower = (lane & j) == 0;
             const uint32_t mn = min(v, o), mx = max(v, o);
             v = (lower == up) ? mn : mx;
@@ -47,46 +146,43 @@ __device__ __forceinline__ uint32_t kth_smallest32(uint32_t v, int kth, int lane
     return __shfl_sync(B4D_FULL, v, kth);
 }
 
-// SSDs of one (dz, dy) row of candidates, all NS dx positions, uint32 path.
+// Cross terms sum(a*b) of one (dz, dy) row of candidates, all NS dx positions.
 template <int NS>
-__device__ __forceinline__ void ssd_row_u32(const uint16_t *__restrict__ base, const int (&ref)[B4D_LV],
-                                            uint32_t (&acc)[NS]) {
-    constexpr int E = NS + 12;
+__device__ __forceinline__ void xcorr_row(const uint16_t *__restrict__ base, const uint32_t (&ref)[B4D_LV],
+                                          uint32_t (&acc)[NS]) {
+    using G = Geo<NS>;
 #pragma unroll
     for (int j = 0; j < NS; ++j) acc[j] = 0u;
 #pragma unroll
     for (int z = 0; z < 4; ++z) {
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
-            int v[NS + 3];
+            uint32_t v[NS + 3];
 #pragma unroll
-            for (int i = 0; i < NS + 3; ++i) v[i] = base[(z * E + y) * E + i];
+            for (int i = 0; i < NS + 3; ++i) v[i] = base[z * G::SZ + y * G::SY + i];
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                const int r = ref[(z * 4 + y) * 4 + x];
+                const uint32_t r = ref[(z * 4 + y) * 4 + x];
 #pragma unroll
-                for (int j = 0; j < NS; ++j) {
-                    const int d = v[x + j] - r;
-                    acc[j] += (uint32_t)(d * d);
-                }
+                for (int j = 0; j < NS; ++j) acc[j] = v[x + j] * r + acc[j];
             }
         }
     }
 }
 
-// Same, 64-bit accumulation for tiles whose value range is too wide for uint32.
-// Rare (bright structures above 8191 counts over background); kept compact.
+// Direct 64-bit SSDs for tiles whose value range is too wide for the modular
+// form.  Rare (bright structures above 8191 counts over background); compact.
 template <int NS>
 __device__ __noinline__ void ssd_row_u64(const uint16_t *__restrict__ base, const uint16_t *__restrict__ refp,
                                          unsigned long long *acc) {
-    constexpr int E = NS + 12;
+    using G = Geo<NS>;
     for (int j = 0; j < NS; ++j) acc[j] = 0ull;
 #pragma unroll 1
     for (int z = 0; z < 4; ++z) {
 #pragma unroll 1
         for (int y = 0; y < 4; ++y) {
-            const uint16_t *row = base + (z * E + y) * E;
-            const uint16_t *rr = refp + (z * E + y) * E;
+            const uint16_t *row = base + z * G::SZ + y * G::SY;
+            const uint16_t *rr = refp + z * G::SZ + y * G::SY;
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 const int r = rr[x];
@@ -103,14 +199,12 @@ __device__ __noinline__ void ssd_row_u64(const uint16_t *__restrict__ base, cons
 
 template <int NS, bool K32>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
-    constexpr int R_ = NS / 2;
-    constexpr int E = NS + 12;
-    constexpr int KB = (NS * NS * NS <= 2048) ? 11 : 12;
-    constexpr int UNITS = NS * NS;
-    constexpr int ITERS = (UNITS + 31) / 32;
-    constexpr int EV = E * E * E;
+    using G = Geo<NS>;
+    constexpr int R_ = G::R, E = G::E, EC = G::EC, KB = G::KB, UNITS = G::UNITS, ITERS = G::ITERS;
 
-    extern __shared__ __align__(16) uint16_t s_win[];  // E^3 (+ pad)
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint16_t *s_win = reinterpret_cast<uint16_t *>(s_raw);
+    uint32_t *s_s2 = reinterpret_cast<uint32_t *>(s_raw + (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15));
     __shared__ uint32_t s_surv[WARPS][CAP];
     __shared__ int s_cnt[WARPS];
     __shared__ uint32_t s_min, s_max;
@@ -128,6 +222,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
     const int iz0 = tz * 4, iy0 = ty * 4, ix0 = tx * 4;
     const int bz = g.refz[iz0] - R_, by = g.refy[iy0] - R_, bx = g.refx[ix0] - R_;
     const uint16_t *__restrict__ uv = p.u + (long long)vol * g.vol_stride;
+    const uint32_t *__restrict__ s2v = p.s2 + (long long)vol * g.vol_stride;
 
     if (threadIdx.x == 0) {
         s_min = 0xFFFFFFFFu;
@@ -136,7 +231,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
     __syncthreads();
     {
         uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-        for (int i = threadIdx.x; i < EV; i += WARPS * 32) {
+        for (int i = threadIdx.x; i < E * E * E; i += WARPS * 32) {
             const int x = i % E, y = (i / E) % E, z = i / (E * E);
             const int gz = bz + z, gy = by + y, gx = bx + x;
             uint32_t v = 0;
@@ -145,7 +240,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
                 mn = min(mn, v);
                 mx = max(mx, v);
             }
-            s_win[i] = (uint16_t)v;
+            s_win[z * G::SZ + y * G::SY + x] = (uint16_t)v;
+        }
+        for (int i = threadIdx.x; i < EC * EC * EC; i += WARPS * 32) {
+            const int x = i % EC, y = (i / EC) % EC, z = i / (EC * EC);
+            const int gz = bz + z, gy = by + y, gx = bx + x;
+            uint32_t v = 0;
+            if ((unsigned)gz <= (unsigned)(g.D - 4) && (unsigned)gy <= (unsigned)(g.H - 4) &&
+                (unsigned)gx <= (unsigned)(g.W - 4))
+                v = s2v[((long long)gz * g.H + gy) * g.W + gx];
+            s_s2[z * G::AC + y * G::BC + x] = v;
         }
         mn = __reduce_min_sync(B4D_FULL, mn);
         mx = __reduce_max_sync(B4D_FULL, mx);
@@ -166,33 +270,39 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
         if (iz >= g.nrz || iy >= g.nry || ix >= g.nrx) continue;  // warp-uniform
         const int oz = g.refz[iz], oy = g.refy[iy], ox = g.refx[ix];
         const int wz0 = oz - R_ - bz, wy0 = oy - R_ - by, wx0 = ox - R_ - bx;  // window origin in the tile
-        const uint16_t *refp = s_win + ((wz0 + R_) * E + (wy0 + R_)) * E + (wx0 + R_);
-        int ref[B4D_LV];
+        const uint16_t *refp = s_win + (wz0 + R_) * G::SZ + (wy0 + R_) * G::SY + (wx0 + R_);
+        uint32_t ref[B4D_LV];
+        uint32_t s2ref = 0;
         if (narrow) {
 #pragma unroll
             for (int z = 0; z < 4; ++z)
 #pragma unroll
                 for (int y = 0; y < 4; ++y)
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) ref[(z * 4 + y) * 4 + x] = refp[(z * E + y) * E + x];
+                    for (int x = 0; x < 4; ++x) ref[(z * 4 + y) * 4 + x] = refp[z * G::SZ + y * G::SY + x];
+            s2ref = s_s2[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
         }
         // valid dx range of candidates: cx = ox - R_ + j in [0, W-4]
         const int jlo = max(0, R_ - ox), jhi = min(NS - 1, g.W - 4 - ox + R_);
 
         const long long rlin = (long long)vol * g.refs_per_vol + ((long long)iz * g.nry + iy) * g.nrx + ix;
 
-        bool fallback = false;
-        uint32_t prev = 0;      // fallback: last extracted key
-        int nsel = 0;           // fallback: keys extracted so far
-        uint32_t mykey = B4D_INVALID_KEY;  // fallback: lane k holds the k-th key
+        // mode 0: one pass, bound refined on the fly.  mode 1 (survivor list overflowed):
+        // one more pass with the final bound of mode 0 fixed from the start.  mode 2 (still
+        // overflowing): K rounds of "smallest key greater than the previous one".
+        int mode = 0;
+        uint32_t Bfix = B4D_INVALID_KEY - 1u;
+        uint32_t prev = 0;                 // mode 2: last extracted key
+        int nsel = 0;                      // mode 2: keys extracted so far
+        uint32_t mykey = B4D_INVALID_KEY;  // mode 2: lane k holds the k-th key
         for (;;) {
             uint32_t lmin1 = B4D_INVALID_KEY, lmin2 = B4D_INVALID_KEY;
-            uint32_t B = B4D_INVALID_KEY - 1u;
+            uint32_t B = Bfix;
             if (lane == 0) s_cnt[warp] = 0;
             __syncwarp();
 #pragma unroll 1
             for (int it = 0; it < ITERS; ++it) {
-                const int unit = it * 32 + lane;
+                const int unit = (int)((G::ORDER >> (4 * it)) & 15ull) * 32 + lane;
                 const int dz = unit / NS, dy = unit - dz * NS;
                 const int cz = oz - R_ + dz, cy = oy - R_ + dy;
                 const bool uvalid = unit < UNITS && cz >= 0 && cz <= g.D - 4 && cy >= 0 && cy <= g.H - 4;
@@ -201,14 +311,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
 #pragma unroll
                 for (int j = 0; j < NS; ++j) key[j] = B4D_INVALID_KEY;
                 if (uvalid) {
-                    const uint16_t *base = s_win + ((wz0 + dz) * E + (wy0 + dy)) * E + wx0;
+                    const uint16_t *base = s_win + (wz0 + dz) * G::SZ + (wy0 + dy) * G::SY + wx0;
                     if (narrow) {
                         uint32_t acc[NS];
-                        ssd_row_u32<NS>(base, ref, acc);
+                        xcorr_row<NS>(base, ref, acc);
+                        const uint32_t *e = s_s2 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
 #pragma unroll
                         for (int j = 0; j < NS; ++j) {
-                            const bool ok = acc[j] <= tau && j >= jlo && j <= jhi;
-                            key[j] = ok ? ((acc[j] << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                            const uint32_t ssd = (e[j] + s2ref) - 2u * acc[j];  // exact: true SSD < 2^32
+                            const bool ok = ssd <= tau && j >= jlo && j <= jhi;
+                            key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                         }
                     } else {
                         unsigned long long acc[NS];
@@ -220,14 +332,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
                         }
                     }
                 }
-                if (!fallback) {
+                if (mode < 2) {
+                    if (mode == 0) {
 #pragma unroll
-                    for (int j = 0; j < NS; ++j) {
-                        if (K32) lmin2 = min(lmin2, max(lmin1, key[j]));
-                        lmin1 = min(lmin1, key[j]);
+                        for (int j = 0; j < NS; ++j) {
+                            if (K32) lmin2 = min(lmin2, max(lmin1, key[j]));
+                            lmin1 = min(lmin1, key[j]);
+                        }
+                        const uint32_t b = kth_smallest32(K32 ? lmin2 : lmin1, K32 ? 15 : K - 1, lane);
+                        B = min(B, b);
                     }
-                    const uint32_t b = kth_smallest32(K32 ? lmin2 : lmin1, K32 ? 15 : K - 1, lane);
-                    B = min(B, b);
 #pragma unroll
                     for (int j = 0; j < NS; ++j) {
                         if (key[j] <= B) {
@@ -244,41 +358,59 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
                 }
             }
             __syncwarp();
-            if (!fallback) {
+            if (mode < 2) {
                 const int n = s_cnt[warp];
                 if (n <= CAP) {
-                    // rank sort of the survivors that are <= the final bound
+                    // compact the survivors that are <= the final bound, then rank-sort them
                     uint32_t mine[CAP / 32];
-                    int nf = 0;
 #pragma unroll
                     for (int s = 0; s < CAP / 32; ++s) {
                         const int e = s * 32 + lane;
                         uint32_t k = (e < n) ? s_surv[warp][e] : B4D_INVALID_KEY;
-                        if (k > B) k = B4D_INVALID_KEY;
-                        mine[s] = k;
-                        nf += __popc(__ballot_sync(B4D_FULL, k != B4D_INVALID_KEY));
+                        mine[s] = (k > B) ? B4D_INVALID_KEY : k;
                     }
-                    const int ns = min(nf, K);
-                    const int kp = ns > 0 ? (1 << (31 - __clz(ns))) : 0;
+                    __syncwarp();
+                    int nf = 0;
 #pragma unroll
                     for (int s = 0; s < CAP / 32; ++s) {
                         if (s * 32 >= n) break;  // warp-uniform
-                        int rank = 0;
-                        const uint32_t k = mine[s];
-                        for (int e = 0; e < n; ++e) rank += (s_surv[warp][e] < k) ? 1 : 0;
-                        if (k != B4D_INVALID_KEY && rank < kp) {
-                            p.widx[rlin * K + rank] = (uint16_t)(k & ((1u << KB) - 1u));
-                            if (p.ssd_out) p.ssd_out[rlin * K + rank] = k >> KB;
+                        const bool keep = mine[s] != B4D_INVALID_KEY;
+                        const unsigned bal = __ballot_sync(B4D_FULL, keep);
+                        if (keep) s_surv[warp][nf + __popc(bal & ((1u << lane) - 1u))] = mine[s];
+                        nf += __popc(bal);
+                    }
+                    __syncwarp();
+                    const int ns = min(nf, K);
+                    const int kp = ns > 0 ? (1 << (31 - __clz(ns))) : 0;
+                    for (int s0 = 0; s0 < nf; s0 += 64) {
+                        const int e0 = s0 + lane, e1 = s0 + 32 + lane;
+                        const uint32_t k0 = e0 < nf ? s_surv[warp][e0] : B4D_INVALID_KEY;
+                        const uint32_t k1 = e1 < nf ? s_surv[warp][e1] : B4D_INVALID_KEY;
+                        int r0 = 0, r1 = 0;
+                        for (int e = 0; e < nf; ++e) {
+                            const uint32_t o = s_surv[warp][e];
+                            r0 += (o < k0) ? 1 : 0;
+                            r1 += (o < k1) ? 1 : 0;
+                        }
+                        if (k0 != B4D_INVALID_KEY && r0 < kp) {
+                            p.widx[rlin * K + r0] = (uint16_t)(k0 & ((1u << KB) - 1u));
+                            if (p.ssd_out) p.ssd_out[rlin * K + r0] = k0 >> KB;
+                        }
+                        if (k1 != B4D_INVALID_KEY && r1 < kp) {
+                            p.widx[rlin * K + r1] = (uint16_t)(k1 & ((1u << KB) - 1u));
+                            if (p.ssd_out) p.ssd_out[rlin * K + r1] = k1 >> KB;
                         }
                     }
                     if (lane == 0) p.cnt[rlin] = (uint8_t)kp;
                     break;
                 }
-                fallback = true;  // list overflowed: exact but slow path
-                if (lane == 0 && p.stats) atomicAdd(&p.stats[0], 1ull);
+                // list overflowed: retry once with the (tightest) final bound, then go exact-but-slow
+                if (lane == 0 && p.stats) atomicAdd(&p.stats[mode == 0 ? 0 : 2], 1ull);
+                Bfix = B;
+                ++mode;
                 continue;
             }
-            // fallback round finished: lmin1 = smallest key > prev in this lane
+            // mode 2 round finished: lmin1 = smallest key > prev in this lane
             const uint32_t m = warp_min_u32(lmin1);
             if (m != B4D_INVALID_KEY) {
                 if (lane == nsel) mykey = m;
@@ -301,8 +433,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
 
 template <int NS>
 void launch_ns(const MatchParams &p, cudaStream_t s) {
-    constexpr int E = NS + 12;
-    const size_t smem = ((size_t)E * E * E * sizeof(uint16_t) + 15) & ~(size_t)15;
+    using G = Geo<NS>;
+    const size_t smem = G::SMEM;
     const long long tiles = (long long)p.g.nvol * p.g.tz * p.g.ty * p.g.tx;
     if (p.K > 16) {
         cudaFuncSetAttribute(k_match<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -314,6 +446,14 @@ void launch_ns(const MatchParams &p, cudaStream_t s) {
 }
 
 }  // namespace
+
+void b4d_launch_block_energy(const uint16_t *u, uint32_t *s2, int D, int H, int W, int nvol, cudaStream_t s) {
+    const long long total = (long long)(D - 3) * (H - 3) * ((W - 3 + 3) / 4) * nvol;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148ll * 64) blocks = 148ll * 64;
+    if (blocks < 1) blocks = 1;
+    k_block_energy<<<(unsigned)blocks, 256, 0, s>>>(u, s2, D, H, W, nvol);
+}
 
 void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s) {
     switch (Ns) {

@@ -69,27 +69,29 @@ __global__ void __launch_bounds__(256) k_u16_to_f32(const uint16_t *__restrict__
 }
 
 // ---------------------------------------------- f32 -> matching image (u16) --
-__device__ __forceinline__ uint32_t to_match(float v, float shift, float scale) {
-    float q = rintf((v + shift) * scale);
-    q = fminf(fmaxf(q, 0.0f), 65535.0f);
+// u = clamp(int(rint((v + cf) * scale)) + ishift, 0, 65535): the integer shift is
+// applied after rounding so that rounding never depends on it.
+__device__ __forceinline__ uint32_t to_match(float v, float cf, float scale, int ishift) {
+    long long q = (long long)__float2ll_rn((v + cf) * scale) + ishift;
+    q = min(max(q, 0ll), 65535ll);
     return (uint32_t)q;
 }
 __global__ void __launch_bounds__(256) k_to_match(const float *__restrict__ in, uint16_t *__restrict__ out,
-                                                  long long n, float shift, float scale) {
+                                                  long long n, float shift, float scale, int ishift) {
     const long long nv = n >> 3;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
         const float4 a = reinterpret_cast<const float4 *>(in)[2 * i];
         const float4 b = reinterpret_cast<const float4 *>(in)[2 * i + 1];
         uint4 o;
-        o.x = to_match(a.x, shift, scale) | (to_match(a.y, shift, scale) << 16);
-        o.y = to_match(a.z, shift, scale) | (to_match(a.w, shift, scale) << 16);
-        o.z = to_match(b.x, shift, scale) | (to_match(b.y, shift, scale) << 16);
-        o.w = to_match(b.z, shift, scale) | (to_match(b.w, shift, scale) << 16);
+        o.x = to_match(a.x, shift, scale, ishift) | (to_match(a.y, shift, scale, ishift) << 16);
+        o.y = to_match(a.z, shift, scale, ishift) | (to_match(a.w, shift, scale, ishift) << 16);
+        o.z = to_match(b.x, shift, scale, ishift) | (to_match(b.y, shift, scale, ishift) << 16);
+        o.w = to_match(b.z, shift, scale, ishift) | (to_match(b.w, shift, scale, ishift) << 16);
         reinterpret_cast<uint4 *>(out)[i] = o;
     }
     for (long long i = (nv << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = (uint16_t)to_match(in[i], shift, scale);
+        out[i] = (uint16_t)to_match(in[i], shift, scale, ishift);
 }
 
 // ------------------------------------------------------------- normalise ----
@@ -276,8 +278,9 @@ __global__ void __launch_bounds__(1024) k_pipe(int iters, unsigned *sink) {
 void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, unsigned *minmax, cudaStream_t s) {
     k_u16_to_f32<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, minmax);
 }
-void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float shift, float scale, cudaStream_t s) {
-    k_to_match<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, shift, scale);
+void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, float scale, int ishift,
+                         cudaStream_t s) {
+    k_to_match<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, cf, scale, ishift);
 }
 void b4d_launch_normalise(const float2 *acc, const float *fallback, float *out, long long n, cudaStream_t s) {
     k_normalise<<<grid_for(n >> 2, 256, 8), 256, 0, s>>>(acc, fallback, out, n);

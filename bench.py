@@ -173,7 +173,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    shape = (96, 128, 128)
+    shape = (128, 192, 192)
     cores = os.cpu_count() or 1
     real = probe_real_bm4d()
     from oracle import np_oracle
@@ -387,7 +387,7 @@ def main():
             "tile_stats": stats,
         }
         if not args.no_cpu_baseline:
-            shape = (96, 128, 128)
+            shape = (192, 256, 256)
             v, secs = cpu_port_throughput(shape)
             line["cpu_baseline"] = {
                 "value": v, "unit": "voxels/s", "cores": os.cpu_count() or 1, "kind": "port",

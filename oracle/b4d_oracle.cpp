@@ -577,17 +577,23 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
 }
 
 // ----------------------------------------------------- matching image ------
-// Matching runs on a uint16 image: u = clamp(rint((z + shift) * scale), 0, 65535).
-//  * uint16 input: shift 0, scale 1 (the data itself).
+// Matching runs on a uint16 image:
+//     u = clamp(int(rint((z + cf) * scale)) + ishift, 0, 65535)
+//  * uint16 input: stage 1 matches on the data itself.
 //  * float32 input that is uint16 counts minus one scalar (data_handling.py:
-//    353-354): shift restores the integers, scale 1 — matching is then exactly
-//    the matching on the original counts (offset invariance).
-//  * any other float32 input: a power-of-two scale puts sigma at 32..64 steps
-//    (bounded by the 16-bit range).
+//    353-354): cf restores the integers (|cf| <= 0.5), scale 1 — matching is then
+//    exactly the matching on the original counts (offset invariance).
+//  * any other float32 input: cf 0 and a power-of-two scale that puts sigma at
+//    32..64 steps (bounded by the 16-bit range).
+// Stage 2 quantises the basic estimate with cf = 0: u = int(rint(y*scale)) + ishift.
+// ishift is an INTEGER that centres the range in uint16, applied after rounding,
+// so the rounding never depends on it (a batch and a single patch agree).
 struct MatchMap {
-    float shift, scale;
+    float cf, scale;
+    int ishift;
     int integral;
 };
+int centre_shift(double lo, double hi) { return (int)(std::floor((65535.0 - (hi - lo)) * 0.5) - lo); }
 MatchMap derive_match_map(const float *z, int64_t n, float sigma) {
     double c = std::rint((double)z[0]) - (double)z[0];
     double dev = 0, lo = 1e300, hi = -1e300, zlo = 1e300, zhi = -1e300;
@@ -604,7 +610,8 @@ MatchMap derive_match_map(const float *z, int64_t n, float sigma) {
     if (dev <= 1.0 / 64.0 && hi - lo <= 65535.0) {
         mm.integral = 1;
         mm.scale = 1.0f;
-        mm.shift = (float)(c - lo + std::floor((65535.0 - (hi - lo)) * 0.5));  // centred: no clamping
+        mm.cf = (float)c;
+        mm.ishift = centre_shift(lo, hi);
         return mm;
     }
     double range = std::max(zhi - zlo, 1e-30);
@@ -613,12 +620,13 @@ MatchMap derive_match_map(const float *z, int64_t n, float sigma) {
     int e = std::min(e_range, e_sigma);
     mm.integral = 0;
     mm.scale = (float)std::ldexp(1.0, e);
-    mm.shift = (float)(-zlo + std::floor((65535.0 - range * (double)mm.scale) * 0.5) / (double)mm.scale);
+    mm.cf = 0.0f;
+    mm.ishift = centre_shift(std::floor(zlo * (double)mm.scale), std::ceil(zhi * (double)mm.scale));
     return mm;
 }
-inline uint16_t to_match_u16(float v, const MatchMap &mm) {
-    float q = rintf((v + mm.shift) * mm.scale);
-    q = fminf(fmaxf(q, 0.0f), 65535.0f);
+inline uint16_t to_match_u16(float v, float cf, float scale, int ishift) {
+    long long q = (long long)rintf((v + cf) * scale) + ishift;
+    q = std::min<long long>(std::max<long long>(q, 0), 65535);
     return (uint16_t)q;
 }
 
@@ -634,7 +642,7 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     const int64_t V = (int64_t)g1.D * g1.H * g1.W;
     std::vector<float> zf(V);
     std::vector<uint16_t> u(V);
-    MatchMap mm{0.0f, 1.0f, 1};
+    MatchMap mm{0.0f, 1.0f, 0, 1};
     if (in_u16) {
         // stage 1 matches on the raw integers; the stage-2 matching image is the
         // basic estimate centred in the uint16 range so that it is never clamped
@@ -645,12 +653,12 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
             lo = std::min(lo, (double)in_u16[i]);
             hi = std::max(hi, (double)in_u16[i]);
         }
-        mm.shift = (float)(std::floor((65535.0 - (hi - lo)) * 0.5) - lo);
+        mm.ishift = centre_shift(lo, hi);
     } else {
         mm = derive_match_map(in_f32, V, sigma);
         for (int64_t i = 0; i < V; ++i) {
             zf[i] = in_f32[i];
-            u[i] = to_match_u16(in_f32[i], mm);
+            u[i] = to_match_u16(in_f32[i], mm.cf, mm.scale, mm.ishift);
         }
     }
     Matches m;
@@ -663,7 +671,7 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
             for (int64_t i = 0; i < V; ++i) out[i] = (float)basic[i];
             return 0;
         }
-        for (int64_t i = 0; i < V; ++i) u[i] = to_match_u16((float)basic[i], mm);
+        for (int64_t i = 0; i < V; ++i) u[i] = to_match_u16((float)basic[i], 0.0f, mm.scale, mm.ishift);
         match_all(u.data(), g2, p.search_wie, p.k_wie, tau_int(p.tau_wie, sigma, mm.scale), m);
         std::fill(num.begin(), num.end(), 0.0);
         std::fill(den.begin(), den.end(), 0.0);
@@ -681,7 +689,7 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
         std::memcpy(out, basic.data(), V * sizeof(float));
         return 0;
     }
-    for (int64_t i = 0; i < V; ++i) u[i] = to_match_u16(basic[i], mm);
+    for (int64_t i = 0; i < V; ++i) u[i] = to_match_u16(basic[i], 0.0f, mm.scale, mm.ishift);
     match_all(u.data(), g2, p.search_wie, p.k_wie, tau_int(p.tau_wie, sigma, mm.scale), m);
     std::fill(numq.begin(), numq.end(), 0);
     std::fill(denq.begin(), denq.end(), 0);
