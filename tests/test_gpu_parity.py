@@ -236,7 +236,7 @@ def test_errors(dn, b4d_mod):
         b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(max_stack_size_ht=12))
 
 
-def test_full_size_properties_128(dn):
+def test_full_size_properties_128(dn, b4d_mod):
     """BASELINE config 2's patch size (128^3): properties that need no oracle —
     constant volume is a fixed point, output finite, noise reduced."""
     from b4d import synth
@@ -246,5 +246,11 @@ def test_full_size_properties_128(dn):
     y = dn.denoise(vol, 24.0)
     assert np.isfinite(y).all()
     assert np.sqrt(np.mean((y - clean) ** 2)) < 0.5 * np.sqrt(np.mean((vol - clean) ** 2))
+    # constant volume: every SSD ties at 0, every group takes the 32 lowest-index candidates, so
+    # some voxels collect thousands of contributions — float atomics drift by ~1e-5 relative,
+    # the fixed-point aggregation does not
     c = np.full((128, 128, 128), 4321, np.uint16)
-    assert np.abs(dn.denoise(c, 24.0) - 4321.0).max() < 1e-2
+    assert np.abs(dn.denoise(c, 24.0) - 4321.0).max() < 0.25
+    d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(deterministic=True))
+    assert np.abs(d.denoise(c, 24.0) - 4321.0).max() < 1e-2
+    d.close()
