@@ -68,7 +68,7 @@ struct b4d_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     b4d_profile prof;
-    DevBuf in, u16, zf, acc, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2;
+    DevBuf in, u16, zf, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2;
     cudaEvent_t ev[B4D_T_COUNT + 1];
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
@@ -285,38 +285,29 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     B4D_TRY(h->basic.ensure((size_t)TV * sizeof(float)));
     B4D_TRY(h->s2.ensure((size_t)TV * sizeof(uint32_t)));
     B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
-    // Stage 1 ALWAYS aggregates in order-independent fixed point: the basic estimate feeds a
-    // discontinuous decision (quantise -> match), so it must not depend on atomic ordering.
-    // `deterministic` only selects the aggregation of the last stage.
-    const bool det = p.deterministic != 0;
-    const bool det1 = true, det2 = det;
-    if (det1 || det2) {
-        B4D_TRY(h->numq.ensure((size_t)TV * sizeof(long long)));
-        B4D_TRY(h->denq.ensure((size_t)TV * sizeof(long long)));
-    }
-    if (!det1 || (p.stages == 2 && !det2)) B4D_TRY(h->acc.ensure((size_t)TV * sizeof(float2)));
+    // Both stages aggregate in order-independent 2^32 fixed point (int64): the result does not
+    // depend on scheduling, a slab equals the whole volume bit for bit, and the basic estimate
+    // that feeds the stage-2 matching (a discontinuous decision) is reproducible.
+    // profile.deterministic is kept in the ABI and is always honoured.
+    B4D_TRY(h->numq.ensure((size_t)TV * sizeof(long long)));
+    B4D_TRY(h->denq.ensure((size_t)TV * sizeof(long long)));
     const B4dTables tab = make_tables(p, sigma);
     b4d_upload_tables(tab, s);
     CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
 
-    auto zero_acc = [&](bool det) -> int {
-        if (det) {
-            CU_TRY(cudaMemsetAsync(h->numq.p, 0, (size_t)TV * sizeof(long long), s));
-            CU_TRY(cudaMemsetAsync(h->denq.p, 0, (size_t)TV * sizeof(long long), s));
-        } else {
-            CU_TRY(cudaMemsetAsync(h->acc.p, 0, (size_t)TV * sizeof(float2), s));
-        }
+    auto zero_acc = [&]() -> int {
+        CU_TRY(cudaMemsetAsync(h->numq.p, 0, (size_t)TV * sizeof(long long), s));
+        CU_TRY(cudaMemsetAsync(h->denq.p, 0, (size_t)TV * sizeof(long long), s));
         return 0;
     };
-    auto normalise = [&](bool det, const float *fb, float *dst) {
-        if (det) b4d_launch_normalise_det(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, TV, s);
-        else b4d_launch_normalise(h->acc.as<float2>(), fb, dst, TV, s);
+    auto normalise = [&](const float *fb, float *dst) {
+        b4d_launch_normalise_det(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, TV, s);
     };
 
     float *d_basic = (p.stages == 1) ? d_out : h->basic.as<float>();
 
     // ---- stage 1: hard thresholding
-    B4D_TRY(zero_acc(det1));
+    B4D_TRY(zero_acc());
     b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 2);
     MatchParams mp;
@@ -339,19 +330,19 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.cnt = mp.cnt;
     fp.K = p.k_ht;
     fp.Ns = p.search_ht;
-    fp.acc = h->acc.as<float2>();
+    fp.nseg = 1;
     fp.numq = h->numq.as<long long>();
     fp.denq = h->denq.as<long long>();
-    if (R1 > 0) b4d_launch_filter(fp, false, det1, s);
+    if (R1 > 0) b4d_launch_filter(fp, false, s);
     clk.mark(B4D_T_FILTER1, 1);
-    normalise(det1, d_zf, d_basic);
+    normalise(d_zf, d_basic);
     clk.mark(B4D_T_NORM1, 1);
     CU_TRY(cudaGetLastError());
     if (p.stages == 1) return 0;
 
     // ---- stage 2: Wiener, matching on the basic estimate
     b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
-    B4D_TRY(zero_acc(det2));
+    B4D_TRY(zero_acc());
     b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 3);
     mp.g = g2;
@@ -363,9 +354,9 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.basic = d_basic;
     fp.K = p.k_wie;
     fp.Ns = p.search_wie;
-    if (R2 > 0) b4d_launch_filter(fp, true, det2, s);
+    if (R2 > 0) b4d_launch_filter(fp, true, s);
     clk.mark(B4D_T_FILTER2, 1);
-    normalise(det2, d_basic, d_out);
+    normalise(d_basic, d_out);
     clk.mark(B4D_T_NORM2, 1);
     CU_TRY(cudaGetLastError());
     return 0;
@@ -550,7 +541,7 @@ int b4d_create(int device, const b4d_profile *profile, b4d_handle **out) {
 void b4d_destroy(b4d_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->acc, &h->numq, &h->denq, &h->basic, &h->out, &h->widx, &h->cnt,
+    for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->numq, &h->denq, &h->basic, &h->out, &h->widx, &h->cnt,
                       &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2})
         b->release();
     for (auto &ev : h->ev) cudaEventDestroy(ev);

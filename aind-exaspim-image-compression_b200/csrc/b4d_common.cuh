@@ -52,20 +52,19 @@ struct FilterParams {
     const uint8_t *cnt;
     int K;
     int Ns;
-    float2 *acc;                 // fast mode: (num, den) per voxel
-    long long *numq, *denq;      // deterministic mode: 2^32 fixed point
+    int nseg;                    // z segments per column (set by the launcher)
+    long long *numq, *denq;      // 2^32 fixed-point accumulators (order independent)
 };
 
 void b4d_launch_block_energy(const uint16_t *u, uint32_t *s2, int D, int H, int W, int nvol, cudaStream_t s);
 void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s);
-void b4d_launch_filter(const FilterParams &p, bool wiener, bool deterministic, cudaStream_t s);
+void b4d_launch_filter(const FilterParams &p, bool wiener, cudaStream_t s);
 void b4d_upload_tables(const B4dTables &t, cudaStream_t s);
 
 // misc kernels (b4d_misc.cu)
 void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, unsigned *minmax, cudaStream_t s);
 void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, float scale, int ishift,
                          cudaStream_t s);
-void b4d_launch_normalise(const float2 *acc, const float *fallback, float *out, long long n, cudaStream_t s);
 void b4d_launch_normalise_det(const long long *numq, const long long *denq, const float *fallback, float *out,
                               long long n, cudaStream_t s);
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,

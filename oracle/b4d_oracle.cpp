@@ -426,14 +426,14 @@ inline void haar4_inv(float *v, int s) {
 }
 inline void dct4_fwd(float *v, int s, float c1, float c3) {
     float a = v[0] + v[3 * s], b = v[s] + v[2 * s], c = v[0] - v[3 * s], d = v[s] - v[2 * s];
-    v[0] = (a + b) * 0.5f;
-    v[2 * s] = (a - b) * 0.5f;
+    v[0] = fmaf(0.5f, a, 0.5f * b);
+    v[2 * s] = fmaf(-0.5f, b, 0.5f * a);
     v[s] = fmaf(c1, c, c3 * d);
-    v[3 * s] = fmaf(c3, c, -(c1 * d));
+    v[3 * s] = fmaf(-c1, d, c3 * c);
 }
 inline void dct4_inv(float *v, int s, float c1, float c3) {
-    float a = (v[0] + v[2 * s]) * 0.5f, b = (v[0] - v[2 * s]) * 0.5f;
-    float c = fmaf(c1, v[s], c3 * v[3 * s]), d = fmaf(c3, v[s], -(c1 * v[3 * s]));
+    float a = fmaf(0.5f, v[0], 0.5f * v[2 * s]), b = fmaf(-0.5f, v[2 * s], 0.5f * v[0]);
+    float c = fmaf(c1, v[s], c3 * v[3 * s]), d = fmaf(-c1, v[3 * s], c3 * v[s]);
     v[0] = a + c;
     v[3 * s] = a - c;
     v[s] = b + d;
@@ -479,6 +479,16 @@ inline int group_level(int k, int lg) { return k == 0 ? lg : 1 + __builtin_ctz((
 inline int spatial_class(int v) { return ((v & 3) >= 2) + (((v >> 2) & 3) >= 2) + ((v >> 4) >= 2); }
 
 constexpr float FIX_SCALE = 4294967296.0f;  // 2^32
+
+// Which DCT coefficient (cz*16 + cy*4 + cx) lane (zh, y, x), register rr of the
+// CUDA filter kernel holds after the forward transform (csrc/b4d_filter.cu):
+// along x and y lane position 0,1,2,3 holds output 0,2,3,1; along z (zh, rr) holds
+// output 2*zh + rr.
+inline int wiener_coeff(int lane, int rr) {
+    static const int pos2out[4] = {0, 2, 3, 1};
+    const int x = lane & 3, y = (lane >> 2) & 3, zh = lane >> 4;
+    return (2 * zh + rr) * 16 + pos2out[y] * 4 + pos2out[x];
+}
 
 template <bool WIENER>
 void filter_mirror(const float *zf, const float *basic, const Geom &g, const Matches &m, int Ns,
@@ -536,19 +546,30 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
             ghaar_fwd(est, kp);
             for (int k = 0; k < kp; ++k) xf3_fwd<true>(noisy + k * LV, t);
             ghaar_fwd(noisy, kp);
-            float part[32];
-            for (int k = 0; k < 32; ++k) part[k] = 0.0f;
+            // Wiener attenuation, elementwise; sum of W^2 in the kernel's order: lane
+            // (zh, y, x) of the warp owns two coefficients of every slot and chains
+            // fma over (slot ascending, register 0 then 1); the 32 partial sums meet in
+            // an xor butterfly.  Coefficient held by (lane, register): see wiener_coeff().
+            float wgt[32 * LV];
             for (int k = 0; k < kp; ++k) {
                 const int l = group_level(k, lg);
-                float acc = 0.0f;
                 for (int v = 0; v < LV; ++v) {
                     const float yn = est[k * LV + v] * t.gs[l];
                     const float y2 = yn * yn;
                     const float w = y2 / (y2 + t.sigma2);
-                    acc = fmaf(w, w, acc);
+                    wgt[k * LV + v] = w;
                     noisy[k * LV + v] = ldexpf(noisy[k * LV + v] * w, -l);
                 }
-                part[k] = acc;
+            }
+            float part[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                float acc = 0.0f;
+                for (int k = 0; k < kp; ++k)
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const float w = wgt[k * LV + wiener_coeff(lane, rr)];
+                        acc = fmaf(w, w, acc);
+                    }
+                part[lane] = acc;
             }
             for (int mm = 16; mm >= 1; mm >>= 1) {  // xor-butterfly reduction, as __shfl_xor does
                 float nx[32];
