@@ -547,7 +547,7 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
             for (int k = 0; k < kp; ++k) xf3_fwd<true>(noisy + k * LV, t);
             ghaar_fwd(noisy, kp);
             // Wiener attenuation, elementwise; sum of W^2 in the kernel's order: lane
-            // (zh, y, x) of the warp owns two coefficients of every slot and chains
+            // (zh, y, x) of a warp owns two coefficients of every slot and chains
             // fma over (slot ascending, register 0 then 1); the 32 partial sums meet in
             // an xor butterfly.  Coefficient held by (lane, register): see wiener_coeff().
             float wgt[32 * LV];
@@ -561,22 +561,29 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
                     noisy[k * LV + v] = ldexpf(noisy[k * LV + v] * w, -l);
                 }
             }
-            float part[32];
-            for (int lane = 0; lane < 32; ++lane) {
-                float acc = 0.0f;
-                for (int k = 0; k < kp; ++k)
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const float w = wgt[k * LV + wiener_coeff(lane, rr)];
-                        acc = fmaf(w, w, acc);
-                    }
-                part[lane] = acc;
+            // one chain per 16-slot half of the group (the kernel gives each half to one warp
+            // of a pair when the group has 32 blocks); halves are added last
+            float half_sum[2] = {0.0f, 0.0f};
+            for (int h = 0; h * 16 < kp; ++h) {
+                float part[32];
+                for (int lane = 0; lane < 32; ++lane) {
+                    float acc = 0.0f;
+                    for (int k = h * 16; k < std::min(kp, h * 16 + 16); ++k)
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const float w = wgt[k * LV + wiener_coeff(lane, rr)];
+                            acc = fmaf(w, w, acc);
+                        }
+                    part[lane] = acc;
+                }
+                for (int mm = 16; mm >= 1; mm >>= 1) {  // xor-butterfly reduction, as __shfl_xor does
+                    float nx[32];
+                    for (int k = 0; k < 32; ++k) nx[k] = part[k] + part[k ^ mm];
+                    std::memcpy(part, nx, sizeof(nx));
+                }
+                half_sum[h] = part[0];
             }
-            for (int mm = 16; mm >= 1; mm >>= 1) {  // xor-butterfly reduction, as __shfl_xor does
-                float nx[32];
-                for (int k = 0; k < 32; ++k) nx[k] = part[k] + part[k ^ mm];
-                std::memcpy(part, nx, sizeof(nx));
-            }
-            weight = 1.0f / fmaxf(part[0], 1.0f);
+            const float sumw = kp > 16 ? half_sum[0] + half_sum[1] : half_sum[0];
+            weight = 1.0f / fmaxf(sumw, 1.0f);
             ghaar_inv(noisy, kp);
             for (int k = 0; k < kp; ++k) xf3_inv<true>(noisy + k * LV, t);
         }
