@@ -29,6 +29,7 @@ EXPORTS = (
     "b4d_quantize_u16",
     "b4d_tile_stats",
     "b4d_last_timings",
+    "b4d_stream",
     "b4d_last_match_stats",
     "b4d_measure_pipe_peaks",
 )
@@ -91,6 +92,7 @@ def load():
     lib.b4d_last_error.restype = ctypes.c_char_p
     lib.b4d_num_refs.restype = ctypes.c_int64
     lib.b4d_destroy.restype = None
+    lib.b4d_stream.restype = ctypes.c_void_p
     lib.b4d_default_profile.restype = None
     if lib.b4d_version() != ABI_VERSION:
         raise B4DLibraryError("libb4d.so ABI %d != binding ABI %d" % (lib.b4d_version(), ABI_VERSION))

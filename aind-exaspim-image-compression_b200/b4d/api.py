@@ -51,7 +51,7 @@ class BM4DProfile:
         self.search_window_wiener = (5, 5, 5)
         self.tau_match_wiener = 0.7693
         self.beta = 2.0  # Kaiser window parameter of the aggregation window
-        self.deterministic = False  # fixed-point, order-independent aggregation
+        self.deterministic = True  # always: fixed-point, order-independent aggregation (kept for compatibility)
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError("unknown profile field %r" % k)
@@ -319,6 +319,11 @@ class Denoiser:
         d = {k: getattr(st, k) for k, _ in _lib.Stats._fields_}
         return (d, hist) if return_hist else d
 
+    def stream_ptr(self):
+        """cudaStream_t of the handle (int): wrap it in torch.cuda.ExternalStream to
+        record CUDA events around calls."""
+        return int(self.lib.b4d_stream(self._h) or 0)
+
     def last_timings(self):
         ms = (ctypes.c_float * _lib.T_COUNT)()
         nl = (ctypes.c_int64 * _lib.T_COUNT)()
@@ -328,7 +333,7 @@ class Denoiser:
     def last_match_stats(self):
         out = (ctypes.c_uint64 * 4)()
         _lib.check(self.lib.b4d_last_match_stats(self._h, out))
-        return {"retry_refs": int(out[0]), "wide_tiles": int(out[1]), "slow_refs": int(out[2])}
+        return {"retry_refs": int(out[0]), "wide_tiles": int(out[1]), "slow_refs": int(out[2]), "byte_tiles": int(out[3])}
 
     def measure_pipe_peaks(self):
         out = (ctypes.c_double * 4)()

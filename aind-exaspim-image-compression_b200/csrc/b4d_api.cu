@@ -68,7 +68,7 @@ struct b4d_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     b4d_profile prof;
-    DevBuf in, u16, zf, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2;
+    DevBuf in, u16, zf, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2, s1, cells, tcls;
     cudaEvent_t ev[B4D_T_COUNT + 1];
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
@@ -284,6 +284,13 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     B4D_TRY(h->cnt.ensure((size_t)std::max(R1, R2)));
     B4D_TRY(h->basic.ensure((size_t)TV * sizeof(float)));
     B4D_TRY(h->s2.ensure((size_t)TV * sizeof(uint32_t)));
+    B4D_TRY(h->s1.ensure((size_t)TV * sizeof(uint32_t)));
+    {
+        const size_t ncell = (size_t)pl.nvol * ((pl.D + 3) / 4) * ((pl.H + 3) / 4) * ((pl.W + 3) / 4);
+        const size_t ntile = (size_t)pl.nvol * std::max(g1.tz, g2.tz) * g1.ty * g1.tx;
+        B4D_TRY(h->cells.ensure(ncell * sizeof(uint32_t)));
+        B4D_TRY(h->tcls.ensure(ntile * sizeof(uint32_t)));
+    }
     B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
     // Both stages aggregate in order-independent 2^32 fixed point (int64): the result does not
     // depend on scheduling, a slab equals the whole volume bit for bit, and the basic estimate
@@ -308,12 +315,15 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
 
     // ---- stage 1: hard thresholding
     B4D_TRY(zero_acc());
-    b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
+    b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), h->s1.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 2);
     MatchParams mp;
     mp.g = g1;
     mp.u = d_u;
     mp.s2 = h->s2.as<uint32_t>();
+    mp.s1 = h->s1.as<uint32_t>();
+    mp.cells = h->cells.as<uint32_t>();
+    mp.tcls = h->tcls.as<uint32_t>();
     mp.tau = tau1;
     mp.K = p.k_ht;
     mp.widx = h->widx.as<uint16_t>();
@@ -321,7 +331,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     mp.ssd_out = nullptr;
     mp.stats = h->stats.as<unsigned long long>();
     if (R1 > 0) b4d_launch_match(mp, p.search_ht, s);
-    clk.mark(B4D_T_MATCH1, 1);
+    clk.mark(B4D_T_MATCH1, 4);
     FilterParams fp;
     fp.g = g1;
     fp.zf = d_zf;
@@ -343,13 +353,13 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     // ---- stage 2: Wiener, matching on the basic estimate
     b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
     B4D_TRY(zero_acc());
-    b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
+    b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), h->s1.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 3);
     mp.g = g2;
     mp.tau = tau2;
     mp.K = p.k_wie;
     if (R2 > 0) b4d_launch_match(mp, p.search_wie, s);
-    clk.mark(B4D_T_MATCH2, 1);
+    clk.mark(B4D_T_MATCH2, 4);
     fp.g = g2;
     fp.basic = d_basic;
     fp.K = p.k_wie;
@@ -542,7 +552,7 @@ void b4d_destroy(b4d_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->numq, &h->denq, &h->basic, &h->out, &h->widx, &h->cnt,
-                      &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2})
+                      &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2, &h->s1, &h->cells, &h->tcls})
         b->release();
     for (auto &ev : h->ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -647,11 +657,17 @@ int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], 
     B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
     CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
     B4D_TRY(h->s2.ensure((size_t)V * sizeof(uint32_t)));
-    b4d_launch_block_energy(h->u16.as<uint16_t>(), h->s2.as<uint32_t>(), pl.D, pl.H, pl.W, 1, s);
+    B4D_TRY(h->s1.ensure((size_t)V * sizeof(uint32_t)));
+    B4D_TRY(h->cells.ensure((size_t)((pl.D + 3) / 4) * ((pl.H + 3) / 4) * ((pl.W + 3) / 4) * sizeof(uint32_t)));
+    B4D_TRY(h->tcls.ensure((size_t)g.tz * g.ty * g.tx * sizeof(uint32_t)));
+    b4d_launch_block_energy(h->u16.as<uint16_t>(), h->s2.as<uint32_t>(), h->s1.as<uint32_t>(), pl.D, pl.H, pl.W, 1, s);
     MatchParams mp;
     mp.g = g;
     mp.u = h->u16.as<uint16_t>();
     mp.s2 = h->s2.as<uint32_t>();
+    mp.s1 = h->s1.as<uint32_t>();
+    mp.cells = h->cells.as<uint32_t>();
+    mp.tcls = h->tcls.as<uint32_t>();
     B4D_TRY(tau_for(p.tau_ht, sigma, 1.0f, Ns, &mp.tau));
     mp.K = K;
     mp.widx = h->widx.as<uint16_t>();
@@ -661,7 +677,7 @@ int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], 
     StageClock clk(h);
     clk.mark(-1, 0);
     b4d_launch_match(mp, Ns, s);
-    clk.mark(B4D_T_MATCH1, 1);
+    clk.mark(B4D_T_MATCH1, 4);
     CU_TRY(cudaGetLastError());
     std::vector<uint16_t> hw((size_t)R * K);
     std::vector<uint32_t> hs((size_t)R * K);
@@ -828,7 +844,9 @@ int b4d_last_timings(b4d_handle *h, float ms[B4D_T_COUNT], int64_t launches[B4D_
     return 0;
 }
 
-// oracle-free diagnostics: [0] survivor-list fallbacks, [1] wide (uint64) tiles
+void *b4d_stream(b4d_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+// oracle-free diagnostics: [0] survivor-list retries, [1] wide (uint64) tiles, [2] slow refs, [3] byte tiles
 int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]) {
     if (!h || !out) return fail(B4D_ERR_INVALID, "NULL argument");
     for (int i = 0; i < 4; ++i) out[i] = h->match_stats[i];

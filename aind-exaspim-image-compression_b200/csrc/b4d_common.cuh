@@ -36,6 +36,10 @@ struct MatchParams {
     B4dGeom g;
     const uint16_t *u;   // matching image [nvol][D][H][W]
     const uint32_t *s2;  // block energies mod 2^32, same indexing (K0)
+    const uint32_t *s1;  // block sums, same indexing (K0; byte path)
+    uint32_t *cells;     // scratch: min | max << 16 per aligned 4^3 cell (NULL with tcls)
+    uint32_t *tcls;      // scratch: per matcher tile, 1 << 16 | min for byte tiles, 0 otherwise;
+                         // NULL disables the byte path
     uint32_t tau;        // acceptance threshold (SSD <= tau)
     int K;               // max group size
     uint16_t *widx;      // [R][K] window index of each match
@@ -56,7 +60,8 @@ struct FilterParams {
     long long *numq, *denq;      // 2^32 fixed-point accumulators (order independent)
 };
 
-void b4d_launch_block_energy(const uint16_t *u, uint32_t *s2, int D, int H, int W, int nvol, cudaStream_t s);
+void b4d_launch_block_energy(const uint16_t *u, uint32_t *s2, uint32_t *s1, int D, int H, int W, int nvol,
+                             cudaStream_t s);
 void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s);
 void b4d_launch_filter(const FilterParams &p, bool wiener, cudaStream_t s);
 void b4d_upload_tables(const B4dTables &t, cudaStream_t s);

@@ -24,6 +24,17 @@
 // padded so that the 32 rows a warp reads at once fall in 32 distinct banks
 // (bank = B * (Ns*dz + dy) mod 32 with B odd).
 //
+// Byte path.  A tile whose staged neighbourhood spans at most 255 counts (pure
+// background: noise only, or the smooth basic estimate of stage 2) is matched on
+// bytes: v - tile_min fits 8 bits, four voxel products go through one IDP.4A
+// (dp4a runs at the IMAD issue rate on sm_100a, measured by tools/mb_pipes.cu:
+// 4x the multiply-accumulate rate), candidates are cut out of the row words with
+// PRMT on the ALU pipe.  SSD = S2'(a) + S2'(b) - 2*sum(a'b') with the centred
+// energies S2' = S2 - 2m*S1 + 64m^2 rebuilt from the block sums S1 that K0 writes
+// beside S2.  Tiles are classified beforehand (k_cell_minmax, k_tile_class: a
+// conservative range over 4^3 cells); k_match<.., BYTE=true> takes the byte
+// tiles, k_match<.., false> the others, each exits at once on a foreign tile.
+//
 // Selection is exact and deterministic: key = SSD << KB | window index (unique),
 // rejected candidates get 0xFFFFFFFF.  Rows are visited centre-out so the good
 // matches arrive first; a running per-lane minimum (second minimum for K = 32)
@@ -31,6 +42,8 @@
 // <= B; only keys <= B are appended to a small per-warp survivor list, which is
 // rank-sorted at the end.  If the list overflows (adversarial key order) the warp
 // falls back to K rounds of "smallest key greater than the previous one".
+#include <algorithm>
+
 #include "b4d_common.cuh"
 
 namespace {
@@ -59,6 +72,15 @@ struct Geo {
     static constexpr int AC = AC0 + (((NS * BC) % 32 - AC0 % 32) + 32) % 32;
     static constexpr int S2_WORDS = EC * AC;
     static constexpr size_t SMEM = (((size_t)WIN_ELEMS * 2 + 15) & ~(size_t)15) + (size_t)S2_WORDS * 4;
+    // byte window: row stride RSW words (odd), plane stride PSW = NS*RSW (mod 32): the 32
+    // (dz, dy) rows a warp reads at once fall in 32 distinct banks
+    static constexpr int RW = (E + 3) / 4;     // words of a row that hold data
+    static constexpr int RSW = (RW + 1) | 1;   // > RW: the realignment reads one word past
+    static constexpr int PSW0 = E * RSW;
+    static constexpr int PSW = PSW0 + (((NS * RSW) % 32 - PSW0 % 32) + 32) % 32;
+    static constexpr int BWIN_WORDS = E * PSW;
+    static constexpr int NWR = (NS + 9) / 4;   // row words a lane loads: bytes [a, a + NS + 3), a <= 3
+    static constexpr size_t SMEM_B = (((size_t)BWIN_WORDS * 4 + 15) & ~(size_t)15) + (size_t)S2_WORDS * 4;
     // centre-out visiting order of the 32-unit groups: mc, mc+1, mc-1, mc+2, ...
     // packed 4 bits per entry so the device reads it with a shift and a mask
     static constexpr int order_at(int it) {
@@ -86,7 +108,7 @@ struct Geo {
 // for every origin with z <= D-4, y <= H-4, x <= W-4 (others are left untouched).
 // One thread per (z, y, 4 consecutive x): 16 rows of 7 values from L1/L2.
 __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict__ u, uint32_t *__restrict__ s2,
-                                                      int D, int H, int W, int nvol) {
+                                                      uint32_t *__restrict__ s1, int D, int H, int W, int nvol) {
     const int xq = (W - 3 + 3) / 4;
     const long long per_vol = (long long)(D - 3) * (H - 3) * xq;
     const long long total = per_vol * nvol;
@@ -99,18 +121,28 @@ __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict
         const int y = (int)(r % (H - 3)), z = (int)(r / (H - 3));
         const uint16_t *p = u + (long long)vol * D * H * W + ((long long)z * H + y) * W + x0;
         uint32_t s[4] = {0u, 0u, 0u, 0u};
+        uint32_t t[4] = {0u, 0u, 0u, 0u};  // block sums S1 (byte path)
         const int nx = min(7, W - x0);
 #pragma unroll
         for (int dz = 0; dz < 4; ++dz)
 #pragma unroll
             for (int dy = 0; dy < 4; ++dy) {
                 const uint16_t *row = p + ((long long)dz * H + dy) * W;
-                uint32_t q[7];
+                uint32_t q[7], l[7];
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
                     const uint32_t v = (k < nx) ? (uint32_t)__ldg(row + k) : 0u;
                     q[k] = v * v;
+                    l[k] = v;
                 }
+                const uint32_t m0 = l[0] + l[1] + l[2] + l[3];
+                const uint32_t m1 = m0 - l[0] + l[4];
+                const uint32_t m2 = m1 - l[1] + l[5];
+                const uint32_t m3 = m2 - l[2] + l[6];
+                t[0] += m0;
+                t[1] += m1;
+                t[2] += m2;
+                t[3] += m3;
                 const uint32_t w0 = q[0] + q[1] + q[2] + q[3];
                 const uint32_t w1 = w0 - q[0] + q[4];
                 const uint32_t w2 = w1 - q[1] + q[5];
@@ -120,11 +152,79 @@ __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict
                 s[2] += w2;
                 s[3] += w3;
             }
-        uint32_t *o = s2 + (long long)vol * D * H * W + ((long long)z * H + y) * W + x0;
+        const long long oo = (long long)vol * D * H * W + ((long long)z * H + y) * W + x0;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (x0 + k <= W - 4) o[k] = s[k];
+            if (x0 + k <= W - 4) {
+                s2[oo + k] = s[k];
+                s1[oo + k] = t[k];
+            }
     }
+}
+
+// ------------------------------------------------- tile classification ------
+// cells[vol][cz][cy][cx] = min | max << 16 over the in-volume voxels of the aligned 4^3 cell
+__global__ void __launch_bounds__(256) k_cell_minmax(const uint16_t *__restrict__ u, uint32_t *__restrict__ cells,
+                                                     int D, int H, int W, int nvol) {
+    const int cd = (D + 3) >> 2, ch = (H + 3) >> 2, cw = (W + 3) >> 2;
+    const long long total = (long long)nvol * cd * ch * cw;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        long long r = i;
+        const int cx = (int)(r % cw);
+        r /= cw;
+        const int cy = (int)(r % ch);
+        r /= ch;
+        const int cz = (int)(r % cd);
+        const int vol = (int)(r / cd);
+        const uint16_t *v = u + (long long)vol * D * H * W;
+        uint32_t mn = 0xFFFFu, mx = 0u;
+        for (int z = cz * 4; z < min(cz * 4 + 4, D); ++z)
+            for (int y = cy * 4; y < min(cy * 4 + 4, H); ++y) {
+                const uint16_t *row = v + ((long long)z * H + y) * W;
+                for (int x = cx * 4; x < min(cx * 4 + 4, W); ++x) {
+                    const uint32_t q = __ldg(row + x);
+                    mn = min(mn, q);
+                    mx = max(mx, q);
+                }
+            }
+        cells[i] = mn | (mx << 16);
+    }
+}
+// One warp per matcher tile: range over the cells that cover its staged neighbourhood
+// (a superset of it, hence conservative).  tcls[tile] = 1 << 16 | min when the range
+// fits a byte, else 0.
+template <int NS>
+__global__ void __launch_bounds__(256) k_tile_class(const uint32_t *__restrict__ cells, const B4dGeom g,
+                                                    uint32_t *__restrict__ tcls) {
+    using G = Geo<NS>;
+    const int lane = threadIdx.x & 31;
+    const long long tiles = (long long)g.nvol * g.tz * g.ty * g.tx;
+    const long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= tiles) return;
+    long long t = tile;
+    const int tx = (int)(t % g.tx);
+    t /= g.tx;
+    const int ty = (int)(t % g.ty);
+    t /= g.ty;
+    const int tz = (int)(t % g.tz);
+    const int vol = (int)(t / g.tz);
+    const int cd = (g.D + 3) >> 2, ch = (g.H + 3) >> 2, cw = (g.W + 3) >> 2;
+    const int bz = g.refz[tz * 4] - G::R, by = g.refy[ty * 4] - G::R, bx = g.refx[tx * 4] - G::R;
+    const int z0 = max(bz, 0) >> 2, z1 = min(bz + G::E - 1, g.D - 1) >> 2;
+    const int y0 = max(by, 0) >> 2, y1 = min(by + G::E - 1, g.H - 1) >> 2;
+    const int x0 = max(bx, 0) >> 2, x1 = min(bx + G::E - 1, g.W - 1) >> 2;
+    const int nz = z1 - z0 + 1, ny = y1 - y0 + 1, nx = x1 - x0 + 1;
+    uint32_t mn = 0xFFFFu, mx = 0u;
+    for (int i = lane; i < nz * ny * nx; i += 32) {
+        const int x = i % nx, y = (i / nx) % ny, z = i / (nx * ny);
+        const uint32_t c = __ldg(cells + (((long long)vol * cd + z0 + z) * ch + y0 + y) * cw + x0 + x);
+        mn = min(mn, c & 0xFFFFu);
+        mx = max(mx, c >> 16);
+    }
+    mn = __reduce_min_sync(B4D_FULL, mn);
+    mx = __reduce_max_sync(B4D_FULL, mx);
+    if (lane == 0) tcls[tile] = (mx >= mn && mx - mn <= 255u) ? ((1u << 16) | mn) : 0u;
 }
 
 // ------------------------------------------------------------ helpers -------
@@ -170,6 +270,37 @@ __device__ __forceinline__ void xcorr_row(const uint16_t *__restrict__ base, con
     }
 }
 
+// Byte path: cross terms of one (dz, dy) row of candidates from the byte window.
+// `base` points at the aligned word that holds byte wx0 of the first row, `sel` is the
+// PRMT selector of the run-time alignment wx0 & 3, refw[16] the reference block rows.
+template <int NS>
+__device__ __forceinline__ void bcorr_row(const uint32_t *__restrict__ base, uint32_t sel, const uint32_t (&refw)[16],
+                                          uint32_t (&acc)[NS]) {
+    using G = Geo<NS>;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) acc[j] = 0u;
+#pragma unroll
+    for (int z = 0; z < 4; ++z) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            uint32_t w[G::NWR], q[G::NWR - 1];
+#pragma unroll
+            for (int i = 0; i < G::NWR; ++i) w[i] = base[z * G::PSW + y * G::RSW + i];
+#pragma unroll
+            for (int i = 0; i < G::NWR - 1; ++i) q[i] = __byte_perm(w[i], w[i + 1], sel);  // bytes wx0 + 4i ..
+            const uint32_t r = refw[z * 4 + y];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const uint32_t c = (j & 3) == 0   ? q[j >> 2]
+                                   : (j & 3) == 1 ? __byte_perm(q[j >> 2], q[(j >> 2) + 1], 0x4321)
+                                   : (j & 3) == 2 ? __byte_perm(q[j >> 2], q[(j >> 2) + 1], 0x5432)
+                                                  : __byte_perm(q[j >> 2], q[(j >> 2) + 1], 0x6543);
+                acc[j] = __dp4a(c, r, acc[j]);
+            }
+        }
+    }
+}
+
 // Direct 64-bit SSDs for tiles whose value range is too wide for the modular
 // form.  Rare (bright structures above 8191 counts over background); compact.
 template <int NS>
@@ -197,14 +328,26 @@ __device__ __noinline__ void ssd_row_u64(const uint16_t *__restrict__ base, cons
     }
 }
 
-template <int NS, bool K32>
-__global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
+template <int NS, bool K32, bool BYTE>
+__global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchParams p) {
     using G = Geo<NS>;
     constexpr int R_ = G::R, E = G::E, EC = G::EC, KB = G::KB, UNITS = G::UNITS, ITERS = G::ITERS;
 
+    // tile class: byte tiles belong to the BYTE instantiation, all others to the general one
+    uint32_t tmin = 0;
+    if (p.tcls) {
+        const uint32_t cls = p.tcls[blockIdx.x];
+        if (BYTE != ((cls >> 16) != 0u)) return;
+        tmin = cls & 0xFFFFu;
+    } else if (BYTE) {
+        return;
+    }
+
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint16_t *s_win = reinterpret_cast<uint16_t *>(s_raw);
-    uint32_t *s_s2 = reinterpret_cast<uint32_t *>(s_raw + (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15));
+    uint32_t *s_bw = reinterpret_cast<uint32_t *>(s_raw);  // byte path: packed bytes
+    uint32_t *s_s2 = reinterpret_cast<uint32_t *>(
+        s_raw + (BYTE ? (((size_t)G::BWIN_WORDS * 4 + 15) & ~(size_t)15) : (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15)));
     __shared__ uint32_t s_surv[WARPS][CAP];
     __shared__ int s_cnt[WARPS];
     __shared__ uint32_t s_min, s_max;
@@ -229,7 +372,37 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
         s_max = 0u;
     }
     __syncthreads();
-    {
+    if (BYTE) {
+        // bytes v - tile_min (0 outside the volume), four per word
+        for (int i = threadIdx.x; i < E * E * G::RW; i += WARPS * 32) {
+            const int xw = i % G::RW, y = (i / G::RW) % E, z = i / (G::RW * E);
+            const int gz = bz + z, gy = by + y;
+            uint32_t packed = 0u;
+            if ((unsigned)gz < (unsigned)g.D && (unsigned)gy < (unsigned)g.H) {
+                const uint16_t *row = uv + ((long long)gz * g.H + gy) * g.W;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int gx = bx + 4 * xw + b;
+                    if (4 * xw + b < E && (unsigned)gx < (unsigned)g.W)
+                        packed |= (((uint32_t)row[gx] - tmin) & 0xFFu) << (8 * b);
+                }
+            }
+            s_bw[z * G::PSW + y * G::RSW + xw] = packed;
+        }
+        // centred block energies S2' = S2 - 2 m S1 + 64 m^2 (exact: S2' <= 64 * 255^2)
+        const uint32_t *__restrict__ s1v = p.s1 + (long long)vol * g.vol_stride;
+        for (int i = threadIdx.x; i < EC * EC * EC; i += WARPS * 32) {
+            const int x = i % EC, y = (i / EC) % EC, z = i / (EC * EC);
+            const int gz = bz + z, gy = by + y, gx = bx + x;
+            uint32_t v = 0;
+            if ((unsigned)gz <= (unsigned)(g.D - 4) && (unsigned)gy <= (unsigned)(g.H - 4) &&
+                (unsigned)gx <= (unsigned)(g.W - 4)) {
+                const long long a = ((long long)gz * g.H + gy) * g.W + gx;
+                v = s2v[a] - 2u * tmin * s1v[a] + 64u * tmin * tmin;
+            }
+            s_s2[z * G::AC + y * G::BC + x] = v;
+        }
+    } else {
         uint32_t mn = 0xFFFFFFFFu, mx = 0u;
         for (int i = threadIdx.x; i < E * E * E; i += WARPS * 32) {
             const int x = i % E, y = (i / E) % E, z = i / (E * E);
@@ -259,8 +432,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
         }
     }
     __syncthreads();
-    const bool narrow = (s_max - s_min) <= 8191u || s_max < s_min;
+    const bool narrow = BYTE || (s_max - s_min) <= 8191u || s_max < s_min;
     if (!narrow && threadIdx.x == 0 && p.stats) atomicAdd(&p.stats[1], 1ull);
+    if (BYTE && threadIdx.x == 0 && p.stats) atomicAdd(&p.stats[3], 1ull);
 
     const int K = p.K;
     const uint32_t tau = p.tau;
@@ -271,16 +445,31 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
         const int oz = g.refz[iz], oy = g.refy[iy], ox = g.refx[ix];
         const int wz0 = oz - R_ - bz, wy0 = oy - R_ - by, wx0 = ox - R_ - bx;  // window origin in the tile
         const uint16_t *refp = s_win + (wz0 + R_) * G::SZ + (wy0 + R_) * G::SY + (wx0 + R_);
-        uint32_t ref[B4D_LV];
+        uint32_t ref[BYTE ? 1 : B4D_LV];
+        uint32_t refw[BYTE ? 16 : 1];
         uint32_t s2ref = 0;
-        if (narrow) {
+        const uint32_t bsel = 0x3210u + 0x1111u * (uint32_t)(wx0 & 3);  // PRMT selector of the row alignment
+        if constexpr (BYTE) {
+            const int rx = wx0 + R_;
+            const uint32_t rsel = 0x3210u + 0x1111u * (uint32_t)(rx & 3);
 #pragma unroll
             for (int z = 0; z < 4; ++z)
 #pragma unroll
-                for (int y = 0; y < 4; ++y)
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) ref[(z * 4 + y) * 4 + x] = refp[z * G::SZ + y * G::SY + x];
+                for (int y = 0; y < 4; ++y) {
+                    const uint32_t *rw = s_bw + (wz0 + R_ + z) * G::PSW + (wy0 + R_ + y) * G::RSW + (rx >> 2);
+                    refw[z * 4 + y] = __byte_perm(rw[0], rw[1], rsel);
+                }
             s2ref = s_s2[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
+        } else {
+            if (narrow) {
+#pragma unroll
+                for (int z = 0; z < 4; ++z)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) ref[(z * 4 + y) * 4 + x] = refp[z * G::SZ + y * G::SY + x];
+                s2ref = s_s2[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
+            }
         }
         // valid dx range of candidates: cx = ox - R_ + j in [0, W-4]
         const int jlo = max(0, R_ - ox), jhi = min(NS - 1, g.W - 4 - ox + R_);
@@ -310,25 +499,40 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
                 uint32_t key[NS];
 #pragma unroll
                 for (int j = 0; j < NS; ++j) key[j] = B4D_INVALID_KEY;
-                if (uvalid) {
-                    const uint16_t *base = s_win + (wz0 + dz) * G::SZ + (wy0 + dy) * G::SY + wx0;
-                    if (narrow) {
+                if constexpr (BYTE) {
+                    if (uvalid) {
                         uint32_t acc[NS];
-                        xcorr_row<NS>(base, ref, acc);
+                        bcorr_row<NS>(s_bw + (wz0 + dz) * G::PSW + (wy0 + dy) * G::RSW + (wx0 >> 2), bsel, refw, acc);
                         const uint32_t *e = s_s2 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
 #pragma unroll
                         for (int j = 0; j < NS; ++j) {
-                            const uint32_t ssd = (e[j] + s2ref) - 2u * acc[j];  // exact: true SSD < 2^32
+                            const uint32_t ssd = (e[j] + s2ref) - 2u * acc[j];
                             const bool ok = ssd <= tau && j >= jlo && j <= jhi;
                             key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                         }
-                    } else {
-                        unsigned long long acc[NS];
-                        ssd_row_u64<NS>(base, refp, acc);
+                    }
+                } else {
+                    if (uvalid) {
+                        const uint16_t *base = s_win + (wz0 + dz) * G::SZ + (wy0 + dy) * G::SY + wx0;
+                        if (narrow) {
+                            uint32_t acc[NS];
+                            xcorr_row<NS>(base, ref, acc);
+                            const uint32_t *e = s_s2 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
 #pragma unroll
-                        for (int j = 0; j < NS; ++j) {
-                            const bool ok = acc[j] <= (unsigned long long)tau && j >= jlo && j <= jhi;
-                            key[j] = ok ? (((uint32_t)acc[j] << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                            for (int j = 0; j < NS; ++j) {
+                                const uint32_t ssd = (e[j] + s2ref) - 2u * acc[j];  // exact: true SSD < 2^32
+                                const bool ok = ssd <= tau && j >= jlo && j <= jhi;
+                                key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                            }
+                        } else {
+                            unsigned long long acc[NS];
+                            ssd_row_u64<NS>(base, refp, acc);
+#pragma unroll
+                            for (int j = 0; j < NS; ++j) {
+                                const bool ok = acc[j] <= (unsigned long long)tau && j >= jlo && j <= jhi;
+                                key[j] =
+                                    ok ? (((uint32_t)acc[j] << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                            }
                         }
                     }
                 }
@@ -431,28 +635,39 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p) {
     }
 }
 
+template <int NS, bool K32>
+void launch_k(const MatchParams &p, long long tiles, cudaStream_t s) {
+    using G = Geo<NS>;
+    if (p.tcls) {  // byte tiles first (cheap), then everything else
+        cudaFuncSetAttribute(k_match<NS, K32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_B);
+        k_match<NS, K32, true><<<(unsigned)tiles, WARPS * 32, G::SMEM_B, s>>>(p);
+    }
+    cudaFuncSetAttribute(k_match<NS, K32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    k_match<NS, K32, false><<<(unsigned)tiles, WARPS * 32, G::SMEM, s>>>(p);
+}
 template <int NS>
 void launch_ns(const MatchParams &p, cudaStream_t s) {
-    using G = Geo<NS>;
-    const size_t smem = G::SMEM;
     const long long tiles = (long long)p.g.nvol * p.g.tz * p.g.ty * p.g.tx;
-    if (p.K > 16) {
-        cudaFuncSetAttribute(k_match<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_match<NS, true><<<(unsigned)tiles, WARPS * 32, smem, s>>>(p);
-    } else {
-        cudaFuncSetAttribute(k_match<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_match<NS, false><<<(unsigned)tiles, WARPS * 32, smem, s>>>(p);
+    if (p.tcls) {
+        const long long cells = (long long)p.g.nvol * ((p.g.D + 3) / 4) * ((p.g.H + 3) / 4) * ((p.g.W + 3) / 4);
+        long long blocks = std::min<long long>((cells + 255) / 256, 148ll * 32);
+        k_cell_minmax<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, s>>>(p.u, p.cells, p.g.D, p.g.H, p.g.W,
+                                                                               p.g.nvol);
+        k_tile_class<NS><<<(unsigned)((tiles + 7) / 8), 256, 0, s>>>(p.cells, p.g, p.tcls);
     }
+    if (p.K > 16) launch_k<NS, true>(p, tiles, s);
+    else launch_k<NS, false>(p, tiles, s);
 }
 
 }  // namespace
 
-void b4d_launch_block_energy(const uint16_t *u, uint32_t *s2, int D, int H, int W, int nvol, cudaStream_t s) {
+void b4d_launch_block_energy(const uint16_t *u, uint32_t *s2, uint32_t *s1, int D, int H, int W, int nvol,
+                             cudaStream_t s) {
     const long long total = (long long)(D - 3) * (H - 3) * ((W - 3 + 3) / 4) * nvol;
     long long blocks = (total + 255) / 256;
     if (blocks > 148ll * 64) blocks = 148ll * 64;
     if (blocks < 1) blocks = 1;
-    k_block_energy<<<(unsigned)blocks, 256, 0, s>>>(u, s2, D, H, W, nvol);
+    k_block_energy<<<(unsigned)blocks, 256, 0, s>>>(u, s2, s1, D, H, W, nvol);
 }
 
 void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s) {

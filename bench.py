@@ -154,6 +154,16 @@ def workload_config(S, halo):
     }
 
 
+def traffic_per_launch(size, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_match launch, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get("k_match", {}).get("%d^3/%d" % (size, world))
+    except Exception:
+        return None
+
+
 def cpu_port_throughput(sample_shape, repeats=1):
     """voxels/s of the CPU oracle (float32 path, OpenMP over all host cores)."""
     from oracle import np_oracle
@@ -287,14 +297,18 @@ def main():
         del y
     barrier()
 
-    # ---- timed: resident inputs
+    # ---- timed: resident inputs.  CUDA events on the library's own stream (every kernel and
+    # copy of the handle is enqueued there; torch.cuda.Event only sees the stream it is
+    # recorded on), bracketed by barrier + synchronize.
+    ext = torch.cuda.ExternalStream(dn.stream_ptr(), device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     fam = {}
     launches = 0
     barrier()
-    t = time.perf_counter()
+    ev0.record(ext)
     for _ in range(args.steps):
         stats, y = step_resident()
         del y
@@ -303,19 +317,21 @@ def main():
             fam[k] = fam.get(k, 0.0) + ms
             launches += nl
         launches += 1  # histogram kernel
+    ev1.record(ext)
     barrier()
-    dt = time.perf_counter() - t
+    dt = ev0.elapsed_time(ev1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
     mstats = dn.last_match_stats()
 
     # ---- timed: end to end with host buffers
     step_e2e()
     barrier()
-    t = time.perf_counter()
+    ev0.record(ext)
     for _ in range(args.steps):
         step_e2e()
+    ev1.record(ext)
     barrier()
-    dt_e2e = time.perf_counter() - t
+    dt_e2e = ev0.elapsed_time(ev1) * 1e-3
 
     times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -346,9 +362,10 @@ def main():
             "match": {"bound": "int32", "achieved": achieved / 1e12, "peak": peaks["sub_mad"] / 1e12, "unit": "TOP/s",
                       "frac": achieved / peaks["sub_mad"] if peaks["sub_mad"] else None,
                       "ms_per_launch": t_match * 1e3},
-            "normalise": {"bound": "hbm", "achieved": 12.0 * slab_vox / t_norm / 1e9 if t_norm > 0 else None,
+            # 2 x int64 accumulators + float32 fallback read, float32 written: 24 B/voxel
+            "normalise": {"bound": "hbm", "achieved": 24.0 * slab_vox / t_norm / 1e9 if t_norm > 0 else None,
                           "peak": hbm_peak, "unit": "GB/s",
-                          "frac": 12.0 * slab_vox / t_norm / 1e9 / hbm_peak if t_norm > 0 else None,
+                          "frac": 24.0 * slab_vox / t_norm / 1e9 / hbm_peak if t_norm > 0 else None,
                           "ms_per_launch": t_norm * 1e3},
             "filter_ht_ms": fam.get("filter1", 0.0) / args.steps,
             "filter_wiener_ms": fam.get("filter2", 0.0) / args.steps,
@@ -364,12 +381,12 @@ def main():
             "higher_is_better": True,
             "scaling": "strong",
             "vs_baseline": None,
-            "dtype": "int32 matching + f32 filtering",
+            "dtype": "int32+f32",
             "data": "synthetic",
             "config": dict(
                 workload_config(S, halo),
                 l2="inputs larger than L2 (%.2f GiB slab per rank)" % (slab_pin.numel() * 2 / 2 ** 30),
-                timing="wall clock around synchronous C-ABI calls between cuda synchronize + barrier, max over ranks",
+                timing="CUDA events on the library stream around the K steps, between barrier + synchronize, max over ranks",
             ),
             "e2e": {"value": V * args.steps / dt_e2e, "unit": "voxels/s",
                     "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1])},
@@ -377,7 +394,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "int32", "achieved": achieved / 1e12, "peak": peaks["sub_mad"] / 1e12,
                          "unit": "TOP/s", "frac": achieved / peaks["sub_mad"] if peaks["sub_mad"] else None,
-                         "traffic": None,
+                         "traffic": traffic_per_launch(S, world),
                          "kernel": "k_match<11> (stage-1 and stage-2 launches averaged)",
                          "peak_source": "shipped microbenchmark, dependent (sub, mad) pairs, measured in this run"},
             "roofline_kernels": kernels,

@@ -60,7 +60,8 @@ typedef struct b4d_profile {
     int32_t k_ht;           /* max group size, stage 1 (power of two, <= 32)           */
     int32_t k_wie;          /* max group size, stage 2 (power of two, <= 32)           */
     int32_t stages;         /* 1 = hard-threshold stage only, 2 = + Wiener stage       */
-    int32_t deterministic;  /* 1 = order-independent fixed-point aggregation           */
+    int32_t deterministic;  /* kept for ABI stability: aggregation is ALWAYS order-      *
+                             * independent 2^32 fixed point (bit-reproducible)          */
     int32_t reserved0;
     float tau_ht;           /* match acceptance: SSD <= floor(tau*sigma^2*L^3)         */
     float tau_wie;
@@ -152,8 +153,15 @@ int b4d_tile_stats(b4d_handle *h, const uint16_t *in, int64_t n, double pct, b4d
 #define B4D_T_COUNT 8
 int b4d_last_timings(b4d_handle *h, float ms[B4D_T_COUNT], int64_t launches[B4D_T_COUNT]);
 
+/* The CUDA stream (cudaStream_t, as void *) every kernel and copy of this handle is
+ * enqueued on — for callers that time with CUDA events or order their own work after
+ * a call.  NULL for the CPU oracle build. */
+void *b4d_stream(b4d_handle *h);
+
 /* Diagnostics of the last matching launch(es): out[0] = reference blocks that
- * took the survivor-list overflow fallback, out[1] = tiles on the uint64 path. */
+ * took the survivor-list overflow fallback, out[1] = tiles on the uint64 path,
+ * out[2] = reference blocks on the exact-but-slow selection, out[3] = tiles matched
+ * on the byte (dp4a) path. */
 int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]);
 
 /* Measured issue-rate peaks on this device (shipped microbenchmark):

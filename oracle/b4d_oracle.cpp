@@ -886,6 +886,7 @@ int b4d_quantize_u16(b4d_handle *, const float *in, int64_t n, float offset_sub,
 int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *, int64_t *, int) {
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }
+void *b4d_stream(b4d_handle *) { return nullptr; }
 int b4d_last_timings(b4d_handle *, float *, int64_t *) {
     return fail(B4D_ERR_UNSUPPORTED, "no device timings in the oracle");
 }
