@@ -16,6 +16,7 @@ from .api import (  # noqa: F401
     quantize,
     tile_stats,
 )
+from .cache import load_patch_cache, write_patch_cache  # noqa: F401
 from .sharding import denoise_volume_sharded, merge_histograms, slab_plan, stats_from_hist  # noqa: F401
 
 __all__ = [
@@ -33,4 +34,6 @@ __all__ = [
     "denoise_volume_sharded",
     "merge_histograms",
     "stats_from_hist",
+    "write_patch_cache",
+    "load_patch_cache",
 ]

@@ -68,7 +68,7 @@ struct b4d_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     b4d_profile prof;
-    DevBuf in, u16, zf, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2, s1, cells, tcls;
+    DevBuf in, u16, zf, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2, cells, tcls;
     cudaEvent_t ev[B4D_T_COUNT + 1];
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
@@ -283,8 +283,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     B4D_TRY(h->widx.ensure((size_t)std::max(R1, R2) * Kmax * sizeof(uint16_t)));
     B4D_TRY(h->cnt.ensure((size_t)std::max(R1, R2)));
     B4D_TRY(h->basic.ensure((size_t)TV * sizeof(float)));
-    B4D_TRY(h->s2.ensure((size_t)TV * sizeof(uint32_t)));
-    B4D_TRY(h->s1.ensure((size_t)TV * sizeof(uint32_t)));
+    B4D_TRY(h->s2.ensure((size_t)TV * sizeof(uint2)));
     {
         const size_t ncell = (size_t)pl.nvol * ((pl.D + 3) / 4) * ((pl.H + 3) / 4) * ((pl.W + 3) / 4);
         const size_t ntile = (size_t)pl.nvol * std::max(g1.tz, g2.tz) * g1.ty * g1.tx;
@@ -315,13 +314,12 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
 
     // ---- stage 1: hard thresholding
     B4D_TRY(zero_acc());
-    b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), h->s1.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
+    b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 2);
     MatchParams mp;
     mp.g = g1;
     mp.u = d_u;
-    mp.s2 = h->s2.as<uint32_t>();
-    mp.s1 = h->s1.as<uint32_t>();
+    mp.s21 = h->s2.as<uint2>();
     mp.cells = h->cells.as<uint32_t>();
     mp.tcls = h->tcls.as<uint32_t>();
     mp.tau = tau1;
@@ -353,7 +351,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     // ---- stage 2: Wiener, matching on the basic estimate
     b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
     B4D_TRY(zero_acc());
-    b4d_launch_block_energy(d_u, h->s2.as<uint32_t>(), h->s1.as<uint32_t>(), pl.D, pl.H, pl.W, pl.nvol, s);
+    b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 3);
     mp.g = g2;
     mp.tau = tau2;
@@ -552,7 +550,7 @@ void b4d_destroy(b4d_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->numq, &h->denq, &h->basic, &h->out, &h->widx, &h->cnt,
-                      &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2, &h->s1, &h->cells, &h->tcls})
+                      &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2, &h->cells, &h->tcls})
         b->release();
     for (auto &ev : h->ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -656,16 +654,14 @@ int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], 
     B4D_TRY(h->ssd.ensure((size_t)R * K * sizeof(uint32_t)));
     B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
     CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
-    B4D_TRY(h->s2.ensure((size_t)V * sizeof(uint32_t)));
-    B4D_TRY(h->s1.ensure((size_t)V * sizeof(uint32_t)));
+    B4D_TRY(h->s2.ensure((size_t)V * sizeof(uint2)));
     B4D_TRY(h->cells.ensure((size_t)((pl.D + 3) / 4) * ((pl.H + 3) / 4) * ((pl.W + 3) / 4) * sizeof(uint32_t)));
     B4D_TRY(h->tcls.ensure((size_t)g.tz * g.ty * g.tx * sizeof(uint32_t)));
-    b4d_launch_block_energy(h->u16.as<uint16_t>(), h->s2.as<uint32_t>(), h->s1.as<uint32_t>(), pl.D, pl.H, pl.W, 1, s);
+    b4d_launch_block_energy(h->u16.as<uint16_t>(), h->s2.as<uint2>(), pl.D, pl.H, pl.W, 1, s);
     MatchParams mp;
     mp.g = g;
     mp.u = h->u16.as<uint16_t>();
-    mp.s2 = h->s2.as<uint32_t>();
-    mp.s1 = h->s1.as<uint32_t>();
+    mp.s21 = h->s2.as<uint2>();
     mp.cells = h->cells.as<uint32_t>();
     mp.tcls = h->tcls.as<uint32_t>();
     B4D_TRY(tau_for(p.tau_ht, sigma, 1.0f, Ns, &mp.tau));

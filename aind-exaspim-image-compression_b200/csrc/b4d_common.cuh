@@ -35,8 +35,7 @@ struct B4dTables {
 struct MatchParams {
     B4dGeom g;
     const uint16_t *u;   // matching image [nvol][D][H][W]
-    const uint32_t *s2;  // block energies mod 2^32, same indexing (K0)
-    const uint32_t *s1;  // block sums, same indexing (K0; byte path)
+    const uint2 *s21;    // per block origin (K0): .x = energy sum(v^2) mod 2^32, .y = sum(v)
     uint32_t *cells;     // scratch: min | max << 16 per aligned 4^3 cell (NULL with tcls)
     uint32_t *tcls;      // scratch: per matcher tile, 1 << 16 | min for byte tiles, 0 otherwise;
                          // NULL disables the byte path
@@ -60,8 +59,7 @@ struct FilterParams {
     long long *numq, *denq;      // 2^32 fixed-point accumulators (order independent)
 };
 
-void b4d_launch_block_energy(const uint16_t *u, uint32_t *s2, uint32_t *s1, int D, int H, int W, int nvol,
-                             cudaStream_t s);
+void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s);
 void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s);
 void b4d_launch_filter(const FilterParams &p, bool wiener, cudaStream_t s);
 void b4d_upload_tables(const B4dTables &t, cudaStream_t s);

@@ -35,6 +35,13 @@
 // conservative range over 4^3 cells); k_match<.., BYTE=true> takes the byte
 // tiles, k_match<.., false> the others, each exits at once on a foreign tile.
 //
+// Reference-byte path (general kernel).  When the 64 voxels of the REFERENCE block span
+// at most 255 counts (almost every block that is not on a bright edge), r' = r - r_min
+// fits a byte while the candidates stay 16-bit: sum(a*r) = sum(a*r') + r_min*S1(a), and
+// sum(a*r') runs through IDP.2A (u16 x u8, two products per instruction at the IMAD issue
+// rate) on the pair words of the uint16 window.  Other references of a narrow tile keep
+// the IMAD path; wide tiles the 64-bit path.
+//
 // Selection is exact and deterministic: key = SSD << KB | window index (unique),
 // rejected candidates get 0xFFFFFFFF.  Rows are visited centre-out so the good
 // matches arrive first; a running per-lane minimum (second minimum for K = 32)
@@ -71,7 +78,7 @@ struct Geo {
     static constexpr int AC0 = EC * BC;
     static constexpr int AC = AC0 + (((NS * BC) % 32 - AC0 % 32) + 32) % 32;
     static constexpr int S2_WORDS = EC * AC;
-    static constexpr size_t SMEM = (((size_t)WIN_ELEMS * 2 + 15) & ~(size_t)15) + (size_t)S2_WORDS * 4;
+    static constexpr size_t SMEM = (((size_t)WIN_ELEMS * 2 + 15) & ~(size_t)15) + (size_t)S2_WORDS * 8;  // S2 + S1
     // byte window: row stride RSW words (odd), plane stride PSW = NS*RSW (mod 32): the 32
     // (dz, dy) rows a warp reads at once fall in 32 distinct banks
     static constexpr int RW = (E + 3) / 4;     // words of a row that hold data
@@ -104,11 +111,12 @@ struct Geo {
 };
 
 // ------------------------------------------------------------------ K0 ------
-// S2[z][y][x] = sum over the 4x4x4 block at origin (z,y,x) of u^2, modulo 2^32,
-// for every origin with z <= D-4, y <= H-4, x <= W-4 (others are left untouched).
+// For every block origin (z,y,x) with z <= D-4, y <= H-4, x <= W-4 (others are left
+// untouched): S2 = sum over the 4x4x4 block of u^2 (exact, < 2^38) and S1 = sum of u
+// (< 2^22), packed as uint2 {S2 mod 2^32, S1 | (S2 >> 32) << 24}.
 // One thread per (z, y, 4 consecutive x): 16 rows of 7 values from L1/L2.
-__global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict__ u, uint32_t *__restrict__ s2,
-                                                      uint32_t *__restrict__ s1, int D, int H, int W, int nvol) {
+__global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict__ u, uint2 *__restrict__ s21, int D,
+                                                      int H, int W, int nvol) {
     const int xq = (W - 3 + 3) / 4;
     const long long per_vol = (long long)(D - 3) * (H - 3) * xq;
     const long long total = per_vol * nvol;
@@ -120,8 +128,8 @@ __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict
         r /= xq;
         const int y = (int)(r % (H - 3)), z = (int)(r / (H - 3));
         const uint16_t *p = u + (long long)vol * D * H * W + ((long long)z * H + y) * W + x0;
-        uint32_t s[4] = {0u, 0u, 0u, 0u};
-        uint32_t t[4] = {0u, 0u, 0u, 0u};  // block sums S1 (byte path)
+        unsigned long long s[4] = {0ull, 0ull, 0ull, 0ull};  // block energies (< 2^38)
+        uint32_t t[4] = {0u, 0u, 0u, 0u};                    // block sums S1 (< 2^22)
         const int nx = min(7, W - x0);
 #pragma unroll
         for (int dz = 0; dz < 4; ++dz)
@@ -132,9 +140,17 @@ __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
                     const uint32_t v = (k < nx) ? (uint32_t)__ldg(row + k) : 0u;
-                    q[k] = v * v;
+                    q[k] = v * v;  // < 2^32
                     l[k] = v;
                 }
+                const unsigned long long w0 = (unsigned long long)q[0] + q[1] + q[2] + q[3];
+                const unsigned long long w1 = w0 - q[0] + q[4];
+                const unsigned long long w2 = w1 - q[1] + q[5];
+                const unsigned long long w3 = w2 - q[2] + q[6];
+                s[0] += w0;
+                s[1] += w1;
+                s[2] += w2;
+                s[3] += w3;
                 const uint32_t m0 = l[0] + l[1] + l[2] + l[3];
                 const uint32_t m1 = m0 - l[0] + l[4];
                 const uint32_t m2 = m1 - l[1] + l[5];
@@ -143,22 +159,12 @@ __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict
                 t[1] += m1;
                 t[2] += m2;
                 t[3] += m3;
-                const uint32_t w0 = q[0] + q[1] + q[2] + q[3];
-                const uint32_t w1 = w0 - q[0] + q[4];
-                const uint32_t w2 = w1 - q[1] + q[5];
-                const uint32_t w3 = w2 - q[2] + q[6];
-                s[0] += w0;
-                s[1] += w1;
-                s[2] += w2;
-                s[3] += w3;
             }
         const long long oo = (long long)vol * D * H * W + ((long long)z * H + y) * W + x0;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (x0 + k <= W - 4) {
-                s2[oo + k] = s[k];
-                s1[oo + k] = t[k];
-            }
+            if (x0 + k <= W - 4)  // .x = S2 mod 2^32; .y = S1 | (S2 >> 32) << 24
+                s21[oo + k] = make_uint2((uint32_t)s[k], t[k] | ((uint32_t)(s[k] >> 32) << 24));
     }
 }
 
@@ -246,30 +252,6 @@ __device__ __forceinline__ uint32_t kth_smallest32(uint32_t v, int kth, int lane
     return __shfl_sync(B4D_FULL, v, kth);
 }
 
-// Cross terms sum(a*b) of one (dz, dy) row of candidates, all NS dx positions.
-template <int NS>
-__device__ __forceinline__ void xcorr_row(const uint16_t *__restrict__ base, const uint32_t (&ref)[B4D_LV],
-                                          uint32_t (&acc)[NS]) {
-    using G = Geo<NS>;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) acc[j] = 0u;
-#pragma unroll
-    for (int z = 0; z < 4; ++z) {
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            uint32_t v[NS + 3];
-#pragma unroll
-            for (int i = 0; i < NS + 3; ++i) v[i] = base[z * G::SZ + y * G::SY + i];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const uint32_t r = ref[(z * 4 + y) * 4 + x];
-#pragma unroll
-                for (int j = 0; j < NS; ++j) acc[j] = v[x + j] * r + acc[j];
-            }
-        }
-    }
-}
-
 // Byte path: cross terms of one (dz, dy) row of candidates from the byte window.
 // `base` points at the aligned word that holds byte wx0 of the first row, `sel` is the
 // PRMT selector of the run-time alignment wx0 & 3, refw[16] the reference block rows.
@@ -301,28 +283,34 @@ __device__ __forceinline__ void bcorr_row(const uint32_t *__restrict__ base, uin
     }
 }
 
-// Direct 64-bit SSDs for tiles whose value range is too wide for the modular
-// form.  Rare (bright structures above 8191 counts over background); compact.
+// Reference-byte path: sum(a * r') of one (dz, dy) row of candidates; a = uint16 window,
+// r' = reference bytes (rw[16], one word per block row).  `base` = aligned word that holds
+// window element wx0 - P of the first row, P = wx0 & 1; `sel` = PRMT selector that realigns
+// two neighbouring words by P elements (0x3210 or 0x5432).
 template <int NS>
-__device__ __noinline__ void ssd_row_u64(const uint16_t *__restrict__ base, const uint16_t *__restrict__ refp,
-                                         unsigned long long *acc) {
+__device__ __forceinline__ void r8corr_row(const uint32_t *__restrict__ base, uint32_t sel, const uint32_t (&rw)[16],
+                                           uint32_t (&acc)[NS]) {
     using G = Geo<NS>;
-    for (int j = 0; j < NS; ++j) acc[j] = 0ull;
-#pragma unroll 1
-    for (int z = 0; z < 4; ++z) {
-#pragma unroll 1
-        for (int y = 0; y < 4; ++y) {
-            const uint16_t *row = base + z * G::SZ + y * G::SY;
-            const uint16_t *rr = refp + z * G::SZ + y * G::SY;
+    constexpr int NA = (NS + 4) / 2;  // pair words (v[2i], v[2i+1]) covering elements [0, NS + 3)
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const int r = rr[x];
-#pragma unroll 1
-                for (int j = 0; j < NS; ++j) {
-                    const int d = (int)row[x + j] - r;
-                    const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
-                    acc[j] += (unsigned long long)ad * ad;
-                }
+    for (int j = 0; j < NS; ++j) acc[j] = 0u;
+#pragma unroll
+    for (int z = 0; z < 4; ++z) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            uint32_t w[NA + 1], al[NA];
+#pragma unroll
+            for (int i = 0; i < NA + 1; ++i) w[i] = base[z * G::AW + y * G::BW + i];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) al[i] = __byte_perm(w[i], w[i + 1], sel);
+            const uint32_t r = rw[z * 4 + y];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                // pair words (v[j], v[j+1]) and (v[j+2], v[j+3])
+                const uint32_t p0 = (j & 1) == 0 ? al[j / 2] : __byte_perm(al[j / 2], al[j / 2 + 1], 0x5432);
+                const uint32_t p1 = (j & 1) == 0 ? al[j / 2 + 1] : __byte_perm(al[j / 2 + 1], al[j / 2 + 2], 0x5432);
+                acc[j] = __dp2a_lo(p0, r, acc[j]);
+                acc[j] = __dp2a_hi(p1, r, acc[j]);
             }
         }
     }
@@ -348,6 +336,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     uint32_t *s_bw = reinterpret_cast<uint32_t *>(s_raw);  // byte path: packed bytes
     uint32_t *s_s2 = reinterpret_cast<uint32_t *>(
         s_raw + (BYTE ? (((size_t)G::BWIN_WORDS * 4 + 15) & ~(size_t)15) : (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15)));
+    uint32_t *s_s1 = s_s2 + G::S2_WORDS;  // general kernel only: block sums S1
     __shared__ uint32_t s_surv[WARPS][CAP];
     __shared__ int s_cnt[WARPS];
     __shared__ uint32_t s_min, s_max;
@@ -365,70 +354,65 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     const int iz0 = tz * 4, iy0 = ty * 4, ix0 = tx * 4;
     const int bz = g.refz[iz0] - R_, by = g.refy[iy0] - R_, bx = g.refx[ix0] - R_;
     const uint16_t *__restrict__ uv = p.u + (long long)vol * g.vol_stride;
-    const uint32_t *__restrict__ s2v = p.s2 + (long long)vol * g.vol_stride;
+    const uint2 *__restrict__ s21v = p.s21 + (long long)vol * g.vol_stride;
 
     if (threadIdx.x == 0) {
         s_min = 0xFFFFFFFFu;
         s_max = 0u;
     }
     __syncthreads();
-    if (BYTE) {
-        // bytes v - tile_min (0 outside the volume), four per word
-        for (int i = threadIdx.x; i < E * E * G::RW; i += WARPS * 32) {
-            const int xw = i % G::RW, y = (i / G::RW) % E, z = i / (G::RW * E);
+    // Staging, one row per warp iteration, lanes along x (coalesced, several rows in flight).
+    {
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+        const int gx = bx + lane;
+        const bool xin = lane < E && (unsigned)gx < (unsigned)g.W;
+#pragma unroll 4
+        for (int row = warp; row < E * E; row += WARPS) {
+            const int z = row / E, y = row - z * E;
             const int gz = bz + z, gy = by + y;
-            uint32_t packed = 0u;
-            if ((unsigned)gz < (unsigned)g.D && (unsigned)gy < (unsigned)g.H) {
-                const uint16_t *row = uv + ((long long)gz * g.H + gy) * g.W;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int gx = bx + 4 * xw + b;
-                    if (4 * xw + b < E && (unsigned)gx < (unsigned)g.W)
-                        packed |= (((uint32_t)row[gx] - tmin) & 0xFFu) << (8 * b);
+            uint32_t v = 0;
+            const bool in = xin && (unsigned)gz < (unsigned)g.D && (unsigned)gy < (unsigned)g.H;
+            if (in) v = uv[((long long)gz * g.H + gy) * g.W + gx];
+            if (BYTE) {
+                // bytes v - tile_min (0 outside the volume), four per word
+                uint32_t bt = in ? ((v - tmin) & 0xFFu) : 0u;
+                bt |= __shfl_down_sync(B4D_FULL, bt, 1) << 8;
+                bt |= __shfl_down_sync(B4D_FULL, bt, 2) << 16;
+                if ((lane & 3) == 0 && lane < 4 * G::RW) s_bw[z * G::PSW + y * G::RSW + (lane >> 2)] = bt;
+            } else {
+                if (in) {
+                    mn = min(mn, v);
+                    mx = max(mx, v);
+                }
+                if (lane < E) s_win[z * G::SZ + y * G::SY + lane] = (uint16_t)v;
+            }
+        }
+        const bool cin = lane < EC && (unsigned)gx <= (unsigned)(g.W - 4);
+        const uint32_t m2 = 2u * tmin, m64 = 64u * tmin * tmin;
+#pragma unroll 4
+        for (int row = warp; row < EC * EC; row += WARPS) {
+            const int z = row / EC, y = row - z * EC;
+            const int gz = bz + z, gy = by + y;
+            uint2 v = make_uint2(0u, 0u);
+            if (cin && (unsigned)gz <= (unsigned)(g.D - 4) && (unsigned)gy <= (unsigned)(g.H - 4))
+                v = s21v[((long long)gz * g.H + gy) * g.W + gx];
+            if (lane < EC) {
+                if (BYTE) {
+                    // centred block energies S2' = S2 - 2 m S1 + 64 m^2 (exact: S2' <= 64 * 255^2)
+                    s_s2[z * G::AC + y * G::BC + lane] = (v.x | v.y) ? v.x - m2 * (v.y & 0xFFFFFFu) + m64 : 0u;
+                } else {
+                    s_s2[z * G::AC + y * G::BC + lane] = v.x;
+                    s_s1[z * G::AC + y * G::BC + lane] = v.y;
                 }
             }
-            s_bw[z * G::PSW + y * G::RSW + xw] = packed;
         }
-        // centred block energies S2' = S2 - 2 m S1 + 64 m^2 (exact: S2' <= 64 * 255^2)
-        const uint32_t *__restrict__ s1v = p.s1 + (long long)vol * g.vol_stride;
-        for (int i = threadIdx.x; i < EC * EC * EC; i += WARPS * 32) {
-            const int x = i % EC, y = (i / EC) % EC, z = i / (EC * EC);
-            const int gz = bz + z, gy = by + y, gx = bx + x;
-            uint32_t v = 0;
-            if ((unsigned)gz <= (unsigned)(g.D - 4) && (unsigned)gy <= (unsigned)(g.H - 4) &&
-                (unsigned)gx <= (unsigned)(g.W - 4)) {
-                const long long a = ((long long)gz * g.H + gy) * g.W + gx;
-                v = s2v[a] - 2u * tmin * s1v[a] + 64u * tmin * tmin;
+        if (!BYTE) {
+            mn = __reduce_min_sync(B4D_FULL, mn);
+            mx = __reduce_max_sync(B4D_FULL, mx);
+            if (lane == 0) {
+                atomicMin(&s_min, mn);
+                atomicMax(&s_max, mx);
             }
-            s_s2[z * G::AC + y * G::BC + x] = v;
-        }
-    } else {
-        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-        for (int i = threadIdx.x; i < E * E * E; i += WARPS * 32) {
-            const int x = i % E, y = (i / E) % E, z = i / (E * E);
-            const int gz = bz + z, gy = by + y, gx = bx + x;
-            uint32_t v = 0;
-            if ((unsigned)gz < (unsigned)g.D && (unsigned)gy < (unsigned)g.H && (unsigned)gx < (unsigned)g.W) {
-                v = uv[((long long)gz * g.H + gy) * g.W + gx];
-                mn = min(mn, v);
-                mx = max(mx, v);
-            }
-            s_win[z * G::SZ + y * G::SY + x] = (uint16_t)v;
-        }
-        for (int i = threadIdx.x; i < EC * EC * EC; i += WARPS * 32) {
-            const int x = i % EC, y = (i / EC) % EC, z = i / (EC * EC);
-            const int gz = bz + z, gy = by + y, gx = bx + x;
-            uint32_t v = 0;
-            if ((unsigned)gz <= (unsigned)(g.D - 4) && (unsigned)gy <= (unsigned)(g.H - 4) &&
-                (unsigned)gx <= (unsigned)(g.W - 4))
-                v = s2v[((long long)gz * g.H + gy) * g.W + gx];
-            s_s2[z * G::AC + y * G::BC + x] = v;
-        }
-        mn = __reduce_min_sync(B4D_FULL, mn);
-        mx = __reduce_max_sync(B4D_FULL, mx);
-        if (lane == 0) {
-            atomicMin(&s_min, mn);
-            atomicMax(&s_max, mx);
         }
     }
     __syncthreads();
@@ -445,9 +429,12 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
         const int oz = g.refz[iz], oy = g.refy[iy], ox = g.refx[ix];
         const int wz0 = oz - R_ - bz, wy0 = oy - R_ - by, wx0 = ox - R_ - bx;  // window origin in the tile
         const uint16_t *refp = s_win + (wz0 + R_) * G::SZ + (wy0 + R_) * G::SY + (wx0 + R_);
-        uint32_t ref[BYTE ? 1 : B4D_LV];
-        uint32_t refw[BYTE ? 16 : 1];
+        // reference block as bytes: BYTE kernel one word per row; general kernel low bytes of
+        // r - r_min in [0, 16) and, when the block spans more than 255 counts, high bytes in [16, 32)
+        uint32_t refw[BYTE ? 16 : 32];
         uint32_t s2ref = 0;
+        uint32_t rmin = 0, s1ref = 0;
+        int npass = 1;
         const uint32_t bsel = 0x3210u + 0x1111u * (uint32_t)(wx0 & 3);  // PRMT selector of the row alignment
         if constexpr (BYTE) {
             const int rx = wx0 + R_;
@@ -461,14 +448,24 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                 }
             s2ref = s_s2[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
         } else {
-            if (narrow) {
+            {
+                // range of the reference block: lanes read two voxels each
+                const uint32_t va = refp[(lane >> 4) * G::SZ + ((lane >> 2) & 3) * G::SY + (lane & 3)];
+                const uint32_t vb = refp[(2 + (lane >> 4)) * G::SZ + ((lane >> 2) & 3) * G::SY + (lane & 3)];
+                rmin = __reduce_min_sync(B4D_FULL, min(va, vb));
+                const uint32_t rmax = __reduce_max_sync(B4D_FULL, max(va, vb));
+                npass = (rmax - rmin <= 255u) ? 1 : 2;  // r - r_min < 2^16: low and high byte planes
+                s2ref = s_s2[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
+                s1ref = s_s1[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
 #pragma unroll
                 for (int z = 0; z < 4; ++z)
 #pragma unroll
-                    for (int y = 0; y < 4; ++y)
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) ref[(z * 4 + y) * 4 + x] = refp[z * G::SZ + y * G::SY + x];
-                s2ref = s_s2[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
+                    for (int y = 0; y < 4; ++y) {
+                        const uint16_t *rp = refp + z * G::SZ + y * G::SY;
+                        const uint32_t r0 = rp[0] - rmin, r1 = rp[1] - rmin, r2 = rp[2] - rmin, r3 = rp[3] - rmin;
+                        refw[z * 4 + y] = (r0 & 0xFFu) | ((r1 & 0xFFu) << 8) | ((r2 & 0xFFu) << 16) | (r3 << 24);
+                        refw[16 + z * 4 + y] = (r0 >> 8) | ((r1 >> 8) << 8) | ((r2 >> 8) << 16) | ((r3 >> 8) << 24);
+                    }
             }
         }
         // valid dx range of candidates: cx = ox - R_ + j in [0, W-4]
@@ -513,25 +510,51 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                     }
                 } else {
                     if (uvalid) {
-                        const uint16_t *base = s_win + (wz0 + dz) * G::SZ + (wy0 + dy) * G::SY + wx0;
-                        if (narrow) {
-                            uint32_t acc[NS];
-                            xcorr_row<NS>(base, ref, acc);
-                            const uint32_t *e = s_s2 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
+                        // sum(a r) = sum(a rl) + 256 sum(a rh) + r_min S1(a): one IDP.2A pass per
+                        // reference byte plane (each pass < 2^31)
+                        const int pp = wx0 & 1;
+                        const uint32_t *wb = reinterpret_cast<const uint32_t *>(s_win) +
+                                             (((wz0 + dz) * G::SZ + (wy0 + dy) * G::SY + wx0 - pp) >> 1);
+                        const uint32_t psel = pp ? 0x5432u : 0x3210u;
+                        uint32_t acc[NS], acch[NS];
+#pragma unroll
+                        for (int j = 0; j < NS; ++j) acch[j] = 0u;
+#pragma unroll 1
+                        for (int ps = 0; ps < npass; ++ps) {
+                            uint32_t rw16[16], part[NS];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) rw16[i] = ps ? refw[16 + i] : refw[i];
+                            r8corr_row<NS>(wb, psel, rw16, part);
 #pragma unroll
                             for (int j = 0; j < NS; ++j) {
-                                const uint32_t ssd = (e[j] + s2ref) - 2u * acc[j];  // exact: true SSD < 2^32
+                                if (ps) acch[j] = part[j];
+                                else acc[j] = part[j];
+                            }
+                        }
+                        const uint32_t *e = s_s2 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
+                        const uint32_t *e1 = s_s1 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
+                        if (narrow) {
+                            // everything modulo 2^32: exact because the true SSD < 2^32 on a narrow tile
+                            const uint32_t rm2 = 2u * rmin;
+#pragma unroll
+                            for (int j = 0; j < NS; ++j) {
+                                const uint32_t dot = acc[j] + (acch[j] << 8);
+                                const uint32_t ssd = (e[j] + s2ref) - 2u * dot - rm2 * (e1[j] & 0xFFFFFFu);
                                 const bool ok = ssd <= tau && j >= jlo && j <= jhi;
                                 key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                             }
                         } else {
-                            unsigned long long acc[NS];
-                            ssd_row_u64<NS>(base, refp, acc);
+                            // wide tile: the same sums, combined exactly in 64 bits
+                            const unsigned long long s2r = (unsigned long long)s2ref | ((unsigned long long)(s1ref >> 24) << 32);
 #pragma unroll
                             for (int j = 0; j < NS; ++j) {
-                                const bool ok = acc[j] <= (unsigned long long)tau && j >= jlo && j <= jhi;
-                                key[j] =
-                                    ok ? (((uint32_t)acc[j] << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                                const uint32_t e1j = e1[j];
+                                const unsigned long long s2a = (unsigned long long)e[j] | ((unsigned long long)(e1j >> 24) << 32);
+                                const unsigned long long dot = (unsigned long long)acc[j] + ((unsigned long long)acch[j] << 8) +
+                                                               (unsigned long long)rmin * (e1j & 0xFFFFFFu);
+                                const unsigned long long ssd = s2a + s2r - 2ull * dot;
+                                const bool ok = ssd <= (unsigned long long)tau && j >= jlo && j <= jhi;
+                                key[j] = ok ? (((uint32_t)ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                             }
                         }
                     }
@@ -661,13 +684,12 @@ void launch_ns(const MatchParams &p, cudaStream_t s) {
 
 }  // namespace
 
-void b4d_launch_block_energy(const uint16_t *u, uint32_t *s2, uint32_t *s1, int D, int H, int W, int nvol,
-                             cudaStream_t s) {
+void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s) {
     const long long total = (long long)(D - 3) * (H - 3) * ((W - 3 + 3) / 4) * nvol;
     long long blocks = (total + 255) / 256;
     if (blocks > 148ll * 64) blocks = 148ll * 64;
     if (blocks < 1) blocks = 1;
-    k_block_energy<<<(unsigned)blocks, 256, 0, s>>>(u, s2, s1, D, H, W, nvol);
+    k_block_energy<<<(unsigned)blocks, 256, 0, s>>>(u, s21, D, H, W, nvol);
 }
 
 void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s) {

@@ -2,13 +2,12 @@
 
 Bars (BASELINE.json north_star / DESIGN.md §5):
   * stage-1 match lists: bit-exact (idx, ssd, count);
-  * denoised output, deterministic aggregation: BIT-EXACT vs the oracle's float32
-    mirror (same discrete decisions, same rounding);
-  * denoised output, fast (float-atomic) aggregation: max-abs <= 0.5 and
-    rel-L2 <= 1e-3 vs the mirror; rel-L2 <= 1e-3 vs the plain float64 oracle
-    (block matching is discontinuous, so a float64 pipeline may flip a handful
-    of near-tied matches; max-abs vs float64 is bounded at 0.5 for >= 99.99 %
-    of voxels and reported);
+  * denoised output: BIT-EXACT vs the oracle's float32 mirror (same discrete
+    decisions, same rounding; aggregation is always order-independent fixed point,
+    the `deterministic` profile flag is kept for compatibility);
+  * denoised output vs the plain float64 oracle: rel-L2 <= 1e-3 (north_star);
+    block matching is discontinuous, so a float64 pipeline may flip a handful of
+    near-tied matches: max-abs is bounded at 0.5 for >= 99.99 % of voxels and reported;
   * quantize, statistics: bit-exact.
 """
 import numpy as np
@@ -118,7 +117,8 @@ def test_deterministic_f32_offset_input_bit_exact(b4d_mod, oracle_lib):
     d.close()
 
 
-def test_fast_mode_within_tolerance(dn, oracle_lib):
+def test_default_profile_config1_patch(dn, oracle_lib):
+    """BASELINE config 1: one 64^3 patch through the precompute path, default profile."""
     from b4d import synth
 
     vol = synth.vol(64, 64, 64, seed=1)  # BASELINE config 1 input
@@ -127,8 +127,8 @@ def test_fast_mode_within_tolerance(dn, oracle_lib):
         y = dn.denoise(z, 24.0)
         m = oracle_lib.Oracle("mirror").denoise(z, 24.0)
         f = oracle_lib.Oracle("f64").denoise(z, 24.0)
-        assert np.abs(y - m).max() <= MAX_ABS and rel_l2(y, m) <= REL_L2
-        assert rel_l2(y, f) <= REL_L2
+        assert np.array_equal(y, m)
+        assert np.abs(y - f).max() <= 16 * MAX_ABS and rel_l2(y, f) <= REL_L2
         frac_bad = float((np.abs(y - f) > MAX_ABS).mean())
         print("fast vs f64: max-abs %.4f, frac > 0.5: %.2e" % (np.abs(y - f).max(), frac_bad))
         assert frac_bad <= 1e-4
@@ -254,3 +254,21 @@ def test_full_size_properties_128(dn, b4d_mod):
     d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(deterministic=True))
     assert np.abs(d.denoise(c, 24.0) - 4321.0).max() < 1e-2
     d.close()
+
+
+def test_patch_cache_written_by_the_gpu_path(tmp_path, b4d_mod, oracle_lib):
+    """the cache precompute.py writes (raw/teacher/fg .npy + transform.json),
+    filled by batched GPU launches; teacher == clip(oracle bm4d(raw), 0, 65535) bit for bit."""
+    from b4d import cache, synth
+
+    patches = np.stack([synth.vol(20, 20, 20, seed=40 + s) for s in range(5)])
+    offs = np.array([37.0, 37.0, 12.5, 37.0, 0.0], np.float32)
+    d = str(tmp_path / "train")
+    assert cache.write_patch_cache(d, patches, offs, 24.0, batch=3) == 5
+    raw, teacher, fg, tcfg = cache.load_patch_cache(d)
+    assert raw.dtype == np.float32 and teacher.dtype == np.float32 and fg.dtype == np.uint8
+    o = oracle_lib.Oracle("mirror")
+    for i in (0, 2, 4):
+        want = np.clip(o.denoise(oracle_lib.read_counts(patches[i], float(offs[i])), 24.0), 0, 65535)
+        assert np.array_equal(teacher[i], want)
+    assert cache.write_patch_cache(d, patches, offs, 24.0, batch=3) == 0  # resume: nothing left
