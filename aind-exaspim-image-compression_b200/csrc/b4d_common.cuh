@@ -36,9 +36,9 @@ struct MatchParams {
     B4dGeom g;
     const uint16_t *u;   // matching image [nvol][D][H][W]
     const uint2 *s21;    // per block origin (K0): .x = energy sum(v^2) mod 2^32, .y = sum(v)
-    uint32_t *cells;     // scratch: min | max << 16 per aligned 4^3 cell (NULL with tcls)
-    uint32_t *tcls;      // scratch: per matcher tile, 1 << 16 | min for byte tiles, 0 otherwise;
-                         // NULL disables the byte path
+    uint32_t *cells;     // scratch: min | max << 16 per aligned 4^3 cell
+    uint32_t *tcls;      // scratch: class of every matcher tile (bit 16 byte tile + min in bits 0-15,
+                         // bit 17 narrow), written by k_tile_class
     uint32_t tau;        // acceptance threshold (SSD <= tau)
     int K;               // max group size
     uint16_t *widx;      // [R][K] window index of each match

@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(256) k_cell_minmax(const uint16_t *__restrict_
     }
 }
 // One warp per matcher tile: range over the cells that cover its staged neighbourhood
-// (a superset of it, hence conservative).  tcls[tile] = 1 << 16 | min when the range
-// fits a byte, else 0.
+// (a superset of it, hence conservative).  tcls[tile]: bit 16 = the range fits a byte (then
+// bits 0-15 hold the minimum), bit 17 = "narrow", range <= 8191 (every SSD < 2^32).
 template <int NS>
 __global__ void __launch_bounds__(256) k_tile_class(const uint32_t *__restrict__ cells, const B4dGeom g,
                                                     uint32_t *__restrict__ tcls) {
@@ -230,7 +230,10 @@ __global__ void __launch_bounds__(256) k_tile_class(const uint32_t *__restrict__
     }
     mn = __reduce_min_sync(B4D_FULL, mn);
     mx = __reduce_max_sync(B4D_FULL, mx);
-    if (lane == 0) tcls[tile] = (mx >= mn && mx - mn <= 255u) ? ((1u << 16) | mn) : 0u;
+    if (lane == 0) {
+        const uint32_t range = mx >= mn ? mx - mn : 0u;
+        tcls[tile] = range <= 255u ? ((3u << 16) | mn) : (range <= 8191u ? (2u << 16) : 0u);
+    }
 }
 
 // ------------------------------------------------------------ helpers -------
@@ -316,30 +319,34 @@ __device__ __forceinline__ void r8corr_row(const uint32_t *__restrict__ base, ui
     }
 }
 
+// cp.async with zero fill: copies `n` (0 or the full size) bytes, zero-fills the rest
+__device__ __forceinline__ void cp_async4_zfill(uint32_t saddr, const void *g, uint32_t n) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(uint32_t saddr, const void *g, uint32_t n) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(g), "r"(n) : "memory");
+}
+
 template <int NS, bool K32, bool BYTE>
 __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchParams p) {
     using G = Geo<NS>;
     constexpr int R_ = G::R, E = G::E, EC = G::EC, KB = G::KB, UNITS = G::UNITS, ITERS = G::ITERS;
 
     // tile class: byte tiles belong to the BYTE instantiation, all others to the general one
-    uint32_t tmin = 0;
-    if (p.tcls) {
-        const uint32_t cls = p.tcls[blockIdx.x];
-        if (BYTE != ((cls >> 16) != 0u)) return;
-        tmin = cls & 0xFFFFu;
-    } else if (BYTE) {
-        return;
-    }
+    const uint32_t cls = p.tcls[blockIdx.x];
+    if (BYTE != (((cls >> 16) & 1u) != 0u)) return;
+    const uint32_t tmin = cls & 0xFFFFu;
+    const bool narrow = BYTE || ((cls >> 17) & 1u) != 0u;
 
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint16_t *s_win = reinterpret_cast<uint16_t *>(s_raw);
     uint32_t *s_bw = reinterpret_cast<uint32_t *>(s_raw);  // byte path: packed bytes
-    uint32_t *s_s2 = reinterpret_cast<uint32_t *>(
-        s_raw + (BYTE ? (((size_t)G::BWIN_WORDS * 4 + 15) & ~(size_t)15) : (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15)));
-    uint32_t *s_s1 = s_s2 + G::S2_WORDS;  // general kernel only: block sums S1
+    unsigned char *s_tab =
+        s_raw + (BYTE ? (((size_t)G::BWIN_WORDS * 4 + 15) & ~(size_t)15) : (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15));
+    uint32_t *s_s2 = reinterpret_cast<uint32_t *>(s_tab);  // byte kernel: centred energies S2'
+    uint2 *s_e = reinterpret_cast<uint2 *>(s_tab);         // general kernel: {S2 mod 2^32, S1 | S2hi << 24}
     __shared__ uint32_t s_surv[WARPS][CAP];
     __shared__ int s_cnt[WARPS];
-    __shared__ uint32_t s_min, s_max;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const B4dGeom &g = p.g;
@@ -355,15 +362,12 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     const int bz = g.refz[iz0] - R_, by = g.refy[iy0] - R_, bx = g.refx[ix0] - R_;
     const uint16_t *__restrict__ uv = p.u + (long long)vol * g.vol_stride;
     const uint2 *__restrict__ s21v = p.s21 + (long long)vol * g.vol_stride;
+    // General kernel: the staged window starts at an EVEN global x when rows are 4-byte aligned
+    // (W even), so that it can be filled by 4-byte cp.async; xo = 0 or 1 shifts window columns.
+    const int xo = (BYTE || (g.W & 1)) ? 0 : (bx & 1);
 
-    if (threadIdx.x == 0) {
-        s_min = 0xFFFFFFFFu;
-        s_max = 0u;
-    }
-    __syncthreads();
-    // Staging, one row per warp iteration, lanes along x (coalesced, several rows in flight).
-    {
-        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    if (BYTE) {
+        // Staging, one row per warp iteration, lanes along x (coalesced, several rows in flight).
         const int gx = bx + lane;
         const bool xin = lane < E && (unsigned)gx < (unsigned)g.W;
 #pragma unroll 4
@@ -373,19 +377,11 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
             uint32_t v = 0;
             const bool in = xin && (unsigned)gz < (unsigned)g.D && (unsigned)gy < (unsigned)g.H;
             if (in) v = uv[((long long)gz * g.H + gy) * g.W + gx];
-            if (BYTE) {
-                // bytes v - tile_min (0 outside the volume), four per word
-                uint32_t bt = in ? ((v - tmin) & 0xFFu) : 0u;
-                bt |= __shfl_down_sync(B4D_FULL, bt, 1) << 8;
-                bt |= __shfl_down_sync(B4D_FULL, bt, 2) << 16;
-                if ((lane & 3) == 0 && lane < 4 * G::RW) s_bw[z * G::PSW + y * G::RSW + (lane >> 2)] = bt;
-            } else {
-                if (in) {
-                    mn = min(mn, v);
-                    mx = max(mx, v);
-                }
-                if (lane < E) s_win[z * G::SZ + y * G::SY + lane] = (uint16_t)v;
-            }
+            // bytes v - tile_min (0 outside the volume), four per word
+            uint32_t bt = in ? ((v - tmin) & 0xFFu) : 0u;
+            bt |= __shfl_down_sync(B4D_FULL, bt, 1) << 8;
+            bt |= __shfl_down_sync(B4D_FULL, bt, 2) << 16;
+            if ((lane & 3) == 0 && lane < 4 * G::RW) s_bw[z * G::PSW + y * G::RSW + (lane >> 2)] = bt;
         }
         const bool cin = lane < EC && (unsigned)gx <= (unsigned)(g.W - 4);
         const uint32_t m2 = 2u * tmin, m64 = 64u * tmin * tmin;
@@ -396,27 +392,47 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
             uint2 v = make_uint2(0u, 0u);
             if (cin && (unsigned)gz <= (unsigned)(g.D - 4) && (unsigned)gy <= (unsigned)(g.H - 4))
                 v = s21v[((long long)gz * g.H + gy) * g.W + gx];
-            if (lane < EC) {
-                if (BYTE) {
-                    // centred block energies S2' = S2 - 2 m S1 + 64 m^2 (exact: S2' <= 64 * 255^2)
-                    s_s2[z * G::AC + y * G::BC + lane] = (v.x | v.y) ? v.x - m2 * (v.y & 0xFFFFFFu) + m64 : 0u;
-                } else {
-                    s_s2[z * G::AC + y * G::BC + lane] = v.x;
-                    s_s1[z * G::AC + y * G::BC + lane] = v.y;
-                }
+            // centred block energies S2' = S2 - 2 m S1 + 64 m^2 (exact: S2' <= 64 * 255^2)
+            if (lane < EC)
+                s_s2[z * G::AC + y * G::BC + lane] = (v.x | v.y) ? v.x - m2 * (v.y & 0xFFFFFFu) + m64 : 0u;
+        }
+    } else {
+        // Asynchronous staging (cp.async, zero fill outside the volume): no register round trip,
+        // every copy of the tile in flight at once, one wait.
+        const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
+        const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(s_e);
+        if (!(g.W & 1)) {
+            const int bxe = bx - xo;  // even
+            for (int id = threadIdx.x; id < E * E * G::BW; id += WARPS * 32) {
+                const int row = id / G::BW, c = id - row * G::BW;
+                const int z = row / E, y = row - z * E;
+                const int gz = bz + z, gy = by + y, gxc = bxe + 2 * c;
+                const bool in = (unsigned)gz < (unsigned)g.D && (unsigned)gy < (unsigned)g.H &&
+                                (unsigned)gxc < (unsigned)g.W;  // gxc and W even: the pair is inside
+                const uint16_t *src = in ? uv + ((long long)gz * g.H + gy) * g.W + gxc : uv;
+                cp_async4_zfill(win_base + 4u * (uint32_t)(z * G::AW + y * G::BW + c), src, in ? 4u : 0u);
+            }
+        } else {  // odd row length: rows are not 4-byte aligned, plain loads
+            for (int id = threadIdx.x; id < E * E * E; id += WARPS * 32) {
+                const int x = id % E, y = (id / E) % E, z = id / (E * E);
+                const int gz = bz + z, gy = by + y, gx = bx + x;
+                uint32_t v = 0;
+                if ((unsigned)gz < (unsigned)g.D && (unsigned)gy < (unsigned)g.H && (unsigned)gx < (unsigned)g.W)
+                    v = uv[((long long)gz * g.H + gy) * g.W + gx];
+                s_win[z * G::SZ + y * G::SY + x] = (uint16_t)v;
             }
         }
-        if (!BYTE) {
-            mn = __reduce_min_sync(B4D_FULL, mn);
-            mx = __reduce_max_sync(B4D_FULL, mx);
-            if (lane == 0) {
-                atomicMin(&s_min, mn);
-                atomicMax(&s_max, mx);
-            }
+        for (int id = threadIdx.x; id < EC * EC * EC; id += WARPS * 32) {
+            const int x = id % EC, y = (id / EC) % EC, z = id / (EC * EC);
+            const int gz = bz + z, gy = by + y, gx = bx + x;
+            const bool in = (unsigned)gz <= (unsigned)(g.D - 4) && (unsigned)gy <= (unsigned)(g.H - 4) &&
+                            (unsigned)gx <= (unsigned)(g.W - 4);
+            const uint2 *src = in ? s21v + ((long long)gz * g.H + gy) * g.W + gx : s21v;
+            cp_async8_zfill(tab_base + 8u * (uint32_t)(z * G::AC + y * G::BC + x), src, in ? 8u : 0u);
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
-    const bool narrow = BYTE || (s_max - s_min) <= 8191u || s_max < s_min;
     if (!narrow && threadIdx.x == 0 && p.stats) atomicAdd(&p.stats[1], 1ull);
     if (BYTE && threadIdx.x == 0 && p.stats) atomicAdd(&p.stats[3], 1ull);
 
@@ -428,7 +444,8 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
         if (iz >= g.nrz || iy >= g.nry || ix >= g.nrx) continue;  // warp-uniform
         const int oz = g.refz[iz], oy = g.refy[iy], ox = g.refx[ix];
         const int wz0 = oz - R_ - bz, wy0 = oy - R_ - by, wx0 = ox - R_ - bx;  // window origin in the tile
-        const uint16_t *refp = s_win + (wz0 + R_) * G::SZ + (wy0 + R_) * G::SY + (wx0 + R_);
+        const int wxw = wx0 + xo;  // window column of the search-window origin
+        const uint16_t *refp = s_win + (wz0 + R_) * G::SZ + (wy0 + R_) * G::SY + (wxw + R_);
         // reference block as bytes: BYTE kernel one word per row; general kernel low bytes of
         // r - r_min in [0, 16) and, when the block spans more than 255 counts, high bytes in [16, 32)
         uint32_t refw[BYTE ? 16 : 32];
@@ -455,8 +472,9 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                 rmin = __reduce_min_sync(B4D_FULL, min(va, vb));
                 const uint32_t rmax = __reduce_max_sync(B4D_FULL, max(va, vb));
                 npass = (rmax - rmin <= 255u) ? 1 : 2;  // r - r_min < 2^16: low and high byte planes
-                s2ref = s_s2[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
-                s1ref = s_s1[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
+                const uint2 er = s_e[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
+                s2ref = er.x;
+                s1ref = er.y;
 #pragma unroll
                 for (int z = 0; z < 4; ++z)
 #pragma unroll
@@ -512,9 +530,9 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                     if (uvalid) {
                         // sum(a r) = sum(a rl) + 256 sum(a rh) + r_min S1(a): one IDP.2A pass per
                         // reference byte plane (each pass < 2^31)
-                        const int pp = wx0 & 1;
+                        const int pp = wxw & 1;
                         const uint32_t *wb = reinterpret_cast<const uint32_t *>(s_win) +
-                                             (((wz0 + dz) * G::SZ + (wy0 + dy) * G::SY + wx0 - pp) >> 1);
+                                             (((wz0 + dz) * G::SZ + (wy0 + dy) * G::SY + wxw - pp) >> 1);
                         const uint32_t psel = pp ? 0x5432u : 0x3210u;
                         uint32_t acc[NS], acch[NS];
 #pragma unroll
@@ -531,15 +549,15 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                                 else acc[j] = part[j];
                             }
                         }
-                        const uint32_t *e = s_s2 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
-                        const uint32_t *e1 = s_s1 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
+                        const uint2 *e = s_e + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
                         if (narrow) {
                             // everything modulo 2^32: exact because the true SSD < 2^32 on a narrow tile
                             const uint32_t rm2 = 2u * rmin;
 #pragma unroll
                             for (int j = 0; j < NS; ++j) {
+                                const uint2 ev = e[j];
                                 const uint32_t dot = acc[j] + (acch[j] << 8);
-                                const uint32_t ssd = (e[j] + s2ref) - 2u * dot - rm2 * (e1[j] & 0xFFFFFFu);
+                                const uint32_t ssd = (ev.x + s2ref) - 2u * dot - rm2 * (ev.y & 0xFFFFFFu);
                                 const bool ok = ssd <= tau && j >= jlo && j <= jhi;
                                 key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                             }
@@ -548,8 +566,9 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                             const unsigned long long s2r = (unsigned long long)s2ref | ((unsigned long long)(s1ref >> 24) << 32);
 #pragma unroll
                             for (int j = 0; j < NS; ++j) {
-                                const uint32_t e1j = e1[j];
-                                const unsigned long long s2a = (unsigned long long)e[j] | ((unsigned long long)(e1j >> 24) << 32);
+                                const uint2 ev = e[j];
+                                const uint32_t e1j = ev.y;
+                                const unsigned long long s2a = (unsigned long long)ev.x | ((unsigned long long)(e1j >> 24) << 32);
                                 const unsigned long long dot = (unsigned long long)acc[j] + ((unsigned long long)acch[j] << 8) +
                                                                (unsigned long long)rmin * (e1j & 0xFFFFFFu);
                                 const unsigned long long ssd = s2a + s2r - 2ull * dot;
@@ -661,17 +680,16 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
 template <int NS, bool K32>
 void launch_k(const MatchParams &p, long long tiles, cudaStream_t s) {
     using G = Geo<NS>;
-    if (p.tcls) {  // byte tiles first (cheap), then everything else
-        cudaFuncSetAttribute(k_match<NS, K32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_B);
-        k_match<NS, K32, true><<<(unsigned)tiles, WARPS * 32, G::SMEM_B, s>>>(p);
-    }
+    // byte tiles first (cheap), then everything else; each kernel exits at once on a foreign tile
+    cudaFuncSetAttribute(k_match<NS, K32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_B);
+    k_match<NS, K32, true><<<(unsigned)tiles, WARPS * 32, G::SMEM_B, s>>>(p);
     cudaFuncSetAttribute(k_match<NS, K32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     k_match<NS, K32, false><<<(unsigned)tiles, WARPS * 32, G::SMEM, s>>>(p);
 }
 template <int NS>
 void launch_ns(const MatchParams &p, cudaStream_t s) {
     const long long tiles = (long long)p.g.nvol * p.g.tz * p.g.ty * p.g.tx;
-    if (p.tcls) {
+    {
         const long long cells = (long long)p.g.nvol * ((p.g.D + 3) / 4) * ((p.g.H + 3) / 4) * ((p.g.W + 3) / 4);
         long long blocks = std::min<long long>((cells + 255) / 256, 148ll * 32);
         k_cell_minmax<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, s>>>(p.u, p.cells, p.g.D, p.g.H, p.g.W,
