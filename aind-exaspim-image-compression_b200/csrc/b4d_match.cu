@@ -346,7 +346,6 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     uint32_t *s_s2 = reinterpret_cast<uint32_t *>(s_tab);  // byte kernel: centred energies S2'
     uint2 *s_e = reinterpret_cast<uint2 *>(s_tab);         // general kernel: {S2 mod 2^32, S1 | S2hi << 24}
     __shared__ uint32_t s_surv[WARPS][CAP];
-    __shared__ int s_cnt[WARPS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const B4dGeom &g = p.g;
@@ -502,7 +501,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
         for (;;) {
             uint32_t lmin1 = B4D_INVALID_KEY, lmin2 = B4D_INVALID_KEY;
             uint32_t B = Bfix;
-            if (lane == 0) s_cnt[warp] = 0;
+            int nsurv = 0;  // survivor count of this warp (uniform; the list is warp-private)
             __syncwarp();
 #pragma unroll 1
             for (int it = 0; it < ITERS; ++it) {
@@ -590,10 +589,11 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                     }
 #pragma unroll
                     for (int j = 0; j < NS; ++j) {
-                        if (key[j] <= B) {
-                            const int pos = atomicAdd(&s_cnt[warp], 1);
-                            if (pos < CAP) s_surv[warp][pos] = key[j];
-                        }
+                        const bool take = key[j] <= B;
+                        const unsigned m = __ballot_sync(B4D_FULL, take);
+                        const int pos = nsurv + __popc(m & ((1u << lane) - 1u));
+                        if (take && pos < CAP) s_surv[warp][pos] = key[j];
+                        nsurv += __popc(m);
                     }
                 } else {
 #pragma unroll
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
             }
             __syncwarp();
             if (mode < 2) {
-                const int n = s_cnt[warp];
+                const int n = nsurv;
                 if (n <= CAP) {
                     // compact the survivors that are <= the final bound, then rank-sort them
                     uint32_t mine[CAP / 32];
