@@ -87,7 +87,10 @@ struct Geo {
     static constexpr int PSW = PSW0 + (((NS * RSW) % 32 - PSW0 % 32) + 32) % 32;
     static constexpr int BWIN_WORDS = E * PSW;
     static constexpr int NWR = (NS + 9) / 4;   // row words a lane loads: bytes [a, a + NS + 3), a <= 3
-    static constexpr size_t SMEM_B = (((size_t)BWIN_WORDS * 4 + 15) & ~(size_t)15) + (size_t)S2_WORDS * 4;
+    // byte kernel: byte window + the S2' table, whose space first holds the raw uint16 window
+    static constexpr size_t TAB_B =
+        (size_t)S2_WORDS * 4 > (size_t)WIN_ELEMS * 2 ? (size_t)S2_WORDS * 4 : (size_t)WIN_ELEMS * 2;
+    static constexpr size_t SMEM_B = (((size_t)BWIN_WORDS * 4 + 15) & ~(size_t)15) + TAB_B;
     // centre-out visiting order of the 32-unit groups: mc, mc+1, mc-1, mc+2, ...
     // packed 4 bits per entry so the device reads it with a shift and a mask
     static constexpr int order_at(int it) {
@@ -366,7 +369,56 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     const int xo = (BYTE || (g.W & 1)) ? 0 : (bx & 1);
 
     if (BYTE) {
-        // Staging, one row per warp iteration, lanes along x (coalesced, several rows in flight).
+        if (!(g.W & 1)) {
+            // (1) raw uint16 window -> scratch (the S2' table's space) by cp.async, as in the
+            // general kernel: even global x origin, zero fill outside the volume
+            uint16_t *s_tmp = reinterpret_cast<uint16_t *>(s_tab);
+            const uint32_t tmp_base = (uint32_t)__cvta_generic_to_shared(s_tmp);
+            const int xb = bx & 1, bxe = bx - xb;
+            for (int id = threadIdx.x; id < E * E * G::BW; id += WARPS * 32) {
+                const int row = id / G::BW, c = id - row * G::BW;
+                const int z = row / E, y = row - z * E;
+                const int gz = bz + z, gy = by + y, gxc = bxe + 2 * c;
+                const bool in = (unsigned)gz < (unsigned)g.D && (unsigned)gy < (unsigned)g.H &&
+                                (unsigned)gxc < (unsigned)g.W;
+                const uint16_t *src = in ? uv + ((long long)gz * g.H + gy) * g.W + gxc : uv;
+                cp_async4_zfill(tmp_base + 4u * (uint32_t)(z * G::AW + y * G::BW + c), src, in ? 4u : 0u);
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            // (2) bytes v - tile_min, four per word (voxels outside the volume give junk bytes that
+            // no valid candidate reads)
+            for (int id = threadIdx.x; id < E * E * G::RW; id += WARPS * 32) {
+                const int row = id / G::RW, xw = id - row * G::RW;
+                const int z = row / E, y = row - z * E;
+                const uint16_t *src = s_tmp + z * G::SZ + y * G::SY + xb + 4 * xw;
+                const uint32_t b0 = (src[0] - tmin) & 0xFFu, b1 = (src[1] - tmin) & 0xFFu;
+                const uint32_t b2 = (src[2] - tmin) & 0xFFu, b3 = (src[3] - tmin) & 0xFFu;
+                s_bw[z * G::PSW + y * G::RSW + xw] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+            }
+            __syncthreads();
+            // (3) centred block energies S2'(z,y,x) = sum over the 4x4x4 block of byte^2, from the
+            // byte window: one thread per (y, x) column marches along z with a 4-plane sliding sum
+            for (int col = threadIdx.x; col < EC * EC; col += WARPS * 32) {
+                const int y = col / EC, x = col - y * EC;
+                const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(x & 3);
+                uint32_t r1 = 0u, r2 = 0u, r3 = 0u;  // plane sums of z-1, z-2, z-3
+                for (int z = 0; z < E; ++z) {
+                    uint32_t r0 = 0u;
+#pragma unroll
+                    for (int dy = 0; dy < 4; ++dy) {
+                        const uint32_t *w = s_bw + z * G::PSW + (y + dy) * G::RSW + (x >> 2);
+                        const uint32_t q = __byte_perm(w[0], w[1], sel);
+                        r0 = __dp4a(q, q, r0);
+                    }
+                    if (z >= 3) s_s2[(z - 3) * G::AC + y * G::BC + x] = r0 + r1 + r2 + r3;
+                    r3 = r2;
+                    r2 = r1;
+                    r1 = r0;
+                }
+            }
+        } else {
+        // odd row length: rows are not 4-byte aligned -> plain loads, one row per warp iteration
         const int gx = bx + lane;
         const bool xin = lane < E && (unsigned)gx < (unsigned)g.W;
 #pragma unroll 4
@@ -394,6 +446,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
             // centred block energies S2' = S2 - 2 m S1 + 64 m^2 (exact: S2' <= 64 * 255^2)
             if (lane < EC)
                 s_s2[z * G::AC + y * G::BC + lane] = (v.x | v.y) ? v.x - m2 * (v.y & 0xFFFFFFu) + m64 : 0u;
+        }
         }
     } else {
         // Asynchronous staging (cp.async, zero fill outside the volume): no register round trip,
