@@ -330,6 +330,35 @@ __device__ __forceinline__ void cp_async8_zfill(uint32_t saddr, const void *g, u
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(g), "r"(n) : "memory");
 }
 
+// The same sums for the HIGH byte plane of a reference block that spans more than 255 counts
+// (rare): rolled over the 16 block rows, reference bytes from shared memory, so that it adds
+// one row body of code instead of sixteen.
+template <int NS>
+__device__ __forceinline__ void r8corr_row_rolled(const uint32_t *__restrict__ base, uint32_t sel,
+                                                  const uint32_t *__restrict__ rw, uint32_t (&acc)[NS]) {
+    using G = Geo<NS>;
+    constexpr int NA = (NS + 4) / 2;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) acc[j] = 0u;
+#pragma unroll 1
+    for (int row = 0; row < 16; ++row) {
+        const uint32_t *b = base + (row >> 2) * G::AW + (row & 3) * G::BW;
+        uint32_t w[NA + 1], al[NA];
+#pragma unroll
+        for (int i = 0; i < NA + 1; ++i) w[i] = b[i];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) al[i] = __byte_perm(w[i], w[i + 1], sel);
+        const uint32_t r = rw[row];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            const uint32_t p0 = (j & 1) == 0 ? al[j / 2] : __byte_perm(al[j / 2], al[j / 2 + 1], 0x5432);
+            const uint32_t p1 = (j & 1) == 0 ? al[j / 2 + 1] : __byte_perm(al[j / 2 + 1], al[j / 2 + 2], 0x5432);
+            acc[j] = __dp2a_lo(p0, r, acc[j]);
+            acc[j] = __dp2a_hi(p1, r, acc[j]);
+        }
+    }
+}
+
 template <int NS, bool K32, bool BYTE>
 __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchParams p) {
     using G = Geo<NS>;
@@ -349,6 +378,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     uint32_t *s_s2 = reinterpret_cast<uint32_t *>(s_tab);  // byte kernel: centred energies S2'
     uint2 *s_e = reinterpret_cast<uint2 *>(s_tab);         // general kernel: {S2 mod 2^32, S1 | S2hi << 24}
     __shared__ uint32_t s_surv[WARPS][CAP];
+    __shared__ uint32_t s_refhi[BYTE ? 1 : WARPS][16];  // high byte plane of a wide-range reference block
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const B4dGeom &g = p.g;
@@ -498,9 +528,10 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
         const int wz0 = oz - R_ - bz, wy0 = oy - R_ - by, wx0 = ox - R_ - bx;  // window origin in the tile
         const int wxw = wx0 + xo;  // window column of the search-window origin
         const uint16_t *refp = s_win + (wz0 + R_) * G::SZ + (wy0 + R_) * G::SY + (wxw + R_);
-        // reference block as bytes: BYTE kernel one word per row; general kernel low bytes of
-        // r - r_min in [0, 16) and, when the block spans more than 255 counts, high bytes in [16, 32)
-        uint32_t refw[BYTE ? 16 : 32];
+        // reference block as bytes, one word per block row: BYTE kernel v - tile_min; general kernel
+        // the low bytes of r - r_min (the high bytes, when the block spans more than 255 counts,
+        // go to shared memory)
+        uint32_t refw[16];
         uint32_t s2ref = 0;
         uint32_t rmin = 0, s1ref = 0;
         int npass = 1;
@@ -534,8 +565,10 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                         const uint16_t *rp = refp + z * G::SZ + y * G::SY;
                         const uint32_t r0 = rp[0] - rmin, r1 = rp[1] - rmin, r2 = rp[2] - rmin, r3 = rp[3] - rmin;
                         refw[z * 4 + y] = (r0 & 0xFFu) | ((r1 & 0xFFu) << 8) | ((r2 & 0xFFu) << 16) | (r3 << 24);
-                        refw[16 + z * 4 + y] = (r0 >> 8) | ((r1 >> 8) << 8) | ((r2 >> 8) << 16) | ((r3 >> 8) << 24);
+                        if (npass == 2 && lane == 0)
+                            s_refhi[warp][z * 4 + y] = (r0 >> 8) | ((r1 >> 8) << 8) | ((r2 >> 8) << 16) | ((r3 >> 8) << 24);
                     }
+                __syncwarp();
             }
         }
         // valid dx range of candidates: cx = ox - R_ + j in [0, W-4]
@@ -587,19 +620,12 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                                              (((wz0 + dz) * G::SZ + (wy0 + dy) * G::SY + wxw - pp) >> 1);
                         const uint32_t psel = pp ? 0x5432u : 0x3210u;
                         uint32_t acc[NS], acch[NS];
+                        r8corr_row<NS>(wb, psel, refw, acc);
+                        if (npass == 2) {
+                            r8corr_row_rolled<NS>(wb, psel, s_refhi[warp], acch);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < NS; ++j) acch[j] = 0u;
-#pragma unroll 1
-                        for (int ps = 0; ps < npass; ++ps) {
-                            uint32_t rw16[16], part[NS];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) rw16[i] = ps ? refw[16 + i] : refw[i];
-                            r8corr_row<NS>(wb, psel, rw16, part);
-#pragma unroll
-                            for (int j = 0; j < NS; ++j) {
-                                if (ps) acch[j] = part[j];
-                                else acc[j] = part[j];
-                            }
+                            for (int j = 0; j < NS; ++j) acch[j] = 0u;
                         }
                         const uint2 *e = s_e + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
                         if (narrow) {
