@@ -291,7 +291,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         B4D_TRY(h->tcls.ensure(ntile * sizeof(uint32_t)));
     }
     B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
-    // Both stages aggregate in order-independent 2^32 fixed point (int64): the result does not
+    // Both stages aggregate in order-independent fixed point (int64): the result does not
     // depend on scheduling, a slab equals the whole volume bit for bit, and the basic estimate
     // that feeds the stage-2 matching (a discontinuous decision) is reproducible.
     // profile.deterministic is kept in the ABI and is always honoured.
@@ -307,7 +307,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         return 0;
     };
     auto normalise = [&](const float *fb, float *dst) {
-        b4d_launch_normalise_det(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, TV, s);
+        b4d_launch_normalise_det(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, TV, 1.0f / mm.scale, s);
     };
 
     float *d_basic = (p.stages == 1) ? d_out : h->basic.as<float>();
@@ -339,6 +339,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.K = p.k_ht;
     fp.Ns = p.search_ht;
     fp.nseg = 1;
+    fp.qscale = mm.scale;  // data * scale spans at most the 16-bit matching range: terms stay below 2^39
     fp.numq = h->numq.as<long long>();
     fp.denq = h->denq.as<long long>();
     if (R1 > 0) b4d_launch_filter(fp, false, s);

@@ -56,7 +56,9 @@ struct FilterParams {
     int K;
     int Ns;
     int nseg;                    // z segments per column (set by the launcher)
-    long long *numq, *denq;      // 2^32 fixed-point accumulators (order independent)
+    float qscale;                // power of two: numerator terms are rint(wq * qscale * x), |.| < 2^39
+    long long *numq, *denq;      // fixed-point accumulators (order independent): sum of numerator
+                                 // terms / sum of the 20-bit weights wq
 };
 
 void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s);
@@ -69,7 +71,7 @@ void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, unsigned
 void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, float scale, int ishift,
                          cudaStream_t s);
 void b4d_launch_normalise_det(const long long *numq, const long long *denq, const float *fallback, float *out,
-                              long long n, cudaStream_t s);
+                              long long n, float inv_qscale, cudaStream_t s);
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s);
 void b4d_launch_hist(const uint16_t *in, long long n, unsigned long long *hist, cudaStream_t s);

@@ -95,15 +95,16 @@ __global__ void __launch_bounds__(256) k_to_match(const float *__restrict__ in, 
 }
 
 // ------------------------------------------------------------- normalise ----
-// K3 / K6: out = num / den (den > 0), else the fallback value.  Accumulators are
-// 2^32 fixed point (int64): 16 B read + 4 B fallback + 4 B write per voxel.
-__device__ __forceinline__ float norm1(long long nq, long long dq, float fb) {
-    return dq > 0 ? (float)((double)nq / (double)dq) : fb;
+// K3 / K6: out = num / den / qscale (den > 0), else the fallback value.  Accumulators are
+// fixed point (int64): 16 B read + 4 B fallback + 4 B write per voxel.
+__device__ __forceinline__ float norm1(long long nq, long long dq, float fb, double inv) {
+    return dq > 0 ? (float)(((double)nq / (double)dq) * inv) : fb;
 }
 __global__ void __launch_bounds__(256) k_normalise_det(const long long *__restrict__ numq,
                                                        const long long *__restrict__ denq,
                                                        const float *__restrict__ fb, float *__restrict__ out,
-                                                       long long n) {
+                                                       long long n, float inv_qscale) {
+    const double inv = (double)inv_qscale;
     const long long nv = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
@@ -113,14 +114,14 @@ __global__ void __launch_bounds__(256) k_normalise_det(const long long *__restri
         const longlong2 d1 = __ldcs(reinterpret_cast<const longlong2 *>(denq) + 2 * i + 1);
         const float4 f = reinterpret_cast<const float4 *>(fb)[i];
         float4 o;
-        o.x = norm1(n0.x, d0.x, f.x);
-        o.y = norm1(n0.y, d0.y, f.y);
-        o.z = norm1(n1.x, d1.x, f.z);
-        o.w = norm1(n1.y, d1.y, f.w);
+        o.x = norm1(n0.x, d0.x, f.x, inv);
+        o.y = norm1(n0.y, d0.y, f.y, inv);
+        o.z = norm1(n1.x, d1.x, f.z, inv);
+        o.w = norm1(n1.y, d1.y, f.w, inv);
         reinterpret_cast<float4 *>(out)[i] = o;
     }
     for (long long i = (nv << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = norm1(numq[i], denq[i], fb[i]);
+        out[i] = norm1(numq[i], denq[i], fb[i], inv);
 }
 
 // -------------------------------------------------------------- quantize ----
@@ -279,8 +280,8 @@ void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, 
     k_to_match<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, cf, scale, ishift);
 }
 void b4d_launch_normalise_det(const long long *numq, const long long *denq, const float *fallback, float *out,
-                              long long n, cudaStream_t s) {
-    k_normalise_det<<<grid_for(n >> 2, 256, 8), 256, 0, s>>>(numq, denq, fallback, out, n);
+                              long long n, float inv_qscale, cudaStream_t s) {
+    k_normalise_det<<<grid_for(n >> 2, 256, 8), 256, 0, s>>>(numq, denq, fallback, out, n, inv_qscale);
 }
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s) {

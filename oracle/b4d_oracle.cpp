@@ -478,7 +478,12 @@ inline void ghaar_inv(float *st, int kp) {
 inline int group_level(int k, int lg) { return k == 0 ? lg : 1 + __builtin_ctz((unsigned)k); }
 inline int spatial_class(int v) { return ((v & 3) >= 2) + (((v >> 2) & 3) >= 2) + ((v >> 4) >= 2); }
 
-constexpr float FIX_SCALE = 4294967296.0f;  // 2^32
+// Aggregation in fixed point (order independent), as csrc/b4d_filter.cu does: the weight of a
+// block position is quantised to 20 bits, wq = rint(w*win*2^20); the denominator is the integer
+// sum of wq, the numerator the sum of rint(wq*qscale*x) clamped below 2^39 (qscale = the
+// power-of-two scale of the matching map, so that |x|*qscale stays within the 16-bit range).
+constexpr float W_SCALE = 1048576.0f;  // 2^20
+constexpr float Q_LIMIT = 5.49e11f;    // < 2^39
 
 // Which DCT coefficient (cz*16 + cy*4 + cx) lane (zh, y, x), register rr of the
 // CUDA filter kernel holds after the forward transform (csrc/b4d_filter.cu):
@@ -492,7 +497,7 @@ inline int wiener_coeff(int lane, int rr) {
 
 template <bool WIENER>
 void filter_mirror(const float *zf, const float *basic, const Geom &g, const Matches &m, int Ns,
-                   const MirrorTables &t, std::vector<int64_t> &numq, std::vector<int64_t> &denq) {
+                   const MirrorTables &t, float qscale, std::vector<int64_t> &numq, std::vector<int64_t> &denq) {
     const int r = Ns / 2;
     const int nry = (int)g.ry.size(), nrx = (int)g.rx.size();
     const int64_t sy = g.W, sz = (int64_t)g.W * g.H;
@@ -594,8 +599,10 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
                         const int v = (z * 4 + y) * 4 + x;
                         const int64_t a = (cz[k] + z) * sz + (cy[k] + y) * sy + cx[k] + x;
                         const float ww = weight * t.win[v];
-                        const int64_t qn = llrintf((ww * noisy[k * LV + v]) * FIX_SCALE);
-                        const int64_t qd = llrintf(ww * FIX_SCALE);
+                        const int64_t qd = (int64_t)lrintf(ww * W_SCALE);
+                        const float wqf = (float)qd * qscale;
+                        const float tq = fminf(fmaxf(wqf * noisy[k * LV + v], -Q_LIMIT), Q_LIMIT);
+                        const int64_t qn = llrintf(tq);
 #pragma omp atomic
                         numq[a] += qn;
 #pragma omp atomic
@@ -710,9 +717,10 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     const MirrorTables t = make_tables(p, sigma);
     std::vector<int64_t> numq(V, 0), denq(V, 0);
     std::vector<float> basic(V);
-    filter_mirror<false>(zf.data(), nullptr, g1, m, p.search_ht, t, numq, denq);
+    const double inv_q = 1.0 / (double)mm.scale;
+    filter_mirror<false>(zf.data(), nullptr, g1, m, p.search_ht, t, mm.scale, numq, denq);
     for (int64_t i = 0; i < V; ++i)
-        basic[i] = denq[i] > 0 ? (float)((double)numq[i] / (double)denq[i]) : zf[i];
+        basic[i] = denq[i] > 0 ? (float)(((double)numq[i] / (double)denq[i]) * inv_q) : zf[i];
     if (p.stages == 1) {
         std::memcpy(out, basic.data(), V * sizeof(float));
         return 0;
@@ -721,9 +729,9 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     match_all(u.data(), g2, p.search_wie, p.k_wie, tau_int(p.tau_wie, sigma, mm.scale), m);
     std::fill(numq.begin(), numq.end(), 0);
     std::fill(denq.begin(), denq.end(), 0);
-    filter_mirror<true>(zf.data(), basic.data(), g2, m, p.search_wie, t, numq, denq);
+    filter_mirror<true>(zf.data(), basic.data(), g2, m, p.search_wie, t, mm.scale, numq, denq);
     for (int64_t i = 0; i < V; ++i)
-        out[i] = denq[i] > 0 ? (float)((double)numq[i] / (double)denq[i]) : basic[i];
+        out[i] = denq[i] > 0 ? (float)(((double)numq[i] / (double)denq[i]) * inv_q) : basic[i];
     return 0;
 }
 
