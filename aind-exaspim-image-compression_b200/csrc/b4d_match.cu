@@ -117,57 +117,59 @@ struct Geo {
 // For every block origin (z,y,x) with z <= D-4, y <= H-4, x <= W-4 (others are left
 // untouched): S2 = sum over the 4x4x4 block of u^2 (exact, < 2^38) and S1 = sum of u
 // (< 2^22), packed as uint2 {S2 mod 2^32, S1 | (S2 >> 32) << 24}.
-// One thread per (z, y, 4 consecutive x): 16 rows of 7 values from L1/L2.
+// Separable box sums: a CTA owns an 8 x 32 (y, x) tile of origins and marches along z; each
+// input plane tile (11 x 35) goes through shared memory once (4-tap sums along x, then along
+// y), the sum over 4 planes slides in registers.  HBM-bound: 2 B read + 8 B written per voxel.
+constexpr int K0_TY = 8, K0_TX = 32, K0_ZC = 64;
 __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict__ u, uint2 *__restrict__ s21, int D,
                                                       int H, int W, int nvol) {
-    const int xq = (W - 3 + 3) / 4;
-    const long long per_vol = (long long)(D - 3) * (H - 3) * xq;
-    const long long total = per_vol * nvol;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int vol = (int)(i / per_vol);
-        long long r = i - (long long)vol * per_vol;
-        const int x0 = (int)(r % xq) * 4;
-        r /= xq;
-        const int y = (int)(r % (H - 3)), z = (int)(r / (H - 3));
-        const uint16_t *p = u + (long long)vol * D * H * W + ((long long)z * H + y) * W + x0;
-        unsigned long long s[4] = {0ull, 0ull, 0ull, 0ull};  // block energies (< 2^38)
-        uint32_t t[4] = {0u, 0u, 0u, 0u};                    // block sums S1 (< 2^22)
-        const int nx = min(7, W - x0);
-#pragma unroll
-        for (int dz = 0; dz < 4; ++dz)
-#pragma unroll
-            for (int dy = 0; dy < 4; ++dy) {
-                const uint16_t *row = p + ((long long)dz * H + dy) * W;
-                uint32_t q[7], l[7];
-#pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                    const uint32_t v = (k < nx) ? (uint32_t)__ldg(row + k) : 0u;
-                    q[k] = v * v;  // < 2^32
-                    l[k] = v;
-                }
-                const unsigned long long w0 = (unsigned long long)q[0] + q[1] + q[2] + q[3];
-                const unsigned long long w1 = w0 - q[0] + q[4];
-                const unsigned long long w2 = w1 - q[1] + q[5];
-                const unsigned long long w3 = w2 - q[2] + q[6];
-                s[0] += w0;
-                s[1] += w1;
-                s[2] += w2;
-                s[3] += w3;
-                const uint32_t m0 = l[0] + l[1] + l[2] + l[3];
-                const uint32_t m1 = m0 - l[0] + l[4];
-                const uint32_t m2 = m1 - l[1] + l[5];
-                const uint32_t m3 = m2 - l[2] + l[6];
-                t[0] += m0;
-                t[1] += m1;
-                t[2] += m2;
-                t[3] += m3;
-            }
-        const long long oo = (long long)vol * D * H * W + ((long long)z * H + y) * W + x0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (x0 + k <= W - 4)  // .x = S2 mod 2^32; .y = S1 | (S2 >> 32) << 24
-                s21[oo + k] = make_uint2((uint32_t)s[k], t[k] | ((uint32_t)(s[k] >> 32) << 24));
+    __shared__ uint16_t s_in[K0_TY + 3][K0_TX + 4];
+    __shared__ unsigned long long s_x2[K0_TY + 3][K0_TX];
+    __shared__ uint32_t s_x1[K0_TY + 3][K0_TX];
+    const int ntx = (W - 3 + K0_TX - 1) / K0_TX, nty = (H - 3 + K0_TY - 1) / K0_TY;
+    const int nzc = (D - 3 + K0_ZC - 1) / K0_ZC;
+    long long t = blockIdx.x;
+    const int txi = (int)(t % ntx);
+    t /= ntx;
+    const int tyi = (int)(t % nty);
+    t /= nty;
+    const int zci = (int)(t % nzc);
+    const int vol = (int)(t / nzc);
+    const int x0 = txi * K0_TX, y0 = tyi * K0_TY, z0 = zci * K0_ZC, z1 = min(z0 + K0_ZC, D - 3);
+    const uint16_t *__restrict__ uv = u + (long long)vol * D * H * W;
+    uint2 *__restrict__ ov = s21 + (long long)vol * D * H * W;
+    const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+    const bool wr = (y0 + ty <= H - 4) && (x0 + tx <= W - 4);
+    unsigned long long q1 = 0ull, q2 = 0ull, q3 = 0ull;  // plane sums of z-1, z-2, z-3
+    uint32_t l1 = 0u, l2 = 0u, l3 = 0u;
+    for (int z = z0; z < z1 + 3; ++z) {
+        for (int i = tid; i < (K0_TY + 3) * (K0_TX + 3); i += 256) {
+            const int yy = i / (K0_TX + 3), xx = i - yy * (K0_TX + 3);
+            const int gy = y0 + yy, gx = x0 + xx;
+            s_in[yy][xx] = (gy < H && gx < W) ? __ldg(uv + ((long long)z * H + gy) * W + gx) : (uint16_t)0;
+        }
+        __syncthreads();
+        for (int i = tid; i < (K0_TY + 3) * K0_TX; i += 256) {
+            const int yy = i >> 5, xx = i & 31;
+            const uint32_t a = s_in[yy][xx], b = s_in[yy][xx + 1], c = s_in[yy][xx + 2], d = s_in[yy][xx + 3];
+            s_x2[yy][xx] = (unsigned long long)(a * a) + (b * b) + (unsigned long long)(c * c) + (d * d);
+            s_x1[yy][xx] = a + b + c + d;
+        }
+        __syncthreads();
+        const unsigned long long q0 = s_x2[ty][tx] + s_x2[ty + 1][tx] + s_x2[ty + 2][tx] + s_x2[ty + 3][tx];
+        const uint32_t l0 = s_x1[ty][tx] + s_x1[ty + 1][tx] + s_x1[ty + 2][tx] + s_x1[ty + 3][tx];
+        if (z >= z0 + 3 && wr) {
+            const unsigned long long s = q0 + q1 + q2 + q3;
+            const uint32_t m = l0 + l1 + l2 + l3;
+            // .x = S2 mod 2^32; .y = S1 | (S2 >> 32) << 24
+            ov[((long long)(z - 3) * H + y0 + ty) * W + x0 + tx] = make_uint2((uint32_t)s, m | ((uint32_t)(s >> 32) << 24));
+        }
+        q3 = q2;
+        q2 = q1;
+        q1 = q0;
+        l3 = l2;
+        l2 = l1;
+        l1 = l0;
     }
 }
 
@@ -782,10 +784,8 @@ void launch_ns(const MatchParams &p, cudaStream_t s) {
 }  // namespace
 
 void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s) {
-    const long long total = (long long)(D - 3) * (H - 3) * ((W - 3 + 3) / 4) * nvol;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148ll * 64) blocks = 148ll * 64;
-    if (blocks < 1) blocks = 1;
+    const long long blocks = (long long)((W - 3 + K0_TX - 1) / K0_TX) * ((H - 3 + K0_TY - 1) / K0_TY) *
+                             ((D - 3 + K0_ZC - 1) / K0_ZC) * nvol;
     k_block_energy<<<(unsigned)blocks, 256, 0, s>>>(u, s21, D, H, W, nvol);
 }
 
