@@ -272,3 +272,45 @@ def test_patch_cache_written_by_the_gpu_path(tmp_path, b4d_mod, oracle_lib):
         want = np.clip(o.denoise(oracle_lib.read_counts(patches[i], float(offs[i])), 24.0), 0, 65535)
         assert np.array_equal(teacher[i], want)
     assert cache.write_patch_cache(d, patches, offs, 24.0, batch=3) == 0  # resume: nothing left
+
+
+@pytest.mark.parametrize(
+    "kw,okw",
+    [
+        # every filter-kernel instantiation: (stage, window class, group capacity)
+        (dict(search_window_ht=(7, 7, 7), search_window_wiener=(7, 7, 7)), dict(search_ht=15, search_wie=15)),
+        (dict(search_window_ht=(6, 6, 6), search_window_wiener=(3, 3, 3)), dict(search_ht=13, search_wie=7)),
+        (dict(max_stack_size_ht=32, max_stack_size_wiener=16), dict(k_ht=32, k_wie=16)),
+        (dict(max_stack_size_ht=8, max_stack_size_wiener=8), dict(k_ht=8, k_wie=8)),
+        (dict(max_stack_size_ht=1, max_stack_size_wiener=2, search_window_ht=(1, 1, 1)), dict(k_ht=1, k_wie=2, search_ht=3)),
+        (dict(beta=0.0, lambda_thr=3.1, tau_match_ht=1.5), dict(kaiser_beta=0.0, lambda_ht=3.1, tau_ht=1.5)),
+    ],
+)
+def test_other_profiles_bit_exact_vs_mirror(kw, okw, b4d_mod, oracle_lib):
+    """Non-default windows / group sizes / constants take other kernel instantiations (two-reference
+    tiles for windows above 11, 32-slot hard-threshold groups, 16-slot Wiener groups without the
+    warp-pair split); all must stay bit-exact against the mirror."""
+    from b4d import synth
+
+    rng = np.random.default_rng(5)
+    vols = [synth.vol(22, 25, 28, seed=21), np.clip(rng.normal(300, 24, (17, 18, 20)), 0, 65535).astype(np.uint16)]
+    d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(**kw))
+    for vol in vols:
+        for stages in (1, 2):
+            d.set_profile(b4d_mod.BM4DProfile(**kw), stages)
+            y = d.denoise(vol, 24.0)
+            m = oracle_lib.Oracle("mirror", stages=stages, **okw).denoise(vol, 24.0)
+            assert np.array_equal(y, m), "stages %d: max-abs %g" % (stages, np.abs(y - m).max())
+    d.close()
+
+
+def test_many_contributions_do_not_overflow_the_shared_accumulators(b4d_mod, oracle_lib):
+    """A constant volume makes every SSD tie at 0: each group takes the lowest-index candidates, the
+    grouped blocks overlap as much as they can and a voxel collects thousands of terms — the bound
+    the 32-bit shared-memory limbs of the filter kernels are sized for."""
+    c = np.full((40, 40, 40), 60000, np.uint16)
+    d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(max_stack_size_ht=32))
+    y = d.denoise(c, 24.0)
+    m = oracle_lib.Oracle("mirror", k_ht=32).denoise(c, 24.0)
+    assert np.array_equal(y, m) and np.abs(y - 60000.0).max() < 1e-2
+    d.close()
