@@ -17,7 +17,15 @@ from .api import (  # noqa: F401
     tile_stats,
 )
 from .cache import load_patch_cache, write_patch_cache  # noqa: F401
-from .sharding import denoise_volume_sharded, merge_histograms, slab_plan, stats_from_hist  # noqa: F401
+from .sharding import (  # noqa: F401
+    denoise_slab_exchange,
+    denoise_volume_sharded,
+    exchange_halo,
+    exchange_planes,
+    merge_histograms,
+    slab_plan,
+    stats_from_hist,
+)
 
 __all__ = [
     "BM4DProfile",
@@ -33,6 +41,9 @@ __all__ = [
     "slab_plan",
     "denoise_volume_sharded",
     "merge_histograms",
+    "denoise_slab_exchange",
+    "exchange_halo",
+    "exchange_planes",
     "stats_from_hist",
     "write_patch_cache",
     "load_patch_cache",

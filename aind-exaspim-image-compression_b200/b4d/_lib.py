@@ -24,6 +24,9 @@ EXPORTS = (
     "b4d_denoise_u16",
     "b4d_denoise_f32",
     "b4d_denoise_slab_u16",
+    "b4d_slab_stage1_u16",
+    "b4d_slab_basic_planes",
+    "b4d_slab_stage2",
     "b4d_match_stage1",
     "b4d_num_refs",
     "b4d_quantize_u16",

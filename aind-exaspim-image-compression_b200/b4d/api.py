@@ -228,6 +228,86 @@ class Denoiser:
         )
         return out
 
+    # ---- the slab in two calls, for one neighbour exchange between the stages ----
+    def slab_stage1(self, slab, z_begin, z_total, sigma):
+        """Stage 1 on a uint16 slab (NumPy or torch); the basic estimate stays on the device."""
+        if _is_torch(slab):
+            import torch
+
+            sc = slab.contiguous()
+            if sc.dtype != torch.uint16 or sc.ndim != 3:
+                raise ValueError("slab must be a 3-D uint16 tensor")
+            on_dev = sc.is_cuda
+            if on_dev:
+                torch.cuda.current_stream(sc.device).synchronize()
+            ptr, shape = sc.data_ptr(), tuple(sc.shape)
+        else:
+            sc = np.ascontiguousarray(slab)
+            if sc.dtype != np.uint16 or sc.ndim != 3:
+                raise ValueError("slab must be a 3-D uint16 array")
+            on_dev, ptr, shape = False, sc.ctypes.data, sc.shape
+        self._slab_shape = tuple(int(v) for v in shape)
+        _lib.check(
+            self.lib.b4d_slab_stage1_u16(self._h, ctypes.c_void_p(ptr), _lib.shape3(shape), ctypes.c_int64(z_begin),
+                                         ctypes.c_int64(z_total), ctypes.c_float(sigma), int(on_dev))
+        )
+
+    def slab_basic(self, plane0, nplanes, device=None):
+        """Planes [plane0, plane0 + nplanes) (slab-local) of the basic estimate: a torch CUDA
+        tensor when `device` is given, else a NumPy array."""
+        shape = (int(nplanes),) + self._slab_shape[1:]
+        if device is not None:
+            import torch
+
+            buf = torch.empty(shape, dtype=torch.float32, device=device)
+            ptr, on_dev = buf.data_ptr(), True
+        else:
+            buf = np.empty(shape, dtype=np.float32)
+            ptr, on_dev = buf.ctypes.data, False
+        if nplanes:
+            _lib.check(self.lib.b4d_slab_basic_planes(self._h, ctypes.c_int64(plane0), ctypes.c_int64(nplanes),
+                                                      ctypes.c_void_p(ptr), 0, int(on_dev)))
+        return buf
+
+    def slab_set_basic(self, plane0, planes):
+        """Overwrite planes of the basic estimate (the neighbour's exact halo planes)."""
+        if _is_torch(planes):
+            import torch
+
+            pc = planes.contiguous()
+            if pc.dtype != torch.float32:
+                raise ValueError("planes must be float32")
+            if pc.is_cuda:
+                torch.cuda.current_stream(pc.device).synchronize()
+            ptr, on_dev, n = pc.data_ptr(), pc.is_cuda, pc.shape[0]
+        else:
+            pc = np.ascontiguousarray(planes, dtype=np.float32)
+            ptr, on_dev, n = pc.ctypes.data, False, pc.shape[0]
+        if tuple(pc.shape[1:]) != self._slab_shape[1:]:
+            raise ValueError("planes must have the slab's (H, W)")
+        if n:
+            _lib.check(self.lib.b4d_slab_basic_planes(self._h, ctypes.c_int64(plane0), ctypes.c_int64(n),
+                                                      ctypes.c_void_p(ptr), 1, int(on_dev)))
+
+    def slab_stage2(self, own_begin, own_end, out=None, device=None):
+        """Stage 2 on the completed basic estimate -> float32 owned planes (NumPy, or torch on
+        `device`; `out` may be a preallocated NumPy array, e.g. pinned)."""
+        oshape = (int(own_end - own_begin),) + self._slab_shape[1:]
+        if device is not None:
+            import torch
+
+            out = torch.empty(oshape, dtype=torch.float32, device=device)
+            ptr, on_dev = out.data_ptr(), True
+        else:
+            if out is None:
+                out = np.empty(oshape, dtype=np.float32)
+            elif out.shape != oshape or out.dtype != np.float32 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float32 array of shape %r" % (oshape,))
+            ptr, on_dev = out.ctypes.data, False
+        _lib.check(self.lib.b4d_slab_stage2(self._h, ctypes.c_int64(own_begin), ctypes.c_int64(own_end),
+                                            ctypes.c_void_p(ptr), int(on_dev)))
+        return out
+
     def match_stage1(self, vol, sigma):
         """Instrumented stage-1 matcher: (idx[R,K] int32, ssd[R,K] uint64, count[R] int32)."""
         vol = np.ascontiguousarray(vol)

@@ -38,16 +38,79 @@ def slab_plan(z_total, world, rank, halo):
     return own_begin, own_end, z_begin, z_end
 
 
-def denoise_volume_sharded(get_slab, z_total, sigma, denoiser, world=1, rank=0):
+def exchange_halo(search_ht=11, search_wie=11):
+    """Halo per interior face when neighbours swap basic-estimate planes between the stages
+    ("one exchange step"): the larger of the two per-stage halos."""
+    return max(search_ht, search_wie) - 1 + L - 1
+
+
+def exchange_planes(send_down, send_up, recv_below, recv_above, rank, world, group=None):
+    """Neighbour exchange of z-planes between consecutive ranks: `send_down` goes to rank - 1
+    (which receives it as its `recv_above`), `send_up` to rank + 1.  Tensors on the rank's CUDA
+    device (NCCL point-to-point over NVLink) or on the CPU (gloo); None where there is no
+    neighbour.  Returns when the received planes are complete."""
+    import torch.distributed as dist
+
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, send_down, rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, recv_below, rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, send_up, rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, recv_above, rank + 1, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def denoise_slab_exchange(denoiser, slab, z_begin, z_total, own_begin, own_end, sigma, rank, world, device=None,
+                          out=None, group=None):
+    """One rank's part of the exchange variant: stage 1 on the slab (halo `exchange_halo`), swap
+    the exact basic-estimate planes next to each interior face with the neighbours, stage 2.
+    `device` = the rank's torch CUDA device (planes then travel device to device)."""
+    import torch
+
+    denoiser.slab_stage1(slab, z_begin, z_total, sigma)
+    lo_h, hi_h = own_begin - z_begin, (z_begin + slab.shape[0]) - own_end
+    if (rank > 0 and own_end - own_begin < lo_h) or (rank < world - 1 and own_end - own_begin < hi_h):
+        raise ValueError("every rank must own at least as many planes as the halo")
+    o0, o1 = own_begin - z_begin, own_end - z_begin  # owned planes, slab-local
+
+    def planes(p0, n):
+        t = denoiser.slab_basic(p0, n, device=device)
+        return t if device is not None else torch.from_numpy(t)
+
+    send_down = planes(o0, lo_h) if rank > 0 else None           # the neighbour's upper halo
+    send_up = planes(o1 - hi_h, hi_h) if rank < world - 1 else None
+    hw = tuple(slab.shape[1:])
+    mk = (lambda n: torch.empty((n,) + hw, dtype=torch.float32, device=device)) if device is not None else (
+        lambda n: torch.empty((n,) + hw, dtype=torch.float32))
+    recv_below = mk(lo_h) if rank > 0 else None
+    recv_above = mk(hi_h) if rank < world - 1 else None
+    exchange_planes(send_down, send_up, recv_below, recv_above, rank, world, group)
+    if recv_below is not None:
+        denoiser.slab_set_basic(0, recv_below if device is not None else recv_below.numpy())
+    if recv_above is not None:
+        denoiser.slab_set_basic(o1, recv_above if device is not None else recv_above.numpy())
+    return denoiser.slab_stage2(own_begin, own_end, out=out, device=device if out is None else None)
+
+
+def denoise_volume_sharded(get_slab, z_total, sigma, denoiser, world=1, rank=0, exchange=False, device=None):
     """Denoise this rank's share of a (z_total, H, W) uint16 volume.
 
     get_slab(z_begin, z_end) -> uint16 array/tensor of those planes (host or
-    device).  Returns (own_begin, own_end, float32 planes).
+    device).  Returns (own_begin, own_end, float32 planes).  With `exchange`
+    (needs an initialised process group when world > 1) the slabs carry half the
+    halo and neighbours swap basic-estimate planes between the stages.
     """
     p = denoiser.profile
-    halo = halo_planes(2 * int(np.ravel(p.search_window_ht)[0]) + 1, 2 * int(np.ravel(p.search_window_wiener)[0]) + 1,
-                       denoiser._stages)
-    own_begin, own_end, z_begin, z_end = slab_plan(z_total, world, rank, halo)
+    ns1, ns2 = 2 * int(np.ravel(p.search_window_ht)[0]) + 1, 2 * int(np.ravel(p.search_window_wiener)[0]) + 1
+    if exchange and denoiser._stages == 2 and world > 1:
+        own_begin, own_end, z_begin, z_end = slab_plan(z_total, world, rank, exchange_halo(ns1, ns2))
+        out = denoise_slab_exchange(denoiser, get_slab(z_begin, z_end), z_begin, z_total, own_begin, own_end, sigma,
+                                    rank, world, device=device)
+        return own_begin, own_end, out
+    own_begin, own_end, z_begin, z_end = slab_plan(z_total, world, rank, halo_planes(ns1, ns2, denoiser._stages))
     slab = get_slab(z_begin, z_end)
     out = denoiser.denoise_slab(slab, z_begin, z_total, own_begin, own_end, sigma)
     return own_begin, own_end, out

@@ -73,6 +73,13 @@ struct b4d_handle {
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
     unsigned long long match_stats[4];
+    // state between b4d_slab_stage1_u16 and b4d_slab_stage2
+    bool slab_open = false;
+    int64_t slab_shape[3] = {0, 0, 0};
+    int64_t slab_z_begin = 0, slab_z_total = 0;
+    float slab_sigma = 0.f;
+    float slab_cf = 0.f, slab_scale = 1.f;
+    int slab_ishift = 0;
 };
 
 namespace {
@@ -249,8 +256,10 @@ struct StageClock {
 //   d_zf   float32 noisy volumes            [nvol*V]
 //   d_u    uint16 matching image (stage 1)  [nvol*V]   (overwritten by stage 2)
 //   d_out  float32 result                   [nvol*V]
+// phase 0 = both stages; 1 = stage 1 only (basic estimate left in h->basic); 2 = stage 2 only
+// (h->basic holds the basic estimate, possibly completed by a neighbour exchange).
 int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u, const MatchMap &mm, float sigma,
-                 float *d_out, StageClock &clk) {
+                 float *d_out, StageClock &clk, int phase = 0) {
     const b4d_profile &p = h->prof;
     const long long V = (long long)pl.D * pl.H * pl.W, TV = V * pl.nvol;
     cudaStream_t s = h->stream;
@@ -299,7 +308,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     B4D_TRY(h->denq.ensure((size_t)TV * sizeof(long long)));
     const B4dTables tab = make_tables(p, sigma);
     b4d_upload_tables(tab, s);
-    CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
+    if (phase != 2) CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
 
     auto zero_acc = [&]() -> int {
         CU_TRY(cudaMemsetAsync(h->numq.p, 0, (size_t)TV * sizeof(long long), s));
@@ -310,13 +319,14 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         b4d_launch_normalise_det(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, TV, 1.0f / mm.scale, s);
     };
 
-    float *d_basic = (p.stages == 1) ? d_out : h->basic.as<float>();
-
+    float *d_basic = (p.stages == 1 && phase == 0) ? d_out : h->basic.as<float>();
+    MatchParams mp;
+    FilterParams fp;
+    if (phase != 2) {
     // ---- stage 1: hard thresholding
     B4D_TRY(zero_acc());
     b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 2);
-    MatchParams mp;
     mp.g = g1;
     mp.u = d_u;
     mp.s21 = h->s2.as<uint2>();
@@ -330,7 +340,6 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     mp.stats = h->stats.as<unsigned long long>();
     if (R1 > 0) b4d_launch_match(mp, p.search_ht, s);
     clk.mark(B4D_T_MATCH1, 4);
-    FilterParams fp;
     fp.g = g1;
     fp.zf = d_zf;
     fp.basic = nullptr;
@@ -347,7 +356,25 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     normalise(d_zf, d_basic);
     clk.mark(B4D_T_NORM1, 1);
     CU_TRY(cudaGetLastError());
-    if (p.stages == 1) return 0;
+    }
+    if (p.stages == 1 || phase == 1) return 0;
+    if (phase == 2) {  // the stage-1 call filled everything but the stage-2 specific fields
+        mp.u = d_u;
+        mp.s21 = h->s2.as<uint2>();
+        mp.cells = h->cells.as<uint32_t>();
+        mp.tcls = h->tcls.as<uint32_t>();
+        mp.widx = h->widx.as<uint16_t>();
+        mp.cnt = h->cnt.as<uint8_t>();
+        mp.ssd_out = nullptr;
+        mp.stats = h->stats.as<unsigned long long>();
+        fp.zf = d_zf;
+        fp.widx = mp.widx;
+        fp.cnt = mp.cnt;
+        fp.nseg = 1;
+        fp.qscale = mm.scale;
+        fp.numq = h->numq.as<long long>();
+        fp.denq = h->denq.as<long long>();
+    }
 
     // ---- stage 2: Wiener, matching on the basic estimate
     b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
@@ -617,6 +644,101 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static Plan slab_plan_of(const b4d_handle *h) {
+    Plan pl;
+    pl.D = (int)h->slab_shape[0];
+    pl.H = (int)h->slab_shape[1];
+    pl.W = (int)h->slab_shape[2];
+    pl.nvol = 1;
+    pl.rz1 = slab_origins(h->slab_z_total, h->slab_z_begin, h->slab_shape[0], h->prof.search_ht / 2);
+    pl.rz2 = slab_origins(h->slab_z_total, h->slab_z_begin, h->slab_shape[0], h->prof.search_wie / 2);
+    pl.ry = ref_origins(h->slab_shape[1]);
+    pl.rx = ref_origins(h->slab_shape[2]);
+    return pl;
+}
+
+int b4d_slab_stage1_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], int64_t z_begin, int64_t z_total,
+                        float sigma, int in_on_device) {
+    B4D_TRY(common_checks(h, in, in, shape, sigma));
+    if (z_begin < 0 || z_begin + shape[0] > z_total) return fail(B4D_ERR_INVALID, "slab range inconsistent");
+    if (h->prof.stages != 2) return fail(B4D_ERR_INVALID, "the two-call slab form needs stages = 2");
+    reset_timings(h);
+    cudaStream_t s = h->stream;
+    const long long V = shape[0] * shape[1] * shape[2];
+    for (int i = 0; i < 3; ++i) h->slab_shape[i] = shape[i];
+    h->slab_z_begin = z_begin;
+    h->slab_z_total = z_total;
+    h->slab_sigma = sigma;
+    h->slab_open = false;
+    const Plan pl = slab_plan_of(h);
+    B4D_TRY(h->in.ensure((size_t)V * sizeof(uint16_t)));
+    B4D_TRY(h->u16.ensure((size_t)V * sizeof(uint16_t) + 16));
+    B4D_TRY(h->zf.ensure((size_t)V * sizeof(float)));
+    B4D_TRY(h->out.ensure((size_t)V * sizeof(float)));
+    StageClock clk(h);
+    CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)V * sizeof(uint16_t),
+                           in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    clk.mark(-1, 0);
+    MatchMap mm;
+    B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), V, &mm));
+    clk.mark(B4D_T_PREP, 1);
+    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk, 1));
+    CU_TRY(cudaStreamSynchronize(s));
+    clk.resolve();
+    h->slab_cf = mm.cf;
+    h->slab_scale = mm.scale;
+    h->slab_ishift = mm.ishift;
+    h->slab_open = true;
+    return 0;
+}
+
+int b4d_slab_basic_planes(b4d_handle *h, int64_t plane0, int64_t nplanes, float *buf, int to_handle,
+                          int buf_on_device) {
+    if (!h || !buf) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!h->slab_open) return fail(B4D_ERR_INVALID, "b4d_slab_stage1_u16 has not been called");
+    if (plane0 < 0 || nplanes < 0 || plane0 + nplanes > h->slab_shape[0])
+        return fail(B4D_ERR_INVALID, "plane range outside the slab");
+    CU_TRY(cudaSetDevice(h->device));
+    const size_t P = (size_t)h->slab_shape[1] * h->slab_shape[2];
+    float *dev = h->basic.as<float>() + (size_t)plane0 * P;
+    const size_t bytes = (size_t)nplanes * P * sizeof(float);
+    if (to_handle)
+        CU_TRY(cudaMemcpyAsync(dev, buf, bytes, buf_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               h->stream));
+    else
+        CU_TRY(cudaMemcpyAsync(buf, dev, bytes, buf_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                               h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int b4d_slab_stage2(b4d_handle *h, int64_t own_begin, int64_t own_end, float *out, int out_on_device) {
+    if (!h || !out) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!h->slab_open) return fail(B4D_ERR_INVALID, "b4d_slab_stage1_u16 has not been called");
+    const int64_t zb = h->slab_z_begin, D = h->slab_shape[0];
+    if (own_begin < zb || own_end > zb + D || own_begin >= own_end)
+        return fail(B4D_ERR_INVALID, "owned range outside the slab");
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const long long P = h->slab_shape[1] * h->slab_shape[2];
+    const Plan pl = slab_plan_of(h);
+    MatchMap mm;
+    mm.cf = h->slab_cf;
+    mm.scale = h->slab_scale;
+    mm.ishift = h->slab_ishift;
+    StageClock clk(h);
+    clk.mark(-1, 0);
+    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, h->slab_sigma, h->out.as<float>(), clk, 2));
+    CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - zb) * P,
+                           (size_t)(own_end - own_begin) * P * sizeof(float),
+                           out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    clk.resolve();
+    CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    h->slab_open = false;
     return 0;
 }
 

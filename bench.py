@@ -147,9 +147,10 @@ def probe_real_bm4d():
         sys.path[:] = saved
 
 
-def workload_config(S, halo):
+def workload_config(S, halo, exchange=False):
     return {
-        "workload": "BM4D HT+Wiener denoise of one uint16 %d^3 volume (BASELINE configs[3]), z-slabs + halo %d" % (S, halo),
+        "workload": "BM4D HT+Wiener denoise of one uint16 %d^3 volume (BASELINE configs[3]), z-slabs + halo %d%s"
+        % (S, halo, " + one neighbour exchange of basic-estimate planes between the stages" if exchange else ""),
         "sigma": SIGMA, "Ns": NS, "K_ht": K_HT, "K_wiener": K_WIE,
     }
 
@@ -232,6 +233,9 @@ def main():
     ap.add_argument("--impl", default="b4d", choices=["b4d", "reference"])
     ap.add_argument("--size", type=int, default=1024, help="volume side (default 1024: the metric's config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true",
+                    help="N > 1: 26-plane halos and no data-path exchange instead of 13-plane halos + one "
+                         "neighbour exchange of basic-estimate planes between the stages")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -240,7 +244,8 @@ def main():
     import torch.distributed as dist
 
     import b4d
-    from b4d.sharding import halo_planes, merge_histograms, slab_plan, stats_from_hist
+    from b4d.sharding import (denoise_slab_exchange, exchange_halo, halo_planes, merge_histograms, slab_plan,
+                              stats_from_hist)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -254,7 +259,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     S = args.size
-    halo = halo_planes(NS, NS, 2)
+    exchange = world > 1 and not args.no_exchange
+    halo = exchange_halo(NS, NS) if exchange else halo_planes(NS, NS, 2)
     own_b, own_e, zb, ze = slab_plan(S, world, rank, halo)
     dn = b4d.Denoiser(local)
     t0 = time.perf_counter()
@@ -283,12 +289,19 @@ def main():
 
     def step_resident():
         st = stats_step()
-        y = dn.denoise_slab(slab_dev, zb, S, own_b, own_e, SIGMA)
+        if exchange:  # stage 1, neighbour exchange of basic-estimate planes (NCCL p2p), stage 2
+            y = denoise_slab_exchange(dn, slab_dev, zb, S, own_b, own_e, SIGMA, rank, world, device=dev)
+        else:
+            y = dn.denoise_slab(slab_dev, zb, S, own_b, own_e, SIGMA)
         return st, y
 
     def step_e2e():
         # host in -> host out through the public API; H2D and D2H happen inside the call
-        dn.denoise_slab(slab_pin.numpy(), zb, S, own_b, own_e, SIGMA, out=out_pin.numpy())
+        if exchange:
+            denoise_slab_exchange(dn, slab_pin.numpy(), zb, S, own_b, own_e, SIGMA, rank, world, device=dev,
+                                  out=out_pin.numpy())
+        else:
+            dn.denoise_slab(slab_pin.numpy(), zb, S, own_b, own_e, SIGMA, out=out_pin.numpy())
 
     # ---- warm-up (also sizes the scratch buffers)
     stats = None
@@ -402,7 +415,7 @@ def main():
             "dtype": "int32+f32",
             "data": "synthetic",
             "config": dict(
-                workload_config(S, halo),
+                workload_config(S, halo, exchange),
                 l2="inputs larger than L2 (%.2f GiB slab per rank)" % (slab_pin.numel() * 2 / 2 ** 30),
                 timing="CUDA events on the library stream around the K steps, between barrier + synchronize, max over ranks",
             ),

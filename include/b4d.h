@@ -119,6 +119,23 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
                          int64_t z_begin, int64_t z_total, int64_t own_begin, int64_t own_end,
                          float sigma, float *out, int in_on_device, int out_on_device);
 
+/* The same slab in two calls with ONE neighbour exchange in between ("one
+ * exchange step"): the slab then needs only (Ns-1+L-1) = 13 halo planes per interior face
+ * instead of 26.
+ *   1. b4d_slab_stage1_u16   stage 1 on the slab; the basic estimate stays on the device.
+ *      It is exact on the planes at least 13 inside the slab's interior faces.
+ *   2. b4d_slab_basic_planes copies planes of the basic estimate out of (to_handle = 0) or
+ *      into (to_handle = 1) the handle, slab-local plane numbering: every rank sends its
+ *      exact planes next to a face and overwrites its halo planes with the neighbour's.
+ *   3. b4d_slab_stage2       stage 2 on the completed basic estimate; `out` receives the
+ *      owned planes [own_begin, own_end) (global numbering).
+ * Equal, bit for bit, to the whole-volume result. */
+int b4d_slab_stage1_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
+                        int64_t z_total, float sigma, int in_on_device);
+int b4d_slab_basic_planes(b4d_handle *h, int64_t plane0, int64_t nplanes, float *buf, int to_handle,
+                          int buf_on_device);
+int b4d_slab_stage2(b4d_handle *h, int64_t own_begin, int64_t own_end, float *out, int out_on_device);
+
 /* Instrumented stage-1 matcher (bit-exactness test, BASELINE config 3).
  * R = number of reference blocks, K = profile.k_ht.  Host pointers.
  *   idx[R*K]   linear candidate origin (z*H' + y)*W' + x, H' = H-L+1, W' = W-L+1; -1 = unused

@@ -895,6 +895,16 @@ int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *,
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }
 void *b4d_stream(b4d_handle *) { return nullptr; }
+// the two-call slab form exists for multi-GPU exchange only; the oracle has the one-call form
+int b4d_slab_stage1_u16(b4d_handle *, const uint16_t *, const int64_t *, int64_t, int64_t, float, int) {
+    return fail(B4D_ERR_UNSUPPORTED, "oracle: use b4d_denoise_slab_u16");
+}
+int b4d_slab_basic_planes(b4d_handle *, int64_t, int64_t, float *, int, int) {
+    return fail(B4D_ERR_UNSUPPORTED, "oracle: use b4d_denoise_slab_u16");
+}
+int b4d_slab_stage2(b4d_handle *, int64_t, int64_t, float *, int) {
+    return fail(B4D_ERR_UNSUPPORTED, "oracle: use b4d_denoise_slab_u16");
+}
 int b4d_last_timings(b4d_handle *, float *, int64_t *) {
     return fail(B4D_ERR_UNSUPPORTED, "no device timings in the oracle");
 }

@@ -314,3 +314,34 @@ def test_many_contributions_do_not_overflow_the_shared_accumulators(b4d_mod, ora
     m = oracle_lib.Oracle("mirror", k_ht=32).denoise(c, 24.0)
     assert np.array_equal(y, m) and np.abs(y - 60000.0).max() < 1e-2
     d.close()
+
+
+def test_exchange_variant_slabs_equal_whole(b4d_mod):
+    """SURVEY §8e "one exchange step": 13-plane halos, neighbours swap their exact basic-estimate
+    planes between the stages.  Ranks are emulated by one handle each on this GPU; the union of
+    the owned planes must equal the whole-volume result bit for bit."""
+    from b4d import synth
+    from b4d.sharding import exchange_halo, slab_plan
+
+    vol = synth.vol(96, 24, 28, seed=9)
+    whole = b4d_mod.Denoiser(0).denoise(vol, 24.0)
+    h = exchange_halo(11, 11)
+    for world in (2, 3):
+        ranks = []
+        for r in range(world):
+            ob, oe, zb, ze = slab_plan(96, world, r, h)
+            d = b4d_mod.Denoiser(0)
+            d.slab_stage1(vol[zb:ze], zb, 96, 24.0)
+            ranks.append((d, ob, oe, zb, ze))
+        sends = []
+        for d, ob, oe, zb, ze in ranks:  # what every rank would send: exact planes next to its faces
+            sends.append((d.slab_basic(ob - zb, h), d.slab_basic(oe - zb - h, h)))
+        parts = []
+        for r, (d, ob, oe, zb, ze) in enumerate(ranks):
+            if r > 0:
+                d.slab_set_basic(0, sends[r - 1][1])        # the lower neighbour's top planes
+            if r < world - 1:
+                d.slab_set_basic(oe - zb, sends[r + 1][0])  # the upper neighbour's bottom planes
+            parts.append(d.slab_stage2(ob, oe))
+            d.close()
+        assert np.array_equal(np.concatenate(parts, 0), whole)

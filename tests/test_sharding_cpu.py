@@ -102,3 +102,48 @@ def test_two_rank_slabs_and_histogram_allgather(oracle_lib):
     assert np.array_equal(got, whole)  # shard == whole, bit for bit
     want = stats_from_hist(np.bincount(vol.reshape(-1), minlength=65536), 1.0)
     assert res[0][4] == want and res[1][4] == want  # every rank derives the same global statistics
+
+
+def _xworker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, "aind-exaspim-image-compression_b200"))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from b4d.sharding import exchange_planes
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        h, hw = 3, (4, 5)
+        down = torch.full((h,) + hw, float(10 * rank + 1)) if rank > 0 else None
+        up = torch.full((h,) + hw, float(10 * rank + 2)) if rank < world - 1 else None
+        below = torch.zeros((h,) + hw) if rank > 0 else None
+        above = torch.zeros((h,) + hw) if rank < world - 1 else None
+        exchange_planes(down, up, below, above, rank, world)
+        q.put((rank, None if below is None else float(below.mean()), None if above is None else float(above.mean())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_neighbour_plane_exchange_three_ranks():
+    """The exchange variant's one data-path collective: every rank swaps halo planes with its two
+    neighbours (gloo here, NCCL point-to-point on the GPUs)."""
+    import torch.multiprocessing as mp
+
+    from b4d.sharding import exchange_halo, halo_planes, slab_plan
+
+    assert exchange_halo(11, 11) == 13 and exchange_halo(15, 11) == 17 and 2 * exchange_halo(11, 11) == halo_planes(11, 11, 2)
+    ob, oe, zb, ze = slab_plan(1024, 8, 3, exchange_halo(11, 11))
+    assert (oe - ob, ze - zb) == (128, 154)  # 128 + 2*13 planes instead of 128 + 2*26
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_xworker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # rank r receives rank r-1's `up` (10(r-1)+2) from below and rank r+1's `down` (10(r+1)+1) from above
+    assert res[0] == (0, None, 11.0) and res[1] == (1, 2.0, 21.0) and res[2] == (2, 12.0, None)
