@@ -67,6 +67,7 @@ struct DevBuf {
 struct b4d_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // normalise + device-to-host of finished planes, overlapped with stage 2
     b4d_profile prof;
     DevBuf in, u16, zf, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2, cells, tcls;
     cudaEvent_t ev[B4D_T_COUNT + 1];
@@ -256,10 +257,20 @@ struct StageClock {
 //   d_zf   float32 noisy volumes            [nvol*V]
 //   d_u    uint16 matching image (stage 1)  [nvol*V]   (overwritten by stage 2)
 //   d_out  float32 result                   [nvol*V]
+// Where the result goes when it is wanted in HOST memory: planes [p0, p1) of the (single)
+// volume, to `host` (p1 - p0 planes).  Stage 2 then runs in z chunks and every chunk of
+// finished planes is normalised and copied out on a second stream while the next chunks
+// still compute — the device-to-host copy (4 B/voxel over PCIe) hides behind the filter.
+struct HostSink {
+    float *host = nullptr;
+    long long p0 = 0, p1 = 0;
+    bool done = false;  // set when run_pipeline delivered the result itself
+};
+
 // phase 0 = both stages; 1 = stage 1 only (basic estimate left in h->basic); 2 = stage 2 only
 // (h->basic holds the basic estimate, possibly completed by a neighbour exchange).
 int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u, const MatchMap &mm, float sigma,
-                 float *d_out, StageClock &clk, int phase = 0) {
+                 float *d_out, StageClock &clk, int phase = 0, HostSink *sink = nullptr) {
     const b4d_profile &p = h->prof;
     const long long V = (long long)pl.D * pl.H * pl.W, TV = V * pl.nvol;
     cudaStream_t s = h->stream;
@@ -390,6 +401,47 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.basic = d_basic;
     fp.K = p.k_wie;
     fp.Ns = p.search_wie;
+    const long long P = (long long)pl.H * pl.W;
+    constexpr int NCH = 8;
+    const int nseg_ch = (sink && sink->host && pl.nvol == 1 && R2 > 0 && (P & 3) == 0) ? b4d_filter_segments(fp, NCH) : 0;
+    if (nseg_ch >= NCH && nseg_ch % NCH == 0) {
+        // chunked: launch everything on the compute stream first (events between the chunks), then
+        // queue normalise + copy of the planes each chunk finishes on the copy stream
+        const int spc = nseg_ch / NCH, r2 = p.search_wie / 2;
+        cudaEvent_t evs[NCH];
+        for (int c = 0; c < NCH; ++c) {
+            b4d_launch_filter_segments(fp, true, nseg_ch, c * spc, spc, s);
+            CU_TRY(cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming));
+            CU_TRY(cudaEventRecord(evs[c], s));
+        }
+        clk.mark(B4D_T_FILTER2, NCH);
+        long long zdone = 0;
+        for (int c = 0; c < NCH; ++c) {
+            // after chunk c: no later segment touches a plane below the window of its first reference
+            long long zfin = pl.D;
+            if (c + 1 < NCH) {
+                const int iz_next = (int)((long long)(c + 1) * spc * g2.nrz / nseg_ch);
+                zfin = std::max<long long>(0, (long long)pl.rz2[iz_next] - r2);
+            }
+            CU_TRY(cudaStreamWaitEvent(h->copy_stream, evs[c], 0));
+            if (zfin > zdone) {
+                const long long off = zdone * P, n = (zfin - zdone) * P;
+                b4d_launch_normalise_det(h->numq.as<long long>() + off, h->denq.as<long long>() + off, d_basic + off,
+                                         d_out + off, n, 1.0f / mm.scale, h->copy_stream);
+                const long long a = std::max(zdone, sink->p0), b = std::min(zfin, sink->p1);
+                if (b > a)
+                    CU_TRY(cudaMemcpyAsync(sink->host + (a - sink->p0) * P, d_out + a * P, (size_t)(b - a) * P * sizeof(float),
+                                           cudaMemcpyDeviceToHost, h->copy_stream));
+                zdone = zfin;
+            }
+        }
+        CU_TRY(cudaStreamSynchronize(h->copy_stream));
+        for (int c = 0; c < NCH; ++c) cudaEventDestroy(evs[c]);
+        clk.mark(B4D_T_NORM2, NCH);
+        sink->done = true;
+        CU_TRY(cudaGetLastError());
+        return 0;
+    }
     if (R2 > 0) b4d_launch_filter(fp, true, s);
     clk.mark(B4D_T_FILTER2, 1);
     normalise(d_basic, d_out);
@@ -520,8 +572,14 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
             d_zf = h->in.as<float>();
         }
         clk.mark(B4D_T_PREP, 2);
-        B4D_TRY(run_pipeline(h, pl, d_zf, d_u, mm, sigma, d_out, clk));
-        if (d_out != out + i0 * V)
+        HostSink sink;
+        if (!out_dev && nb == 1 && h->prof.stages == 2) {
+            sink.host = out + i0 * V;
+            sink.p0 = 0;
+            sink.p1 = pl.D;
+        }
+        B4D_TRY(run_pipeline(h, pl, d_zf, d_u, mm, sigma, d_out, clk, 0, &sink));
+        if (!sink.done && d_out != out + i0 * V)
             CU_TRY(cudaMemcpyAsync(out + i0 * V, d_out, (size_t)TV * sizeof(float),
                                    out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaStreamSynchronize(s));
@@ -567,6 +625,7 @@ int b4d_create(int device, const b4d_profile *profile, b4d_handle **out) {
         delete h;
         return fail(B4D_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(es));
     }
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     reset_timings(h);
     std::memset(h->match_stats, 0, sizeof(h->match_stats));
@@ -582,6 +641,7 @@ void b4d_destroy(b4d_handle *h) {
         b->release();
     for (auto &ev : h->ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
 }
 
@@ -637,10 +697,17 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
     MatchMap mm;
     B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), V, &mm));
     clk.mark(B4D_T_PREP, 1);
-    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk));
-    CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - z_begin) * P,
-                           (size_t)(own_end - own_begin) * P * sizeof(float),
-                           out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    HostSink sink;
+    if (!out_on_device) {
+        sink.host = out;
+        sink.p0 = own_begin - z_begin;
+        sink.p1 = own_end - z_begin;
+    }
+    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk, 0, &sink));
+    if (!sink.done)
+        CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - z_begin) * P,
+                               (size_t)(own_end - own_begin) * P * sizeof(float),
+                               out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -731,10 +798,18 @@ int b4d_slab_stage2(b4d_handle *h, int64_t own_begin, int64_t own_end, float *ou
     mm.ishift = h->slab_ishift;
     StageClock clk(h);
     clk.mark(-1, 0);
-    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, h->slab_sigma, h->out.as<float>(), clk, 2));
-    CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - zb) * P,
-                           (size_t)(own_end - own_begin) * P * sizeof(float),
-                           out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    HostSink sink;
+    if (!out_on_device) {
+        sink.host = out;
+        sink.p0 = own_begin - zb;
+        sink.p1 = own_end - zb;
+    }
+    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, h->slab_sigma, h->out.as<float>(), clk, 2,
+                         &sink));
+    if (!sink.done)
+        CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - zb) * P,
+                               (size_t)(own_end - own_begin) * P * sizeof(float),
+                               out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));

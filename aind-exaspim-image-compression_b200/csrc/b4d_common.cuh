@@ -56,6 +56,7 @@ struct FilterParams {
     int K;
     int Ns;
     int nseg;                    // z segments per column (set by the launcher)
+    int seg0, nseg_launch;       // segments [seg0, seg0 + nseg_launch) belong to this launch
     float qscale;                // power of two: numerator terms are rint(wq * qscale * x), |.| < 2^39
     long long *numq, *denq;      // fixed-point accumulators (order independent): sum of numerator
                                  // terms / sum of the 20-bit weights wq
@@ -64,6 +65,10 @@ struct FilterParams {
 void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s);
 void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s);
 void b4d_launch_filter(const FilterParams &p, bool wiener, cudaStream_t s);
+// the same in pieces: number of z segments (a multiple of `chunks` when the volume is deep enough,
+// else the default), and the launch of segments [seg0, seg0 + count)
+int b4d_filter_segments(const FilterParams &p, int chunks);
+void b4d_launch_filter_segments(const FilterParams &p, bool wiener, int nseg, int seg0, int count, cudaStream_t s);
 void b4d_upload_tables(const B4dTables &t, cudaStream_t s);
 
 // misc kernels (b4d_misc.cu)

@@ -345,3 +345,23 @@ def test_exchange_variant_slabs_equal_whole(b4d_mod):
             parts.append(d.slab_stage2(ob, oe))
             d.close()
         assert np.array_equal(np.concatenate(parts, 0), whole)
+
+
+def test_pipelined_host_writeback_equals_device_result(b4d_mod):
+    """With a host output and a deep volume, stage 2 runs in z chunks and finished planes are
+    normalised and copied out on a second stream while later chunks compute.  The result must equal
+    the device-resident path (one launch, one normalise) bit for bit — volume, slab and two-call form."""
+    import torch
+
+    from b4d import synth
+
+    vol = synth.vol(208, 16, 20, seed=12)  # 69 reference planes: enough for 8 chunks
+    d = b4d_mod.Denoiser(0)
+    dev = d.denoise(torch.from_numpy(vol).cuda(), 24.0).cpu().numpy()  # device in/out: unchunked
+    assert np.array_equal(d.denoise(vol, 24.0), dev)                   # host in/out: chunked
+    part = d.denoise_slab(vol[30:208], 30, 208, 60, 200, 24.0)         # slab, host out
+    ref = d.denoise_slab(torch.from_numpy(vol[30:208]).cuda(), 30, 208, 60, 200, 24.0).cpu().numpy()
+    assert np.array_equal(part, ref)
+    d.slab_stage1(vol, 0, 208, 24.0)                                   # two-call form, host out
+    assert np.array_equal(d.slab_stage2(0, 208), dev)
+    d.close()
