@@ -267,11 +267,26 @@ struct HostSink {
     bool done = false;  // set when run_pipeline delivered the result itself
 };
 
+// Where the input comes from when it is a uint16 volume in HOST memory: it is uploaded in z
+// chunks on the copy stream and the stage-1 front end (float conversion, block energies, tile
+// classification, matching) follows chunk by chunk, so that the host-to-device copy (2 B/voxel
+// over PCIe) hides behind the stage-1 matcher.  d_u / d_zf of run_pipeline are the destinations.
+struct HostSource {
+    const uint16_t *host = nullptr;
+    bool used = false;       // set when run_pipeline did the upload itself
+    int ishift = 0;          // centre shift of the stage-2 matching image (from the data range)
+};
+constexpr int UPLOAD_CHUNKS = 8;
+bool can_stream_upload(const Plan &pl) {
+    return pl.nvol == 1 && ((long long)pl.H * pl.W) % 8 == 0 && pl.D >= 16 * UPLOAD_CHUNKS;
+}
+
 // phase 0 = both stages; 1 = stage 1 only (basic estimate left in h->basic); 2 = stage 2 only
 // (h->basic holds the basic estimate, possibly completed by a neighbour exchange).
-int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u, const MatchMap &mm, float sigma,
-                 float *d_out, StageClock &clk, int phase = 0, HostSink *sink = nullptr) {
+int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u, const MatchMap &mm_in, float sigma,
+                 float *d_out, StageClock &clk, int phase = 0, HostSink *sink = nullptr, HostSource *src = nullptr) {
     const b4d_profile &p = h->prof;
+    MatchMap mm = mm_in;
     const long long V = (long long)pl.D * pl.H * pl.W, TV = V * pl.nvol;
     cudaStream_t s = h->stream;
 
@@ -336,7 +351,8 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     if (phase != 2) {
     // ---- stage 1: hard thresholding
     B4D_TRY(zero_acc());
-    b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
+    const bool streamed = src && src->host && can_stream_upload(pl) && R1 > 0;
+    if (!streamed) b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 2);
     mp.g = g1;
     mp.u = d_u;
@@ -349,7 +365,47 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     mp.cnt = h->cnt.as<uint8_t>();
     mp.ssd_out = nullptr;
     mp.stats = h->stats.as<unsigned long long>();
-    if (R1 > 0) b4d_launch_match(mp, p.search_ht, s);
+    if (streamed) {
+        const long long P = (long long)pl.H * pl.W;
+        const int E = p.search_ht + 12, cd = (pl.D + 3) / 4;
+        B4D_TRY(h->sink.ensure(64));
+        const unsigned init[2] = {0xFFFFu, 0u};
+        CU_TRY(cudaMemcpyAsync(h->sink.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+        cudaEvent_t evs[UPLOAD_CHUNKS];
+        int zprev = 0, odone = 0, cdone = 0, tdone = 0;
+        for (int k = 0; k < UPLOAD_CHUNKS; ++k) {
+            int zu = (k + 1 == UPLOAD_CHUNKS) ? pl.D : (int)(((long long)(k + 1) * pl.D / UPLOAD_CHUNKS + 3) & ~3ll);
+            zu = std::min(zu, pl.D);
+            CU_TRY(cudaMemcpyAsync(d_u + zprev * P, src->host + zprev * P, (size_t)(zu - zprev) * P * sizeof(uint16_t),
+                                   cudaMemcpyHostToDevice, h->copy_stream));
+            CU_TRY(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+            CU_TRY(cudaEventRecord(evs[k], h->copy_stream));
+            CU_TRY(cudaStreamWaitEvent(s, evs[k], 0));
+            // planes [0, zu) are on the device: everything that needs no plane beyond zu - 1
+            b4d_launch_u16_to_f32(d_u + zprev * P, const_cast<float *>(d_zf) + zprev * P, (long long)(zu - zprev) * P,
+                                  h->sink.as<unsigned>(), s);
+            const int o1 = (zu == pl.D) ? pl.D - 3 : zu - 3;            // block origins with all 4 planes present
+            b4d_launch_block_energy_range(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, 1, odone, o1, s);
+            odone = std::max(odone, o1);
+            const int c1 = (zu == pl.D) ? cd : zu / 4;                   // complete 4-plane cells
+            int t1 = tdone;                                              // tile layers whose neighbourhood is complete
+            while (t1 < g1.tz && std::min(pl.rz1[4 * t1] - p.search_ht / 2 + E - 1, pl.D - 1) < zu) ++t1;
+            b4d_launch_match_range(mp, p.search_ht, cdone, c1, (long long)tdone * g1.ty * g1.tx,
+                                   (long long)t1 * g1.ty * g1.tx, s);
+            cdone = c1;
+            tdone = t1;
+            zprev = zu;
+        }
+        unsigned got[2] = {0, 0};
+        CU_TRY(cudaMemcpyAsync(got, h->sink.p, sizeof(got), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        for (int k = 0; k < UPLOAD_CHUNKS; ++k) cudaEventDestroy(evs[k]);
+        mm.ishift = centre_shift((double)got[0], (double)got[1]);
+        src->ishift = mm.ishift;
+        src->used = true;
+    } else if (R1 > 0) {
+        b4d_launch_match(mp, p.search_ht, s);
+    }
     clk.mark(B4D_T_MATCH1, 4);
     fp.g = g1;
     fp.zf = d_zf;
@@ -547,8 +603,13 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
         pl.nvol = (int)nb;
         // input -> device (always into an aligned scratch copy)
         B4D_TRY(h->in.ensure((size_t)TV * sizeof(T)));
-        CU_TRY(cudaMemcpyAsync(h->in.p, in + i0 * V, (size_t)TV * sizeof(T),
-                               in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        HostSource src;
+        // one uint16 volume from host memory: uploaded in chunks behind the stage-1 matcher
+        const bool stream_in = sizeof(T) == 2 && !in_dev && nb == 1 && can_stream_upload(pl);
+        if (stream_in) src.host = reinterpret_cast<const uint16_t *>(in + i0 * V);
+        else
+            CU_TRY(cudaMemcpyAsync(h->in.p, in + i0 * V, (size_t)TV * sizeof(T),
+                                   in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
         B4D_TRY(h->u16.ensure((size_t)TV * sizeof(uint16_t) + 16));
         float *d_out = nullptr;
         if (out_dev && (reinterpret_cast<uintptr_t>(out + i0 * V) & 15) == 0) {
@@ -563,7 +624,7 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
         clk.mark(-1, 0);
         if (sizeof(T) == 2) {
             B4D_TRY(h->zf.ensure((size_t)TV * sizeof(float)));
-            B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), TV, &mm));
+            if (!stream_in) B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), TV, &mm));
             d_zf = h->zf.as<float>();
             d_u = h->in.as<uint16_t>();  // the staged copy doubles as the matching image
         } else {
@@ -578,7 +639,7 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
             sink.p0 = 0;
             sink.p1 = pl.D;
         }
-        B4D_TRY(run_pipeline(h, pl, d_zf, d_u, mm, sigma, d_out, clk, 0, &sink));
+        B4D_TRY(run_pipeline(h, pl, d_zf, d_u, mm, sigma, d_out, clk, 0, &sink, &src));
         if (!sink.done && d_out != out + i0 * V)
             CU_TRY(cudaMemcpyAsync(out + i0 * V, d_out, (size_t)TV * sizeof(float),
                                    out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -691,11 +752,17 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
     B4D_TRY(h->zf.ensure((size_t)V * sizeof(float)));
     B4D_TRY(h->out.ensure((size_t)V * sizeof(float)));
     StageClock clk(h);
-    CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)V * sizeof(uint16_t),
-                           in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-    clk.mark(-1, 0);
     MatchMap mm;
-    B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), V, &mm));
+    HostSource src;
+    if (!in_on_device && can_stream_upload(pl) && !pl.rz1.empty()) {
+        src.host = in;  // uploaded in chunks behind the stage-1 matcher (run_pipeline)
+        clk.mark(-1, 0);
+    } else {
+        CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)V * sizeof(uint16_t),
+                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        clk.mark(-1, 0);
+        B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), V, &mm));
+    }
     clk.mark(B4D_T_PREP, 1);
     HostSink sink;
     if (!out_on_device) {
@@ -703,7 +770,8 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
         sink.p0 = own_begin - z_begin;
         sink.p1 = own_end - z_begin;
     }
-    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk, 0, &sink));
+    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk, 0, &sink,
+                         &src));
     if (!sink.done)
         CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - z_begin) * P,
                                (size_t)(own_end - own_begin) * P * sizeof(float),
@@ -746,18 +814,25 @@ int b4d_slab_stage1_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3
     B4D_TRY(h->zf.ensure((size_t)V * sizeof(float)));
     B4D_TRY(h->out.ensure((size_t)V * sizeof(float)));
     StageClock clk(h);
-    CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)V * sizeof(uint16_t),
-                           in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-    clk.mark(-1, 0);
     MatchMap mm;
-    B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), V, &mm));
+    HostSource src;
+    if (!in_on_device && can_stream_upload(pl) && !pl.rz1.empty()) {
+        src.host = in;  // uploaded in chunks behind the stage-1 matcher (run_pipeline)
+        clk.mark(-1, 0);
+    } else {
+        CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)V * sizeof(uint16_t),
+                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        clk.mark(-1, 0);
+        B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), V, &mm));
+    }
     clk.mark(B4D_T_PREP, 1);
-    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk, 1));
+    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk, 1, nullptr,
+                         &src));
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
     h->slab_cf = mm.cf;
     h->slab_scale = mm.scale;
-    h->slab_ishift = mm.ishift;
+    h->slab_ishift = src.used ? src.ishift : mm.ishift;
     h->slab_open = true;
     return 0;
 }

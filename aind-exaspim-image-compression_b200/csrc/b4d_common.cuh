@@ -44,6 +44,7 @@ struct MatchParams {
     uint16_t *widx;      // [R][K] window index of each match
     uint8_t *cnt;        // [R] group size (power of two)
     uint32_t *ssd_out;   // optional [R][K] exact SSDs (instrumented matcher)
+    long long tile0;     // first tile of this launch (set by the launcher)
     unsigned long long *stats;  // optional: [0] fallback refs, [1] wide tiles
 };
 
@@ -64,6 +65,12 @@ struct FilterParams {
 
 void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s);
 void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s);
+// the same in pieces (one volume arriving over PCIe plane by plane): block energies of origin planes
+// [zo0, zo1); min/max of cell planes [cz0, cz1) and classification + matching of tiles [tile0, tile1)
+void b4d_launch_block_energy_range(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, int zo0, int zo1,
+                                   cudaStream_t s);
+void b4d_launch_match_range(const MatchParams &p, int Ns, int cz0, int cz1, long long tile0, long long tile1,
+                            cudaStream_t s);
 void b4d_launch_filter(const FilterParams &p, bool wiener, cudaStream_t s);
 // the same in pieces: number of z segments (a multiple of `chunks` when the volume is deep enough,
 // else the default), and the launch of segments [seg0, seg0 + count)

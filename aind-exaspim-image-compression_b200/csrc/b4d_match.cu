@@ -122,12 +122,12 @@ struct Geo {
 // y), the sum over 4 planes slides in registers.  HBM-bound: 2 B read + 8 B written per voxel.
 constexpr int K0_TY = 8, K0_TX = 32, K0_ZC = 64;
 __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict__ u, uint2 *__restrict__ s21, int D,
-                                                      int H, int W, int nvol) {
+                                                      int H, int W, int nvol, int zo0, int zo1) {
     __shared__ uint16_t s_in[K0_TY + 3][K0_TX + 4];
     __shared__ unsigned long long s_x2[K0_TY + 3][K0_TX];
     __shared__ uint32_t s_x1[K0_TY + 3][K0_TX];
     const int ntx = (W - 3 + K0_TX - 1) / K0_TX, nty = (H - 3 + K0_TY - 1) / K0_TY;
-    const int nzc = (D - 3 + K0_ZC - 1) / K0_ZC;
+    const int nzc = (zo1 - zo0 + K0_ZC - 1) / K0_ZC;  // origins z in [zo0, zo1) only
     long long t = blockIdx.x;
     const int txi = (int)(t % ntx);
     t /= ntx;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict
     t /= nty;
     const int zci = (int)(t % nzc);
     const int vol = (int)(t / nzc);
-    const int x0 = txi * K0_TX, y0 = tyi * K0_TY, z0 = zci * K0_ZC, z1 = min(z0 + K0_ZC, D - 3);
+    const int x0 = txi * K0_TX, y0 = tyi * K0_TY, z0 = zo0 + zci * K0_ZC, z1 = min(z0 + K0_ZC, zo1);
     const uint16_t *__restrict__ uv = u + (long long)vol * D * H * W;
     uint2 *__restrict__ ov = s21 + (long long)vol * D * H * W;
     const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
@@ -176,18 +176,19 @@ __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict
 // ------------------------------------------------- tile classification ------
 // cells[vol][cz][cy][cx] = min | max << 16 over the in-volume voxels of the aligned 4^3 cell
 __global__ void __launch_bounds__(256) k_cell_minmax(const uint16_t *__restrict__ u, uint32_t *__restrict__ cells,
-                                                     int D, int H, int W, int nvol) {
-    const int cd = (D + 3) >> 2, ch = (H + 3) >> 2, cw = (W + 3) >> 2;
-    const long long total = (long long)nvol * cd * ch * cw;
+                                                     int D, int H, int W, int nvol, int cz0, int cz1) {
+    const int cd = (D + 3) >> 2, ch = (H + 3) >> 2, cw = (W + 3) >> 2, ncz = cz1 - cz0;  // cell planes [cz0, cz1)
+    const long long total = (long long)nvol * ncz * ch * cw;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        long long r = i;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+        long long r = j;
         const int cx = (int)(r % cw);
         r /= cw;
         const int cy = (int)(r % ch);
         r /= ch;
-        const int cz = (int)(r % cd);
-        const int vol = (int)(r / cd);
+        const int cz = cz0 + (int)(r % ncz);
+        const int vol = (int)(r / ncz);
+        const long long i = (((long long)vol * cd + cz) * ch + cy) * cw + cx;
         const uint16_t *v = u + (long long)vol * D * H * W;
         uint32_t mn = 0xFFFFu, mx = 0u;
         for (int z = cz * 4; z < min(cz * 4 + 4, D); ++z)
@@ -207,12 +208,11 @@ __global__ void __launch_bounds__(256) k_cell_minmax(const uint16_t *__restrict_
 // bits 0-15 hold the minimum), bit 17 = "narrow", range <= 8191 (every SSD < 2^32).
 template <int NS>
 __global__ void __launch_bounds__(256) k_tile_class(const uint32_t *__restrict__ cells, const B4dGeom g,
-                                                    uint32_t *__restrict__ tcls) {
+                                                    uint32_t *__restrict__ tcls, long long tile0, long long tile1) {
     using G = Geo<NS>;
     const int lane = threadIdx.x & 31;
-    const long long tiles = (long long)g.nvol * g.tz * g.ty * g.tx;
-    const long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tile >= tiles) return;
+    const long long tile = tile0 + (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= tile1) return;
     long long t = tile;
     const int tx = (int)(t % g.tx);
     t /= g.tx;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     constexpr int R_ = G::R, E = G::E, EC = G::EC, KB = G::KB, UNITS = G::UNITS, ITERS = G::ITERS;
 
     // tile class: byte tiles belong to the BYTE instantiation, all others to the general one
-    const uint32_t cls = p.tcls[blockIdx.x];
+    const uint32_t cls = p.tcls[p.tile0 + blockIdx.x];
     if (BYTE != (((cls >> 16) & 1u) != 0u)) return;
     const uint32_t tmin = cls & 0xFFFFu;
     const bool narrow = BYTE || ((cls >> 17) & 1u) != 0u;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const B4dGeom &g = p.g;
 
-    long long t = blockIdx.x;
+    long long t = p.tile0 + blockIdx.x;
     const int tx = (int)(t % g.tx);
     t /= g.tx;
     const int ty = (int)(t % g.ty);
@@ -759,45 +759,60 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
 }
 
 template <int NS, bool K32>
-void launch_k(const MatchParams &p, long long tiles, cudaStream_t s) {
+void launch_k(const MatchParams &pin, long long tile0, long long tile1, cudaStream_t s) {
     using G = Geo<NS>;
+    MatchParams p = pin;
+    p.tile0 = tile0;
+    const unsigned tiles = (unsigned)(tile1 - tile0);
     // byte tiles first (cheap), then everything else; each kernel exits at once on a foreign tile
     cudaFuncSetAttribute(k_match<NS, K32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_B);
-    k_match<NS, K32, true><<<(unsigned)tiles, WARPS * 32, G::SMEM_B, s>>>(p);
+    k_match<NS, K32, true><<<tiles, WARPS * 32, G::SMEM_B, s>>>(p);
     cudaFuncSetAttribute(k_match<NS, K32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-    k_match<NS, K32, false><<<(unsigned)tiles, WARPS * 32, G::SMEM, s>>>(p);
+    k_match<NS, K32, false><<<tiles, WARPS * 32, G::SMEM, s>>>(p);
 }
+// cell planes [cz0, cz1) (min/max table) and tiles [tile0, tile1) (classification + both matcher
+// kernels); the whole volume in one go is cz = [0, cd), tiles = [0, all)
 template <int NS>
-void launch_ns(const MatchParams &p, cudaStream_t s) {
-    const long long tiles = (long long)p.g.nvol * p.g.tz * p.g.ty * p.g.tx;
-    {
-        const long long cells = (long long)p.g.nvol * ((p.g.D + 3) / 4) * ((p.g.H + 3) / 4) * ((p.g.W + 3) / 4);
+void launch_ns(const MatchParams &p, int cz0, int cz1, long long tile0, long long tile1, cudaStream_t s) {
+    if (cz1 > cz0) {
+        const long long cells = (long long)p.g.nvol * (cz1 - cz0) * ((p.g.H + 3) / 4) * ((p.g.W + 3) / 4);
         long long blocks = std::min<long long>((cells + 255) / 256, 148ll * 32);
         k_cell_minmax<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, s>>>(p.u, p.cells, p.g.D, p.g.H, p.g.W,
-                                                                               p.g.nvol);
-        k_tile_class<NS><<<(unsigned)((tiles + 7) / 8), 256, 0, s>>>(p.cells, p.g, p.tcls);
+                                                                               p.g.nvol, cz0, cz1);
     }
-    if (p.K > 16) launch_k<NS, true>(p, tiles, s);
-    else launch_k<NS, false>(p, tiles, s);
+    if (tile1 > tile0) {
+        k_tile_class<NS><<<(unsigned)((tile1 - tile0 + 7) / 8), 256, 0, s>>>(p.cells, p.g, p.tcls, tile0, tile1);
+        if (p.K > 16) launch_k<NS, true>(p, tile0, tile1, s);
+        else launch_k<NS, false>(p, tile0, tile1, s);
+    }
 }
 
 }  // namespace
 
-void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s) {
+void b4d_launch_block_energy_range(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, int zo0, int zo1,
+                                   cudaStream_t s) {
+    if (zo1 <= zo0) return;
     const long long blocks = (long long)((W - 3 + K0_TX - 1) / K0_TX) * ((H - 3 + K0_TY - 1) / K0_TY) *
-                             ((D - 3 + K0_ZC - 1) / K0_ZC) * nvol;
-    k_block_energy<<<(unsigned)blocks, 256, 0, s>>>(u, s21, D, H, W, nvol);
+                             ((zo1 - zo0 + K0_ZC - 1) / K0_ZC) * nvol;
+    k_block_energy<<<(unsigned)blocks, 256, 0, s>>>(u, s21, D, H, W, nvol, zo0, zo1);
+}
+void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s) {
+    b4d_launch_block_energy_range(u, s21, D, H, W, nvol, 0, D - 3, s);
 }
 
-void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s) {
+void b4d_launch_match_range(const MatchParams &p, int Ns, int cz0, int cz1, long long tile0, long long tile1,
+                            cudaStream_t s) {
     switch (Ns) {
-        case 3: launch_ns<3>(p, s); break;
-        case 5: launch_ns<5>(p, s); break;
-        case 7: launch_ns<7>(p, s); break;
-        case 9: launch_ns<9>(p, s); break;
-        case 11: launch_ns<11>(p, s); break;
-        case 13: launch_ns<13>(p, s); break;
-        case 15: launch_ns<15>(p, s); break;
+        case 3: launch_ns<3>(p, cz0, cz1, tile0, tile1, s); break;
+        case 5: launch_ns<5>(p, cz0, cz1, tile0, tile1, s); break;
+        case 7: launch_ns<7>(p, cz0, cz1, tile0, tile1, s); break;
+        case 9: launch_ns<9>(p, cz0, cz1, tile0, tile1, s); break;
+        case 11: launch_ns<11>(p, cz0, cz1, tile0, tile1, s); break;
+        case 13: launch_ns<13>(p, cz0, cz1, tile0, tile1, s); break;
+        case 15: launch_ns<15>(p, cz0, cz1, tile0, tile1, s); break;
         default: break;
     }
+}
+void b4d_launch_match(const MatchParams &p, int Ns, cudaStream_t s) {
+    b4d_launch_match_range(p, Ns, 0, (p.g.D + 3) / 4, 0, (long long)p.g.nvol * p.g.tz * p.g.ty * p.g.tx, s);
 }

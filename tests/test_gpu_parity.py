@@ -347,10 +347,11 @@ def test_exchange_variant_slabs_equal_whole(b4d_mod):
         assert np.array_equal(np.concatenate(parts, 0), whole)
 
 
-def test_pipelined_host_writeback_equals_device_result(b4d_mod):
-    """With a host output and a deep volume, stage 2 runs in z chunks and finished planes are
-    normalised and copied out on a second stream while later chunks compute.  The result must equal
-    the device-resident path (one launch, one normalise) bit for bit — volume, slab and two-call form."""
+def test_pipelined_host_transfers_equal_device_result(b4d_mod):
+    """With host buffers and a deep volume the transfers are pipelined: the uint16 input is uploaded
+    in z chunks behind the stage-1 matcher, and stage 2 runs in z chunks whose finished planes are
+    normalised and copied out on a second stream.  The result must equal the device-resident path
+    (one upload, one launch per kernel) bit for bit — volume, slab and two-call form."""
     import torch
 
     from b4d import synth
