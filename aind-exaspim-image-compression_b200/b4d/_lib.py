@@ -23,6 +23,7 @@ EXPORTS = (
     "b4d_set_profile",
     "b4d_denoise_u16",
     "b4d_denoise_f32",
+    "b4d_targets_u16",
     "b4d_denoise_slab_u16",
     "b4d_slab_stage1_u16",
     "b4d_slab_basic_planes",

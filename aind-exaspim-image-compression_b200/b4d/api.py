@@ -186,6 +186,38 @@ class Denoiser:
         self.denoise_ptr(zc.ctypes.data, zc.dtype.type, n, zc.shape[-3:], sigma, out.ctypes.data, 0, 0)
         return out
 
+    def targets(self, raw_u16, offsets, sigma, max_count=65535.0, raw_out=None, teacher_out=None):
+        """(N,D,H,W) uint16 patches + per-patch offsets -> (raw, teacher) float32 in one call
+        (b4d_targets_u16: subtraction, BM4D and clip all on the device).  `raw_out` / `teacher_out`
+        may be preallocated C-contiguous float32 arrays (e.g. the cache's memmaps)."""
+        zc = np.ascontiguousarray(raw_u16)
+        if zc.ndim != 4 or zc.dtype != np.uint16:
+            raise ValueError("raw_u16 must be (N, D, H, W) uint16")
+        off = np.ascontiguousarray(np.broadcast_to(np.asarray(offsets, dtype=np.float32), (zc.shape[0],)))
+        outs = []
+        for o in (raw_out, teacher_out):
+            if o is None:
+                o = np.empty(zc.shape, dtype=np.float32)
+            elif o.shape != zc.shape or o.dtype != np.float32 or not o.flags.c_contiguous:
+                raise ValueError("output must be a C-contiguous float32 array of shape %r" % (zc.shape,))
+            outs.append(o)
+        _lib.check(
+            self.lib.b4d_targets_u16(
+                self._h,
+                ctypes.c_void_p(zc.ctypes.data),
+                ctypes.c_int64(zc.shape[0]),
+                _lib.shape3(zc.shape[1:]),
+                ctypes.c_void_p(off.ctypes.data),
+                ctypes.c_float(sigma),
+                ctypes.c_float(max_count),
+                ctypes.c_void_p(outs[0].ctypes.data),
+                ctypes.c_void_p(outs[1].ctypes.data),
+                0,
+                0,
+            )
+        )
+        return outs[0], outs[1]
+
     def denoise_slab(self, slab, z_begin, z_total, own_begin, own_end, sigma, out=None):
         """One z-slab (uint16, with halos) of a larger volume -> float32 owned planes.
         `out` (NumPy path only) receives the result in place, e.g. a pinned buffer."""
@@ -515,18 +547,9 @@ def precompute_targets(raw_u16, offsets, sigma, max_count=65535.0, device=None):
     raw_u16 = np.asarray(raw_u16)
     if raw_u16.ndim != 4 or raw_u16.dtype != np.uint16:
         raise ValueError("raw_u16 must be (N, D, H, W) uint16")
-    off = np.broadcast_to(np.asarray(offsets, dtype=np.float32), (raw_u16.shape[0],))
-    raw = raw_u16.astype(np.float32) - off[:, None, None, None]
     h = get_denoiser(device)
-    groups = {}
-    for i, o in enumerate(off.tolist()):
-        groups.setdefault(o, []).append(i)
-    teacher = np.empty(raw.shape, dtype=np.float32)
-    for _o, idxs in groups.items():  # one launch per distinct offset: the matching map is per call
-        sel = np.asarray(idxs)
-        teacher[sel] = bm4d_batch(raw[sel], sigma, device=h.device)
-    np.clip(teacher, 0, max_count, out=teacher)
-    return raw, teacher
+    h.set_profile("np", 2)
+    return h.targets(raw_u16, offsets, _sigma_scalar(sigma), max_count)
 
 
 def quantize(x, offset_sub=0.0, offset_add=0.0, step=1.0, device=None):

@@ -728,6 +728,70 @@ int b4d_denoise_f32(b4d_handle *h, const float *in, int64_t n, const int64_t sha
     return denoise_batch<float>(h, in, n, shape, sigma, out, in_on_device, out_on_device);
 }
 
+int b4d_targets_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t shape[3], const float *offsets,
+                    float sigma, float max_count, float *raw_out, float *teacher_out, int in_on_device,
+                    int out_on_device) {
+    B4D_TRY(common_checks(h, in, teacher_out, shape, sigma));
+    if (n < 1 || !offsets) return fail(B4D_ERR_INVALID, "n must be >= 1 and offsets non-NULL");
+    if (h->prof.stages != 2) return fail(B4D_ERR_INVALID, "target generation needs stages = 2");
+    reset_timings(h);
+    const long long V = shape[0] * shape[1] * shape[2];
+    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, CHUNK_VOXELS / V));
+    cudaStream_t s = h->stream;
+    Plan pl;
+    pl.D = (int)shape[0];
+    pl.H = (int)shape[1];
+    pl.W = (int)shape[2];
+    pl.rz1 = pl.rz2 = ref_origins(shape[0]);
+    pl.ry = ref_origins(shape[1]);
+    pl.rx = ref_origins(shape[2]);
+    StageClock clk(h);
+    for (int64_t i0 = 0; i0 < n; i0 += per) {
+        const int64_t nb = std::min<int64_t>(per, n - i0);
+        const long long TV = V * nb;
+        pl.nvol = (int)nb;
+        B4D_TRY(h->in.ensure((size_t)TV * sizeof(uint16_t)));
+        B4D_TRY(h->zf.ensure((size_t)TV * sizeof(float)));
+        B4D_TRY(h->out.ensure((size_t)TV * sizeof(float)));
+        B4D_TRY(h->partial.ensure((size_t)nb * sizeof(float)));
+        B4D_TRY(h->sink.ensure(64));
+        CU_TRY(cudaMemcpyAsync(h->in.p, in + i0 * V, (size_t)TV * sizeof(uint16_t),
+                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(h->partial.p, offsets + i0, (size_t)nb * sizeof(float), cudaMemcpyHostToDevice, s));
+        const unsigned init[2] = {0xFFFFu, 0u};
+        CU_TRY(cudaMemcpyAsync(h->sink.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+        clk.mark(-1, 0);
+        b4d_launch_u16_sub_offset(h->in.as<uint16_t>(), h->partial.as<float>(), h->zf.as<float>(), V, TV,
+                                  h->sink.as<unsigned>(), s);
+        unsigned got[2] = {0, 0};
+        CU_TRY(cudaMemcpyAsync(got, h->sink.p, sizeof(got), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        float omin = offsets[i0], omax = offsets[i0];
+        for (int64_t k = 0; k < nb; ++k) {
+            omin = std::min(omin, offsets[i0 + k]);
+            omax = std::max(omax, offsets[i0 + k]);
+        }
+        if (!std::isfinite(omin) || !std::isfinite(omax)) return fail(B4D_ERR_INVALID, "offsets must be finite");
+        // Matching is invariant to a constant shift per volume: stage 1 matches on the counts themselves,
+        // the stage-2 matching image rint(basic) + ishift only has to stay inside uint16.
+        MatchMap mm;
+        mm.integral = 1;
+        mm.scale = 1.0f;
+        mm.cf = 0.0f;
+        mm.ishift = centre_shift((double)got[0] - std::ceil((double)omax), (double)got[1] - std::floor((double)omin));
+        clk.mark(B4D_T_PREP, 1);
+        B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk));
+        b4d_launch_clip(h->out.as<float>(), TV, max_count, s);
+        const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (raw_out) CU_TRY(cudaMemcpyAsync(raw_out + i0 * V, h->zf.p, (size_t)TV * sizeof(float), kind, s));
+        CU_TRY(cudaMemcpyAsync(teacher_out + i0 * V, h->out.p, (size_t)TV * sizeof(float), kind, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        clk.resolve();
+    }
+    CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
                          int64_t z_total, int64_t own_begin, int64_t own_end, float sigma, float *out,
                          int in_on_device, int out_on_device) {

@@ -82,6 +82,9 @@ void b4d_upload_tables(const B4dTables &t, cudaStream_t s);
 void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, unsigned *minmax, cudaStream_t s);
 void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, float scale, int ishift,
                          cudaStream_t s);
+void b4d_launch_u16_sub_offset(const uint16_t *in, const float *off, float *out, long long vol_stride, long long n,
+                               unsigned *minmax, cudaStream_t s);
+void b4d_launch_clip(float *x, long long n, float hi, cudaStream_t s);
 void b4d_launch_normalise_det(const long long *numq, const long long *denq, const float *fallback, float *out,
                               long long n, float inv_qscale, cudaStream_t s);
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,

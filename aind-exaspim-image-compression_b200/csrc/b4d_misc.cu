@@ -94,6 +94,33 @@ __global__ void __launch_bounds__(256) k_to_match(const float *__restrict__ in, 
         out[i] = (uint16_t)to_match(in[i], shift, scale, ishift);
 }
 
+// ------------------------------------------------------ precompute targets --
+// raw = float(u16) - offset[vol] in float32 (data_handling.py:353-354), plus min / max of the counts.
+__global__ void __launch_bounds__(256) k_u16_sub_offset(const uint16_t *__restrict__ in, const float *__restrict__ off,
+                                                        float *__restrict__ out, long long vol_stride, long long n,
+                                                        unsigned *__restrict__ minmax) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned mn = 0xFFFFu, mx = 0u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned e = in[i];
+        mn = min(mn, e);
+        mx = max(mx, e);
+        out[i] = __fsub_rn((float)e, __ldg(off + i / vol_stride));
+    }
+    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&minmax[0], mn);
+        atomicMax(&minmax[1], mx);
+    }
+}
+// teacher = clip(x, 0, max_count) in place (data_handling.py:333)
+__global__ void __launch_bounds__(256) k_clip(float *__restrict__ x, long long n, float hi) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        x[i] = fminf(fmaxf(x[i], 0.0f), hi);
+}
+
 // ------------------------------------------------------------- normalise ----
 // K3 / K6: out = num / den / qscale (den > 0), else the fallback value.  Accumulators are
 // fixed point (int64): 16 B read + 4 B fallback + 4 B write per voxel.
@@ -274,6 +301,13 @@ __global__ void __launch_bounds__(1024) k_pipe(int iters, unsigned *sink) {
 
 void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, unsigned *minmax, cudaStream_t s) {
     k_u16_to_f32<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, minmax);
+}
+void b4d_launch_u16_sub_offset(const uint16_t *in, const float *off, float *out, long long vol_stride, long long n,
+                               unsigned *minmax, cudaStream_t s) {
+    k_u16_sub_offset<<<grid_for(n, 256, 8), 256, 0, s>>>(in, off, out, vol_stride, n, minmax);
+}
+void b4d_launch_clip(float *x, long long n, float hi, cudaStream_t s) {
+    k_clip<<<grid_for(n, 256, 8), 256, 0, s>>>(x, n, hi);
 }
 void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, float scale, int ishift,
                          cudaStream_t s) {

@@ -108,6 +108,17 @@ int b4d_denoise_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t 
 int b4d_denoise_f32(b4d_handle *h, const float *in, int64_t n, const int64_t shape[3],
                     float sigma, float *out, int in_on_device, int out_on_device);
 
+/* Training targets for `n` equal-shape uint16 patches in one call — the core of
+ * `_sample_counts` (data_handling.py:315-354) batched:
+ *     raw     = float32(in) - offsets[i]                 data_handling.py:353-354
+ *     teacher = clip(bm4d(raw, sigma), 0, max_count)     data_handling.py:332-333
+ * `offsets` is a HOST array of n per-patch background offsets.  `raw_out` may be NULL.
+ * Equal, bit for bit, to b4d_denoise_f32 on each raw patch followed by the clip: the counts
+ * go over PCIe as uint16 (2 B/voxel), the subtraction and the clip run on the device. */
+int b4d_targets_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t shape[3],
+                    const float *offsets, float sigma, float max_count, float *raw_out,
+                    float *teacher_out, int in_on_device, int out_on_device);
+
 /* One z-slab of a larger volume.  `in` holds global planes
  * [z_begin, z_begin + shape[0]) of a volume with `z_total` planes; reference
  * blocks sit on the GLOBAL grid and only those whose search window lies inside

@@ -895,6 +895,22 @@ int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *,
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }
 void *b4d_stream(b4d_handle *) { return nullptr; }
+int b4d_targets_u16(b4d_handle *hh, const uint16_t *in, int64_t n, const int64_t shape[3], const float *offsets,
+                    float sigma, float max_count, float *raw_out, float *teacher_out, int, int) {
+    // restatement of data_handling.py:353-354, :332-333 over the oracle's own float32 entry point
+    if (!in || !offsets || !teacher_out || n < 1) return fail(B4D_ERR_INVALID, "NULL argument");
+    const int64_t V = shape[0] * shape[1] * shape[2];
+    std::vector<float> raw((size_t)V);
+    for (int64_t i = 0; i < n; ++i) {
+        for (int64_t v = 0; v < V; ++v) raw[v] = (float)in[i * V + v] - offsets[i];
+        if (raw_out) std::memcpy(raw_out + i * V, raw.data(), (size_t)V * sizeof(float));
+        int rc = b4d_denoise_f32(hh, raw.data(), 1, shape, sigma, teacher_out + i * V, 0, 0);
+        if (rc) return rc;
+        for (int64_t v = 0; v < V; ++v)
+            teacher_out[i * V + v] = std::min(std::max(teacher_out[i * V + v], 0.0f), max_count);
+    }
+    return 0;
+}
 // the two-call slab form exists for multi-GPU exchange only; the oracle has the one-call form
 int b4d_slab_stage1_u16(b4d_handle *, const uint16_t *, const int64_t *, int64_t, int64_t, float, int) {
     return fail(B4D_ERR_UNSUPPORTED, "oracle: use b4d_denoise_slab_u16");

@@ -151,11 +151,20 @@ def test_batch_equals_per_patch_and_precompute_targets(b4d_mod, oracle_lib):
         assert np.array_equal(yb[i], d.denoise(batch[i], 24.0))
         assert np.array_equal(yb[i], oracle_lib.Oracle("mirror").denoise(batch[i], 24.0))
     d.close()
-    raw, teacher = b4d_mod.precompute_targets(batch, [37.0, 37.0, 12.5], 24.0)
+    # one launch for the whole batch, per-patch offsets (b4d_targets_u16): equal, bit for bit, to the float32
+    # entry point on each offset-subtracted patch followed by the clip (data_handling.py:332-333, :353-354)
+    offs = [37.0, 36.37, 12.5]
+    raw, teacher = b4d_mod.precompute_targets(batch, offs, 24.0)
     assert raw.dtype == np.float32 and teacher.dtype == np.float32  # scripts/precompute.py:204-213
     assert teacher.min() >= 0.0 and teacher.max() <= 65535.0
-    want = np.clip(oracle_lib.Oracle("mirror").denoise(oracle_lib.read_counts(batch[2], 12.5), 24.0), 0, 65535)
-    assert np.abs(teacher[2] - want).max() <= MAX_ABS
+    o = oracle_lib.Oracle("mirror")
+    for i in range(3):
+        ri = oracle_lib.read_counts(batch[i], np.float32(offs[i]))
+        assert np.array_equal(raw[i], ri)
+        assert np.array_equal(teacher[i], np.clip(o.denoise(ri, 24.0), 0, 65535))
+        assert np.array_equal(teacher[i], np.clip(b4d_mod.bm4d(ri, 24.0), 0, 65535))
+    _, low = b4d_mod.precompute_targets(batch[:1], 37.0, 24.0, max_count=150.0)
+    assert low.max() <= 150.0 and np.array_equal(low[0], np.minimum(teacher[0], 150.0))
 
 
 def test_slabs_equal_whole_on_device(b4d_mod):

@@ -17,9 +17,10 @@ for i in range(N):
     patches[i] = np.clip(np.rint(clean + rng.normal(0, 24.0, clean.shape)), 0, 65535).astype(np.uint16)
 print("generated %d patches in %.1fs" % (N, time.time() - t0), flush=True)
 d = b4d.get_denoiser(0)
-b4d.precompute_targets(patches[:4], 37.0, 24.0)  # warm-up
+offs = np.round(rng.uniform(30.0, 45.0, N), 2).astype(np.float32)  # per-patch background offsets
+b4d.precompute_targets(patches[:4], offs[:4], 24.0)  # warm-up
 t = time.time()
-raw, teacher = b4d.precompute_targets(patches, 37.0, 24.0)
+raw, teacher = b4d.precompute_targets(patches, offs, 24.0)
 dt = time.time() - t
 print(json.dumps({"config": "512 x 128^3 uint16 patches -> targets (BASELINE configs[1])", "n": N, "seconds": dt,
                   "voxels_per_s_host_to_host": patches.size / dt, "device_ms": d.last_timings(),
