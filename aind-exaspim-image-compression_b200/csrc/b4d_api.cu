@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "b4d_common.cuh"
+#include "b4d_host.cuh"
 
 namespace {
 
@@ -74,6 +75,7 @@ struct b4d_handle {
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
     unsigned long long match_stats[4];
+    HostMover mover;  // pageable host arrays <-> device (pinned ring + copy threads)
     // state between b4d_slab_stage1_u16 and b4d_slab_stage2
     bool slab_open = false;
     int64_t slab_shape[3] = {0, 0, 0};
@@ -84,6 +86,16 @@ struct b4d_handle {
 };
 
 namespace {
+
+// user buffer -> device / device -> user buffer on stream `cs`; host buffers go through the HostMover
+cudaError_t copy_in(b4d_handle *h, void *dev, const void *user, size_t bytes, int user_on_device, cudaStream_t cs) {
+    if (user_on_device) return cudaMemcpyAsync(dev, user, bytes, cudaMemcpyDeviceToDevice, cs);
+    return h->mover.h2d(dev, user, bytes, cs);
+}
+cudaError_t copy_out(b4d_handle *h, void *user, const void *dev, size_t bytes, int user_on_device, cudaStream_t cs) {
+    if (user_on_device) return cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToDevice, cs);
+    return h->mover.d2h(user, dev, bytes, cs);
+}
 
 void default_profile(b4d_profile *p) {
     std::memset(p, 0, sizeof(*p));
@@ -376,8 +388,8 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         for (int k = 0; k < UPLOAD_CHUNKS; ++k) {
             int zu = (k + 1 == UPLOAD_CHUNKS) ? pl.D : (int)(((long long)(k + 1) * pl.D / UPLOAD_CHUNKS + 3) & ~3ll);
             zu = std::min(zu, pl.D);
-            CU_TRY(cudaMemcpyAsync(d_u + zprev * P, src->host + zprev * P, (size_t)(zu - zprev) * P * sizeof(uint16_t),
-                                   cudaMemcpyHostToDevice, h->copy_stream));
+            CU_TRY(copy_in(h, d_u + zprev * P, src->host + zprev * P, (size_t)(zu - zprev) * P * sizeof(uint16_t), 0,
+                           h->copy_stream));
             CU_TRY(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
             CU_TRY(cudaEventRecord(evs[k], h->copy_stream));
             CU_TRY(cudaStreamWaitEvent(s, evs[k], 0));
@@ -486,8 +498,8 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
                                          d_out + off, n, 1.0f / mm.scale, h->copy_stream);
                 const long long a = std::max(zdone, sink->p0), b = std::min(zfin, sink->p1);
                 if (b > a)
-                    CU_TRY(cudaMemcpyAsync(sink->host + (a - sink->p0) * P, d_out + a * P, (size_t)(b - a) * P * sizeof(float),
-                                           cudaMemcpyDeviceToHost, h->copy_stream));
+                    CU_TRY(copy_out(h, sink->host + (a - sink->p0) * P, d_out + a * P, (size_t)(b - a) * P * sizeof(float),
+                                    0, h->copy_stream));
                 zdone = zfin;
             }
         }
@@ -608,8 +620,7 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
         const bool stream_in = sizeof(T) == 2 && !in_dev && nb == 1 && can_stream_upload(pl);
         if (stream_in) src.host = reinterpret_cast<const uint16_t *>(in + i0 * V);
         else
-            CU_TRY(cudaMemcpyAsync(h->in.p, in + i0 * V, (size_t)TV * sizeof(T),
-                                   in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+            CU_TRY(copy_in(h, h->in.p, in + i0 * V, (size_t)TV * sizeof(T), in_dev, s));
         B4D_TRY(h->u16.ensure((size_t)TV * sizeof(uint16_t) + 16));
         float *d_out = nullptr;
         if (out_dev && (reinterpret_cast<uintptr_t>(out + i0 * V) & 15) == 0) {
@@ -641,8 +652,7 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
         }
         B4D_TRY(run_pipeline(h, pl, d_zf, d_u, mm, sigma, d_out, clk, 0, &sink, &src));
         if (!sink.done && d_out != out + i0 * V)
-            CU_TRY(cudaMemcpyAsync(out + i0 * V, d_out, (size_t)TV * sizeof(float),
-                                   out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+            CU_TRY(copy_out(h, out + i0 * V, d_out, (size_t)TV * sizeof(float), out_dev, s));
         CU_TRY(cudaStreamSynchronize(s));
         clk.resolve();
     }
@@ -755,8 +765,7 @@ int b4d_targets_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t 
         B4D_TRY(h->out.ensure((size_t)TV * sizeof(float)));
         B4D_TRY(h->partial.ensure((size_t)nb * sizeof(float)));
         B4D_TRY(h->sink.ensure(64));
-        CU_TRY(cudaMemcpyAsync(h->in.p, in + i0 * V, (size_t)TV * sizeof(uint16_t),
-                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        CU_TRY(copy_in(h, h->in.p, in + i0 * V, (size_t)TV * sizeof(uint16_t), in_on_device, s));
         CU_TRY(cudaMemcpyAsync(h->partial.p, offsets + i0, (size_t)nb * sizeof(float), cudaMemcpyHostToDevice, s));
         const unsigned init[2] = {0xFFFFu, 0u};
         CU_TRY(cudaMemcpyAsync(h->sink.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
@@ -780,12 +789,19 @@ int b4d_targets_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t 
         mm.cf = 0.0f;
         mm.ishift = centre_shift((double)got[0] - std::ceil((double)omax), (double)got[1] - std::floor((double)omin));
         clk.mark(B4D_T_PREP, 1);
+        cudaEvent_t ev_raw;
+        CU_TRY(cudaEventCreateWithFlags(&ev_raw, cudaEventDisableTiming));
+        CU_TRY(cudaEventRecord(ev_raw, s));
         B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk));
         b4d_launch_clip(h->out.as<float>(), TV, max_count, s);
-        const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-        if (raw_out) CU_TRY(cudaMemcpyAsync(raw_out + i0 * V, h->zf.p, (size_t)TV * sizeof(float), kind, s));
-        CU_TRY(cudaMemcpyAsync(teacher_out + i0 * V, h->out.p, (size_t)TV * sizeof(float), kind, s));
+        // the whole chunk is queued: raw goes back on the copy stream while the matcher and the filters run
+        CU_TRY(cudaStreamWaitEvent(h->copy_stream, ev_raw, 0));
+        if (raw_out)
+            CU_TRY(copy_out(h, raw_out + i0 * V, h->zf.p, (size_t)TV * sizeof(float), out_on_device, h->copy_stream));
+        CU_TRY(copy_out(h, teacher_out + i0 * V, h->out.p, (size_t)TV * sizeof(float), out_on_device, s));
+        CU_TRY(cudaStreamSynchronize(h->copy_stream));
         CU_TRY(cudaStreamSynchronize(s));
+        cudaEventDestroy(ev_raw);
         clk.resolve();
     }
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -822,8 +838,7 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
         src.host = in;  // uploaded in chunks behind the stage-1 matcher (run_pipeline)
         clk.mark(-1, 0);
     } else {
-        CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)V * sizeof(uint16_t),
-                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        CU_TRY(copy_in(h, h->in.p, in, (size_t)V * sizeof(uint16_t), in_on_device, s));
         clk.mark(-1, 0);
         B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), V, &mm));
     }
@@ -837,9 +852,8 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
     B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk, 0, &sink,
                          &src));
     if (!sink.done)
-        CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - z_begin) * P,
-                               (size_t)(own_end - own_begin) * P * sizeof(float),
-                               out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        CU_TRY(copy_out(h, out, h->out.as<float>() + (own_begin - z_begin) * P,
+                        (size_t)(own_end - own_begin) * P * sizeof(float), out_on_device, s));
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -884,8 +898,7 @@ int b4d_slab_stage1_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3
         src.host = in;  // uploaded in chunks behind the stage-1 matcher (run_pipeline)
         clk.mark(-1, 0);
     } else {
-        CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)V * sizeof(uint16_t),
-                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        CU_TRY(copy_in(h, h->in.p, in, (size_t)V * sizeof(uint16_t), in_on_device, s));
         clk.mark(-1, 0);
         B4D_TRY(convert_u16(h, h->in.as<uint16_t>(), h->zf.as<float>(), V, &mm));
     }
@@ -912,11 +925,9 @@ int b4d_slab_basic_planes(b4d_handle *h, int64_t plane0, int64_t nplanes, float 
     float *dev = h->basic.as<float>() + (size_t)plane0 * P;
     const size_t bytes = (size_t)nplanes * P * sizeof(float);
     if (to_handle)
-        CU_TRY(cudaMemcpyAsync(dev, buf, bytes, buf_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                               h->stream));
+        CU_TRY(copy_in(h, dev, buf, bytes, buf_on_device, h->stream));
     else
-        CU_TRY(cudaMemcpyAsync(buf, dev, bytes, buf_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                               h->stream));
+        CU_TRY(copy_out(h, buf, dev, bytes, buf_on_device, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -946,9 +957,8 @@ int b4d_slab_stage2(b4d_handle *h, int64_t own_begin, int64_t own_end, float *ou
     B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, h->slab_sigma, h->out.as<float>(), clk, 2,
                          &sink));
     if (!sink.done)
-        CU_TRY(cudaMemcpyAsync(out, h->out.as<float>() + (own_begin - zb) * P,
-                               (size_t)(own_end - own_begin) * P * sizeof(float),
-                               out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        CU_TRY(copy_out(h, out, h->out.as<float>() + (own_begin - zb) * P,
+                        (size_t)(own_end - own_begin) * P * sizeof(float), out_on_device, s));
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -1051,8 +1061,7 @@ int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub
     uint16_t *d_out = out;
     if (!in_on_device || (reinterpret_cast<uintptr_t>(in) & 15)) {
         B4D_TRY(h->in.ensure((size_t)n * sizeof(float)));
-        CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)n * sizeof(float),
-                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        CU_TRY(copy_in(h, h->in.p, in, (size_t)n * sizeof(float), in_on_device, s));
         d_in = h->in.as<float>();
     }
     if (!out_on_device || (reinterpret_cast<uintptr_t>(out) & 15)) {
@@ -1062,8 +1071,7 @@ int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub
     b4d_launch_quantize(d_in, d_out, n, offset_sub, offset_add, step, s);
     CU_TRY(cudaGetLastError());
     if (d_out != out)
-        CU_TRY(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(uint16_t),
-                               out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        CU_TRY(copy_out(h, out, d_out, (size_t)n * sizeof(uint16_t), out_on_device, s));
     CU_TRY(cudaStreamSynchronize(s));
     return 0;
 }
@@ -1113,8 +1121,7 @@ int b4d_tile_stats(b4d_handle *h, const uint16_t *in, int64_t n, double pct, b4d
     const uint16_t *d_in = in;
     if (!in_on_device || (reinterpret_cast<uintptr_t>(in) & 15)) {
         B4D_TRY(h->in.ensure((size_t)n * sizeof(uint16_t)));
-        CU_TRY(cudaMemcpyAsync(h->in.p, in, (size_t)n * sizeof(uint16_t),
-                               in_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        CU_TRY(copy_in(h, h->in.p, in, (size_t)n * sizeof(uint16_t), in_on_device, s));
         d_in = h->in.as<uint16_t>();
     }
     B4D_TRY(h->hist.ensure(65536 * sizeof(unsigned long long)));

@@ -375,3 +375,27 @@ def test_pipelined_host_transfers_equal_device_result(b4d_mod):
     d.slab_stage1(vol, 0, 208, 24.0)                                   # two-call form, host out
     assert np.array_equal(d.slab_stage2(0, 208), dev)
     d.close()
+
+
+def test_pageable_and_pinned_host_arrays_give_the_same_bytes(dn, b4d_mod, oracle_lib):
+    """NumPy arrays are pageable memory: they cross PCIe through the pinned ring + copy threads of
+    the HostMover (16 MiB pieces, several per call, ragged tail); pinned torch tensors are copied
+    directly.  Both must deliver every byte — checked on the bandwidth-bound quantize call with
+    a buffer of many pieces, and on the denoiser with pageable against pinned buffers."""
+    import torch
+
+    from b4d import synth
+
+    rng = np.random.default_rng(9)
+    x = rng.normal(500, 700, 5 * (4 << 20) + 12_345).astype(np.float32)  # 5 pieces + a ragged one
+    want = oracle_lib.quantize_reference(x)
+    assert np.array_equal(dn.quantize(x), want)                                    # pageable in, pageable out
+    xp = torch.from_numpy(x).pin_memory()
+    assert np.array_equal(dn.quantize(xp).numpy(), want)                           # pinned in
+    assert np.array_equal(dn.quantize(x[1:]), want[1:])                            # odd alignment
+    st = dn.tile_stats(want)
+    assert st["n"] == want.size and st["vmax"] == float(want.max())
+    vol = synth.vol(208, 40, 52, seed=5)
+    a = dn.denoise(vol, 24.0)                                                      # pageable, chunked pipeline
+    b = dn.denoise(torch.from_numpy(vol).pin_memory(), 24.0).numpy()               # pinned, chunked pipeline
+    assert np.array_equal(a, b)
