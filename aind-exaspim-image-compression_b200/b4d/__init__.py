@@ -17,6 +17,7 @@ from .api import (  # noqa: F401
     tile_stats,
 )
 from .cache import load_patch_cache, write_patch_cache  # noqa: F401
+from .codec import chunk_grid, chunk_shuffle, compute_cratio, entropy_bytes, estimate_cratio  # noqa: F401
 from .sharding import (  # noqa: F401
     denoise_slab_exchange,
     denoise_volume_sharded,
@@ -46,5 +47,10 @@ __all__ = [
     "exchange_planes",
     "stats_from_hist",
     "write_patch_cache",
+    "chunk_grid",
+    "chunk_shuffle",
+    "compute_cratio",
+    "entropy_bytes",
+    "estimate_cratio",
     "load_patch_cache",
 ]

@@ -397,6 +397,71 @@ class Denoiser:
         )
         return out
 
+    def chunk_shuffle(self, x, chunk=(64, 64, 64), want_bytes=True, want_hist=True):
+        """K9: C-order chunk gather + Blosc 2-byte shuffle of a uint16 volume, plus per-piece byte
+        histograms [pieces, 2, 256] (uint32).  Returns (bytes or None, hist or None)."""
+        if len(chunk) != 3:
+            raise ValueError("chunk must have three entries")
+        if not (want_bytes or want_hist):
+            raise ValueError("nothing requested")
+        torch_in = _is_torch(x)
+        if torch_in:
+            import torch
+
+            xc = x.contiguous()
+            if xc.dtype != torch.uint16 or xc.ndim != 3:
+                raise ValueError("chunk_shuffle expects a 3-D uint16 volume")
+            on_dev = xc.is_cuda
+            if on_dev:
+                torch.cuda.current_stream(xc.device).synchronize()
+            shape, in_ptr = tuple(xc.shape), xc.data_ptr()
+        else:
+            xc = np.ascontiguousarray(x)
+            if xc.dtype != np.uint16 or xc.ndim != 3:
+                raise ValueError("chunk_shuffle expects a 3-D uint16 volume")
+            on_dev = False
+            shape, in_ptr = xc.shape, xc.ctypes.data
+        npieces = 1
+        for s_, c_ in zip(shape, chunk):
+            if int(c_) < 1:
+                raise ValueError("chunk sides must be >= 1")
+            npieces *= -(-int(s_) // int(c_))
+        nvox = int(shape[0]) * int(shape[1]) * int(shape[2])
+        out = hist = None
+        out_ptr = hist_ptr = None
+        if on_dev:
+            if want_bytes:
+                out = torch.empty(2 * nvox, dtype=torch.uint8, device=xc.device)
+                out_ptr = out.data_ptr()
+            if want_hist:
+                hist = torch.empty((npieces, 2, 256), dtype=torch.int32, device=xc.device)
+                hist_ptr = hist.data_ptr()
+        else:
+            if want_bytes:
+                out = np.empty(2 * nvox, dtype=np.uint8)
+                out_ptr = out.ctypes.data
+            if want_hist:
+                hist = np.empty((npieces, 2, 256), dtype=np.uint32)
+                hist_ptr = hist.ctypes.data
+        _lib.check(
+            self.lib.b4d_chunk_shuffle_u16(
+                self._h,
+                ctypes.c_void_p(in_ptr),
+                _lib.shape3(shape),
+                _lib.shape3(chunk),
+                ctypes.c_void_p(out_ptr),
+                ctypes.c_void_p(hist_ptr),
+                int(on_dev),
+                int(on_dev),
+            )
+        )
+        if torch_in and not on_dev:
+            import torch
+
+            out = torch.from_numpy(out) if out is not None else None
+            hist = torch.from_numpy(hist.view(np.int32)) if hist is not None else None
+        return out, hist
+
     def tile_stats(self, x, percentile=1.0, return_hist=False):
         """K8: offset percentile over non-zero voxels + median / MAD sigma of a uint16 tile."""
         if _is_torch(x):

@@ -1112,6 +1112,49 @@ static float percentile_f32(const std::vector<unsigned long long> &hist, int fir
     return r;
 }
 
+int b4d_chunk_shuffle_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], const int64_t chunk[3],
+                          uint8_t *out, uint32_t *hist, int in_on_device, int out_on_device) {
+    if (!h || !in || !shape || !chunk) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!out && !hist) return fail(B4D_ERR_INVALID, "nothing to compute: out and hist are both NULL");
+    for (int a = 0; a < 3; ++a) {
+        if (shape[a] < 1 || shape[a] > INT32_MAX) return fail(B4D_ERR_INVALID, "bad shape");
+        if (chunk[a] < 1 || chunk[a] > INT32_MAX) return fail(B4D_ERR_INVALID, "bad chunk shape");
+    }
+    {
+        double pv = 1.0;  // voxels of the largest piece
+        for (int a = 0; a < 3; ++a) pv *= (double)std::min(chunk[a], shape[a]);
+        if (pv > 1073741824.0) return fail(B4D_ERR_TOO_LARGE, "a piece may hold at most 2^30 voxels");
+    }
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const long long n = shape[0] * shape[1] * shape[2];
+    long long nchunks = 1;
+    for (int a = 0; a < 3; ++a) nchunks *= (shape[a] + chunk[a] - 1) / chunk[a];
+    const uint16_t *d_in = in;
+    if (!in_on_device) {
+        B4D_TRY(h->in.ensure((size_t)n * sizeof(uint16_t)));
+        CU_TRY(copy_in(h, h->in.p, in, (size_t)n * sizeof(uint16_t), 0, s));
+        d_in = h->in.as<uint16_t>();
+    }
+    uint8_t *d_out = out;
+    if (out && !out_on_device) {
+        B4D_TRY(h->u16.ensure((size_t)n * sizeof(uint16_t) + 16));
+        d_out = h->u16.as<uint8_t>();
+    }
+    uint32_t *d_hist = hist;
+    if (hist && !out_on_device) {
+        B4D_TRY(h->hist.ensure((size_t)nchunks * 512 * sizeof(uint32_t)));
+        d_hist = h->hist.as<uint32_t>();
+    }
+    b4d_launch_chunk_shuffle(d_in, (int)shape[0], (int)shape[1], (int)shape[2], (int)chunk[0], (int)chunk[1],
+                             (int)chunk[2], d_out, d_hist, s);
+    CU_TRY(cudaGetLastError());
+    if (out && d_out != out) CU_TRY(copy_out(h, out, d_out, (size_t)n * sizeof(uint16_t), 0, s));
+    if (hist && d_hist != hist) CU_TRY(copy_out(h, hist, d_hist, (size_t)nchunks * 512 * sizeof(uint32_t), 0, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
 int b4d_tile_stats(b4d_handle *h, const uint16_t *in, int64_t n, double pct, b4d_stats *out, int64_t *hist_out,
                    int in_on_device) {
     if (!h || !in || !out || n < 1) return fail(B4D_ERR_INVALID, "NULL argument or empty tile");

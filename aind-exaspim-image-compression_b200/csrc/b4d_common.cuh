@@ -90,6 +90,9 @@ void b4d_launch_normalise_det(const long long *numq, const long long *denq, cons
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s);
 void b4d_launch_hist(const uint16_t *in, long long n, unsigned long long *hist, cudaStream_t s);
+// K9: C-order chunk gather + 2-byte shuffle (+ per-chunk byte histograms [nchunks][2][256])
+void b4d_launch_chunk_shuffle(const uint16_t *in, int D, int H, int W, int cz, int cy, int cx, uint8_t *out,
+                              uint32_t *hist, cudaStream_t s);
 // analysis of a float32 volume for the matching map: partial[6*blocks] doubles
 int b4d_analyze_blocks();
 void b4d_launch_analyze(const float *in, long long n, double c, double *partial, cudaStream_t s);

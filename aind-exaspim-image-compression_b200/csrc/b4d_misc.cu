@@ -180,6 +180,163 @@ __global__ void __launch_bounds__(256) k_quantize(const float *__restrict__ in, 
         out[i] = (uint16_t)quant1(in[i], osub, oadd, step, hi, unit);
 }
 
+// --------------------------------------------------- chunk byte shuffle ----
+// K9 (first step): the chunking of compute_cratio (img_util.py:401-441) — a C-order
+// grid of cz x cy x cx pieces, ragged at the far faces, each piece made contiguous — followed by the
+// byte shuffle Blosc SHUFFLE applies to 2-byte items: all low bytes of the piece, then all high bytes.
+// Piece (iz, iy, ix) starts at element z0*H*W + dz*(y0*W + dy*x0) of the output (the pieces before it
+// in C order hold exactly that many voxels).  Also counts the byte values of both planes per piece
+// (hist[piece][plane][256]); a warp whose 128 bytes are all equal (the high plane of background) adds once.
+// Measured on B200: 32 lane-private replicas of the counters (no intra-warp collisions) were SLOWER than
+// one copy — the kernel is bound by the memory pipeline, not by the shared-memory atomics.
+__device__ __forceinline__ void red_shared_add(uint32_t *p, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void hist_add4(uint32_t *sh, uint32_t b4, bool valid, int nvalid) {
+    const uint32_t b0 = __shfl_sync(B4D_FULL, b4, 0);
+    const bool uni = __all_sync(B4D_FULL, !valid || b4 == b0) && b0 == (b0 & 0xFFu) * 0x01010101u;
+    if (uni) {
+        if ((threadIdx.x & 31) == 0) red_shared_add(&sh[b0 & 0xFFu], 4u * nvalid);
+    } else if (valid) {
+        if (b4 == (b4 & 0xFFu) * 0x01010101u) {
+            red_shared_add(&sh[b4 & 0xFFu], 4u);
+        } else {
+            red_shared_add(&sh[b4 & 0xFFu], 1u);
+            red_shared_add(&sh[(b4 >> 8) & 0xFFu], 1u);
+            red_shared_add(&sh[(b4 >> 16) & 0xFFu], 1u);
+            red_shared_add(&sh[b4 >> 24], 1u);
+        }
+    }
+}
+// One piece whose rows are whole groups of V voxels (V = 4: 8-byte loads, V = 8: 16-byte loads).  Group
+// t = row * q + k holds elements [V t, V t + V) of the piece; (row, k) and (z, y) advance incrementally with
+// carries (no division in the loop) and UN loads are in flight per thread.
+template <int V>
+__device__ __forceinline__ void shuffle_piece_vec(const uint16_t *__restrict__ src0, int H, int W, int dz, int dy,
+                                                  int dx, uint8_t *lo, uint8_t *hi, uint32_t *sh_lo, uint32_t *sh_hi,
+                                                  bool hist) {
+    constexpr int UN = 4, WORDS = V / 4;  // 32-bit words of low (and of high) bytes per group
+    const int q = dx / V, total = dz * dy * q;
+    const int dk = 256 % q, dr = 256 / q;
+    int k = (int)threadIdx.x % q, row = (int)threadIdx.x / q;
+    int z = row / dy, y = row - z * dy;
+    for (int base = 0; base < total; base += 256 * UN) {
+        uint32_t v[UN][2 * WORDS];
+        bool valid[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            valid[u] = base + u * 256 + (int)threadIdx.x < total;
+#pragma unroll
+            for (int w = 0; w < 2 * WORDS; ++w) v[u][w] = 0u;
+            if (valid[u]) {
+                const uint16_t *p = src0 + ((long long)z * H + y) * W + V * k;
+                if (V == 8) {
+                    const uint4 t4 = __ldcs(reinterpret_cast<const uint4 *>(p));
+                    v[u][0] = t4.x, v[u][1] = t4.y, v[u][2 * WORDS - 2] = t4.z, v[u][2 * WORDS - 1] = t4.w;
+                } else {
+                    const uint2 t2 = __ldcs(reinterpret_cast<const uint2 *>(p));
+                    v[u][0] = t2.x, v[u][1] = t2.y;
+                }
+            }
+            k += dk;
+            int step = dr;
+            if (k >= q) {
+                k -= q;
+                ++step;
+            }
+            y += step;
+            if (y >= dy) {
+                if (step <= dy) {
+                    y -= dy;
+                    ++z;
+                } else {
+                    z += y / dy;
+                    y %= dy;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int t = base + u * 256 + (int)threadIdx.x;
+            uint32_t lo4[WORDS], hi4[WORDS];
+#pragma unroll
+            for (int w = 0; w < WORDS; ++w) {
+                lo4[w] = __byte_perm(v[u][2 * w], v[u][2 * w + 1], 0x6420);
+                hi4[w] = __byte_perm(v[u][2 * w], v[u][2 * w + 1], 0x7531);
+            }
+            if (lo && valid[u]) {
+                if (V == 8) {
+                    __stcs(reinterpret_cast<uint2 *>(lo) + t, make_uint2(lo4[0], lo4[WORDS - 1]));
+                    __stcs(reinterpret_cast<uint2 *>(hi) + t, make_uint2(hi4[0], hi4[WORDS - 1]));
+                } else {
+                    __stcs(reinterpret_cast<uint32_t *>(lo) + t, lo4[0]);
+                    __stcs(reinterpret_cast<uint32_t *>(hi) + t, hi4[0]);
+                }
+            }
+            if (hist) {
+                const int nvalid = __popc(__ballot_sync(B4D_FULL, valid[u]));
+                if (nvalid) {
+#pragma unroll
+                    for (int w = 0; w < WORDS; ++w) {
+                        hist_add4(sh_lo, lo4[w], valid[u], nvalid);
+                        hist_add4(sh_hi, hi4[w], valid[u], nvalid);
+                    }
+                }
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_chunk_shuffle(const uint16_t *__restrict__ in, int D, int H, int W, int cz,
+                                                       int cy, int cx, uint8_t *__restrict__ out,
+                                                       uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh_lo[256], sh_hi[256];
+    const int nz = (D + cz - 1) / cz, ny = (H + cy - 1) / cy, nx = (W + cx - 1) / cx;
+    const long long nchunks = (long long)nz * ny * nx;
+    const uintptr_t ai = reinterpret_cast<uintptr_t>(in), ao = reinterpret_cast<uintptr_t>(out);
+    const bool al8 = (W & 7) == 0 && (ai & 15) == 0 && (ao & 7) == 0;
+    const bool al4 = (W & 3) == 0 && (ai & 7) == 0 && (ao & 3) == 0;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        if (hist) {
+            sh_lo[threadIdx.x] = 0u;
+            sh_hi[threadIdx.x] = 0u;
+            __syncthreads();
+        }
+        const int ix = (int)(c % nx), iy = (int)((c / nx) % ny), iz = (int)(c / ((long long)nx * ny));
+        const int z0 = iz * cz, y0 = iy * cy, x0 = ix * cx;
+        const int dz = min(cz, D - z0), dy = min(cy, H - y0), dx = min(cx, W - x0);
+        const long long eoff = (long long)z0 * H * W + (long long)dz * ((long long)y0 * W + (long long)dy * x0);
+        const int ne = dz * dy * dx;
+        uint8_t *lo = out ? out + 2 * eoff : nullptr;
+        uint8_t *hi = out ? lo + ne : nullptr;
+        const uint16_t *src0 = in + ((long long)z0 * H + y0) * W + x0;
+        if (al8 && (dx & 7) == 0 && (x0 & 7) == 0) {
+            shuffle_piece_vec<8>(src0, H, W, dz, dy, dx, lo, hi, sh_lo, sh_hi, hist != nullptr);
+        } else if (al4 && (dx & 3) == 0 && (x0 & 3) == 0) {
+            shuffle_piece_vec<4>(src0, H, W, dz, dy, dx, lo, hi, sh_lo, sh_hi, hist != nullptr);
+        } else {
+            for (int e = threadIdx.x; e < ne; e += 256) {
+                const int row = e / dx;
+                const int x = e - row * dx, z = row / dy, y = row - z * dy;
+                const uint32_t v = src0[((long long)z * H + y) * W + x];
+                if (out) {
+                    lo[e] = (uint8_t)(v & 0xFFu);
+                    hi[e] = (uint8_t)(v >> 8);
+                }
+                if (hist) {
+                    red_shared_add(&sh_lo[v & 0xFFu], 1u);
+                    red_shared_add(&sh_hi[v >> 8], 1u);
+                }
+            }
+        }
+        if (hist) {
+            __syncthreads();
+            hist[c * 512 + threadIdx.x] = sh_lo[threadIdx.x];
+            hist[c * 512 + 256 + threadIdx.x] = sh_hi[threadIdx.x];
+            __syncthreads();
+        }
+    }
+}
+
 // ------------------------------------------------------------- histogram ----
 // K8: exact 65536-bin histogram of a uint16 tile.  Bins below HOT live in a
 // per-CTA shared-memory histogram (ExaSPIM background sits there), the rest go
@@ -320,6 +477,11 @@ void b4d_launch_normalise_det(const long long *numq, const long long *denq, cons
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s) {
     k_quantize<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, offset_sub, offset_add, step);
+}
+void b4d_launch_chunk_shuffle(const uint16_t *in, int D, int H, int W, int cz, int cy, int cx, uint8_t *out,
+                              uint32_t *hist, cudaStream_t s) {
+    const long long nchunks = (long long)((D + cz - 1) / cz) * ((H + cy - 1) / cy) * ((W + cx - 1) / cx);
+    k_chunk_shuffle<<<grid_for(nchunks * 256, 256, 8), 256, 0, s>>>(in, D, H, W, cz, cy, cx, out, hist);
 }
 void b4d_launch_hist(const uint16_t *in, long long n, unsigned long long *hist, cudaStream_t s) {
     k_hist<<<grid_for(n >> 3, 512, 2), 512, 0, s>>>(in, n, hist);

@@ -349,7 +349,23 @@ def main():
         ms = ev0.elapsed_time(ev1)
         q_ms = ms if q_ms is None else min(q_ms, ms)
     q_vox = float(y_last.numel())
-    del y_last, qv
+    # ---- K9: chunk gather + byte shuffle + byte counts of the quantized slab (64^3 pieces), same way
+    c_ms = cb_ms = None
+    for _ in range(4):
+        ev0.record(ext)
+        cby, chist = dn.chunk_shuffle(qv, (64, 64, 64))
+        ev1.record(ext)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        c_ms = ms if c_ms is None else min(c_ms, ms)
+        ev0.record(ext)
+        cby, _ = dn.chunk_shuffle(qv, (64, 64, 64), want_hist=False)
+        ev1.record(ext)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        cb_ms = ms if cb_ms is None else min(cb_ms, ms)
+    cratio_est = b4d.estimate_cratio(chist.cpu().numpy()) if rank == 0 else None
+    del y_last, qv, cby, chist
 
     # ---- timed: end to end with host buffers
     step_e2e()
@@ -398,6 +414,11 @@ def main():
             # K7: float32 read + uint16 write = 6 B/voxel
             "quantize": {"bound": "hbm", "achieved": 6.0 * q_vox / (q_ms * 1e-3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": 6.0 * q_vox / (q_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": q_ms},
+            # K9: uint16 read + 2 bytes written = 4 B/voxel
+            "chunk_shuffle": {"bound": "hbm", "achieved": 4.0 * q_vox / (c_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                              "unit": "GB/s", "frac": 4.0 * q_vox / (c_ms * 1e-3) / 1e9 / hbm_peak,
+                              "ms_per_launch": c_ms, "entropy_cratio_of_quantized_slab": cratio_est,
+                              "bytes_only_ms": cb_ms, "bytes_only_frac": 4.0 * q_vox / (cb_ms * 1e-3) / 1e9 / hbm_peak},
             "filter_ht_ms": fam.get("filter1", 0.0) / args.steps,
             "filter_wiener_ms": fam.get("filter2", 0.0) / args.steps,
         }

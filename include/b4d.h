@@ -163,6 +163,18 @@ int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub
                      float offset_add, float step, uint16_t *out, int in_on_device,
                      int out_on_device);
 
+/* K9 — chunking + byte shuffle ahead of the chunk codec (first step).
+ * The volume is cut the way compute_cratio does (utils/img_util.py:427-438): a C-order grid of
+ * `chunk`-shaped pieces, ragged at the far faces, each piece made contiguous.  Each piece is then
+ * byte-shuffled as Blosc SHUFFLE does for 2-byte items (evaluate.py:40): all low bytes, then all
+ * high bytes.  `out` (2 * voxels bytes, NULL-able) receives the pieces back to back in grid order;
+ * piece (iz,iy,ix) starts at byte 2 * (z0*H*W + dz*(y0*W + dy*x0)).  `hist` (NULL-able) receives
+ * [pieces][2][256] uint32 counts of the byte values of the low and the high plane — the input of
+ * an order-0 entropy estimate of the compressed size.  `out_on_device` applies to both outputs. */
+int b4d_chunk_shuffle_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3],
+                          const int64_t chunk[3], uint8_t *out, uint32_t *hist, int in_on_device,
+                          int out_on_device);
+
 /* Per-tile statistics, K8.  Also returns the exact 65536-bin histogram when
  * `hist` is non-NULL (host pointer, 65536 x int64) — that histogram is the
  * payload ranks allgather to agree on a global offset / sigma. */

@@ -895,6 +895,36 @@ int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *,
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }
 void *b4d_stream(b4d_handle *) { return nullptr; }
+int b4d_chunk_shuffle_u16(b4d_handle *, const uint16_t *in, const int64_t shape[3], const int64_t chunk[3],
+                          uint8_t *out, uint32_t *hist, int, int) {
+    // restatement of the chunk loop of compute_cratio (img_util.py:427-438) + Blosc SHUFFLE, typesize 2
+    if (!in || !shape || !chunk || (!out && !hist)) return fail(B4D_ERR_INVALID, "NULL argument");
+    const int64_t D = shape[0], H = shape[1], W = shape[2];
+    int64_t pos = 0, piece = 0;
+    for (int64_t z0 = 0; z0 < D; z0 += chunk[0])
+        for (int64_t y0 = 0; y0 < H; y0 += chunk[1])
+            for (int64_t x0 = 0; x0 < W; x0 += chunk[2], ++piece) {
+                const int64_t dz = std::min(chunk[0], D - z0), dy = std::min(chunk[1], H - y0),
+                              dx = std::min(chunk[2], W - x0), ne = dz * dy * dx;
+                if (hist) std::memset(hist + piece * 512, 0, 512 * sizeof(uint32_t));
+                int64_t e = 0;
+                for (int64_t z = 0; z < dz; ++z)
+                    for (int64_t y = 0; y < dy; ++y)
+                        for (int64_t x = 0; x < dx; ++x, ++e) {
+                            const uint16_t v = in[((z0 + z) * H + y0 + y) * W + x0 + x];
+                            if (out) {
+                                out[pos + e] = (uint8_t)(v & 0xFF);
+                                out[pos + ne + e] = (uint8_t)(v >> 8);
+                            }
+                            if (hist) {
+                                ++hist[piece * 512 + (v & 0xFF)];
+                                ++hist[piece * 512 + 256 + (v >> 8)];
+                            }
+                        }
+                pos += 2 * ne;
+            }
+    return 0;
+}
 int b4d_targets_u16(b4d_handle *hh, const uint16_t *in, int64_t n, const int64_t shape[3], const float *offsets,
                     float sigma, float max_count, float *raw_out, float *teacher_out, int, int) {
     // restatement of data_handling.py:353-354, :332-333 over the oracle's own float32 entry point

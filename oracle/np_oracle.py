@@ -69,6 +69,26 @@ def quantize_truncating(x):
     return np.ascontiguousarray(np.maximum(x, 0).astype(int), dtype=np.uint16)
 
 
+def chunk_shuffle_reference(img, patch_shape=(64, 64, 64)):
+    """The chunk loop of compute_cratio (utils/img_util.py:427-438) with Blosc's byte shuffle for
+    2-byte items applied to each piece instead of the codec call: returns (bytes of all pieces back
+    to back — low bytes then high bytes per piece —, hist[pieces, 2, 256])."""
+    img = np.ascontiguousarray(img, dtype=np.uint16)  # img_util.py:423
+    parts, hists = [], []
+    z = [range(0, s, c) for s, c in zip(img.shape, patch_shape)]
+    for z0 in z[0]:
+        for z1 in z[1]:
+            for z2 in z[2]:
+                piece = np.ascontiguousarray(
+                    img[z0 : z0 + patch_shape[0], z1 : z1 + patch_shape[1], z2 : z2 + patch_shape[2]]
+                )
+                by = piece.reshape(-1).view(np.uint8).reshape(-1, 2)  # little endian: [:, 0] low, [:, 1] high
+                lo, hi = np.ascontiguousarray(by[:, 0]), np.ascontiguousarray(by[:, 1])
+                parts += [lo, hi]
+                hists.append([np.bincount(lo, minlength=256), np.bincount(hi, minlength=256)])
+    return np.concatenate(parts), np.asarray(hists, dtype=np.uint32)
+
+
 def estimate_offset(sample, percentile=1.0, ignore_zeros=True):
     """Low percentile over non-zero voxels (transforms.py:433-438)."""
     sample = np.asarray(sample, dtype=np.float32).reshape(-1)

@@ -399,3 +399,50 @@ def test_pageable_and_pinned_host_arrays_give_the_same_bytes(dn, b4d_mod, oracle
     a = dn.denoise(vol, 24.0)                                                      # pageable, chunked pipeline
     b = dn.denoise(torch.from_numpy(vol).pin_memory(), 24.0).numpy()               # pinned, chunked pipeline
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize(
+    "shape,chunk",
+    [((64, 64, 64), (64, 64, 64)), ((128, 64, 192), (64, 64, 64)), ((70, 66, 130), (64, 64, 64)),
+     ((20, 33, 35), (8, 16, 4)), ((40, 36, 44), (32, 16, 8)), ((5, 3, 2), (64, 64, 64))],
+)
+def test_chunk_shuffle_bit_exact(shape, chunk, dn, oracle_lib):
+    """K9 (first step): chunk gather + Blosc 2-byte shuffle + per-piece byte counts,
+    against the restatement of compute_cratio's loop (utils/img_util.py:427-438) — bytes and counts equal."""
+    import torch
+
+    from b4d import synth
+
+    vol = synth.vol(*shape, seed=sum(shape))
+    vol[: shape[0] // 2] //= 8  # a region whose high bytes are all zero (the warp-uniform path)
+    by, hist = oracle_lib.chunk_shuffle_reference(vol, chunk)
+    gby, ghist = dn.chunk_shuffle(vol, chunk)
+    assert gby.dtype == np.uint8 and np.array_equal(gby, by)
+    assert ghist.dtype == np.uint32 and np.array_equal(ghist, hist)
+    tby, thist = dn.chunk_shuffle(torch.from_numpy(vol).cuda(), chunk)  # device in -> device out
+    assert tby.is_cuda and np.array_equal(tby.cpu().numpy(), by)
+    assert np.array_equal(thist.cpu().numpy().view(np.uint32), hist)
+    only_hist = dn.chunk_shuffle(vol, chunk, want_bytes=False)
+    assert only_hist[0] is None and np.array_equal(only_hist[1], hist)
+
+
+def test_cratio_of_shuffled_pieces_round_trips(dn, b4d_mod):
+    """Device shuffle -> host zstd (the system library) -> decompress -> unshuffle gives the volume back;
+    the ratio has the reference's shape (total / total, 2 decimals) and denoising raises it."""
+    from b4d import codec, synth
+
+    if not codec.zstd_available():
+        pytest.skip("libzstd not loadable on this host")
+    vol = synth.vol(70, 64, 128, seed=8)
+    by, hist = dn.chunk_shuffle(vol)
+    back = np.zeros_like(vol)
+    for (z0, y0, x0), d, pos in codec.chunk_grid(vol.shape):
+        nb = 2 * d[0] * d[1] * d[2]
+        c = codec.zstd_compress(by[pos : pos + nb], 6)
+        back[z0 : z0 + d[0], y0 : y0 + d[1], x0 : x0 + d[2]] = codec.unshuffle_piece(codec.zstd_decompress(c, nb), d)
+    assert np.array_equal(back, vol)
+    r_noisy = b4d_mod.compute_cratio(vol)
+    den = b4d_mod.quantize(b4d_mod.bm4d(vol, 24.0))
+    r_den = b4d_mod.compute_cratio(den)
+    assert r_noisy == round(r_noisy, 2) and r_den > r_noisy > 1.0
+    assert b4d_mod.estimate_cratio(dn.chunk_shuffle(den, want_bytes=False)[1]) > b4d_mod.estimate_cratio(hist)
