@@ -11,6 +11,7 @@ from .api import (  # noqa: F401
     bm4d,
     bm4d_batch,
     get_denoiser,
+    make_foreground_mask,
     noise_scaled_step,
     precompute_targets,
     quantize,
@@ -35,6 +36,7 @@ __all__ = [
     "bm4d",
     "bm4d_batch",
     "get_denoiser",
+    "make_foreground_mask",
     "noise_scaled_step",
     "precompute_targets",
     "quantize",

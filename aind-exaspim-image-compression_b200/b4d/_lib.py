@@ -25,6 +25,7 @@ EXPORTS = (
     "b4d_denoise_f32",
     "b4d_targets_u16",
     "b4d_chunk_shuffle_u16",
+    "b4d_foreground_mask_u16",
     "b4d_denoise_slab_u16",
     "b4d_slab_stage1_u16",
     "b4d_slab_basic_planes",

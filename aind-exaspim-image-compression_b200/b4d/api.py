@@ -397,6 +397,31 @@ class Denoiser:
         )
         return out
 
+    def foreground_mask(self, raw_u16, offsets=0.0, k=6.0, dilate=1):
+        """make_foreground_mask (metrics.py:32-61) of uint16 patches after the offset subtraction
+        (data_handling.py:353-354): (D,H,W) or (N,D,H,W) uint16 -> bool mask of the same shape."""
+        zc = np.ascontiguousarray(raw_u16)
+        if zc.dtype != np.uint16 or zc.ndim not in (3, 4):
+            raise ValueError("raw_u16 must be a uint16 volume or a (N, D, H, W) batch")
+        n = zc.shape[0] if zc.ndim == 4 else 1
+        off = np.ascontiguousarray(np.broadcast_to(np.asarray(offsets, dtype=np.float32), (n,)))
+        out = np.empty(zc.shape, dtype=np.uint8)
+        _lib.check(
+            self.lib.b4d_foreground_mask_u16(
+                self._h,
+                ctypes.c_void_p(zc.ctypes.data),
+                ctypes.c_int64(n),
+                _lib.shape3(zc.shape[-3:]),
+                ctypes.c_void_p(off.ctypes.data),
+                ctypes.c_float(k),
+                ctypes.c_int(int(dilate)),
+                ctypes.c_void_p(out.ctypes.data),
+                0,
+                0,
+            )
+        )
+        return out.view(np.bool_)
+
     def chunk_shuffle(self, x, chunk=(64, 64, 64), want_bytes=True, want_hist=True):
         """K9: C-order chunk gather + Blosc 2-byte shuffle of a uint16 volume, plus per-piece byte
         histograms [pieces, 2, 256] (uint32).  Returns (bytes or None, hist or None)."""
@@ -615,6 +640,13 @@ def precompute_targets(raw_u16, offsets, sigma, max_count=65535.0, device=None):
     h = get_denoiser(device)
     h.set_profile("np", 2)
     return h.targets(raw_u16, offsets, _sigma_scalar(sigma), max_count)
+
+
+def make_foreground_mask(raw_u16, offset=0.0, k=6.0, dilate=1, device=None):
+    """The reference's ``make_foreground_mask(raw, k, dilate)`` (metrics.py:32-61) for
+    raw = uint16 patch (or batch) -> float32 - offset: the fallback mask of a patch without
+    annotation (data_handling.py:444, :928-929)."""
+    return get_denoiser(device).foreground_mask(raw_u16, offset, k, dilate)
 
 
 def quantize(x, offset_sub=0.0, offset_add=0.0, step=1.0, device=None):

@@ -36,14 +36,24 @@ def _default_targets(raw_u16, offsets, sigma, max_count):
     return api.precompute_targets(raw_u16, offsets, sigma, max_count=max_count)
 
 
+def _default_fg(raw_u16, offsets):
+    from . import api
+
+    return api.make_foreground_mask(raw_u16, offsets)
+
+
 def write_patch_cache(cache_dir, patches_u16, offsets, sigma_bm4d, fg=None, transform_cfg=None, split="train",
-                      extra_config=None, max_count=65535.0, batch=64, resume=True, targets_fn=None):
+                      extra_config=None, max_count=65535.0, batch=64, resume=True, targets_fn=None, fg_fn=None):
     """Build (or finish) a patch cache in the reference's layout.
 
     patches_u16   (N, D, H, W) uint16 array or memmap: the sampled raw patches
     offsets       scalar or (N,) per-patch background offsets (data_handling.py:353-354)
     sigma_bm4d    noise sigma handed to BM4D (precompute.py:284: 24)
-    fg            optional (N, D, H, W) foreground masks (0/1); zeros when absent
+    fg            optional (N, D, H, W) foreground masks (0/1) from annotations; when absent the
+                  reference's no-annotation fallback is used: make_foreground_mask(raw)
+                  (data_handling.py:444, :928-929; metrics.py:32-61), computed on the GPU
+    fg_fn         (raw_u16, offsets) -> mask; defaults to ``b4d.make_foreground_mask`` (tests
+                  inject the CPU oracle)
     transform_cfg resolved transform cfg stamped into transform.json / config.json
     batch         patches per GPU launch
     targets_fn    (raw_u16, offsets, sigma, max_count) -> (raw f32, teacher f32); defaults
@@ -60,6 +70,7 @@ def write_patch_cache(cache_dir, patches_u16, offsets, sigma_bm4d, fg=None, tran
     if fg is not None and tuple(fg.shape) != shape:
         raise ValueError("fg must have the shape of patches_u16")
     targets_fn = targets_fn or _default_targets
+    fg_fn = fg_fn or _default_fg
     tcfg = dict(transform_cfg or DEFAULT_TRANSFORM_CFG)
     os.makedirs(cache_dir, exist_ok=True)
 
@@ -100,7 +111,10 @@ def write_patch_cache(cache_dir, patches_u16, offsets, sigma_bm4d, fg=None, tran
         raw, teacher = targets_fn(np.ascontiguousarray(patches_u16[idx]), off[idx], float(sigma_bm4d), max_count)
         raw_mm[idx] = np.asarray(raw, dtype=COUNT_DTYPE)
         teacher_mm[idx] = np.asarray(teacher, dtype=COUNT_DTYPE)
-        fg_mm[idx] = 0 if fg is None else np.asarray(fg[idx], dtype=np.uint8)
+        if fg is None:
+            fg_mm[idx] = np.asarray(fg_fn(np.ascontiguousarray(patches_u16[idx]), off[idx]), dtype=np.uint8)
+        else:
+            fg_mm[idx] = np.asarray(fg[idx], dtype=np.uint8)
         raw_mm.flush()
         teacher_mm.flush()
         fg_mm.flush()

@@ -1112,6 +1112,96 @@ static float percentile_f32(const std::vector<unsigned long long> &hist, int fir
     return r;
 }
 
+// Threshold of make_foreground_mask (metrics.py:54-58) for raw = float32(u) - off, from the exact histogram of
+// u.  Order statistics commute with the monotone map u -> float32(u) - off, so every float32 step of the NumPy
+// code (median = mean of the two middle values, |raw - med|, its median, + 1e-6, * 1.4826, med + k * sigma;
+// Python-float constants are weak under NEP 50, the arithmetic stays float32) is reproduced on the
+// distinct values only.
+static float robust_threshold(const unsigned long long *hist, long long n, float off, float k) {
+    auto kth_u = [&](long long r) -> int {
+        long long c = 0;
+        for (int v = 0; v < 65536; ++v) {
+            c += (long long)hist[v];
+            if (r < c) return v;
+        }
+        return 65535;
+    };
+    const float a = (float)kth_u((n - 1) / 2) - off, b = (float)kth_u(n / 2) - off;
+    const float med = (a + b) / 2.0f;
+    std::vector<std::pair<float, unsigned long long>> dev;
+    for (int v = 0; v < 65536; ++v)
+        if (hist[v]) dev.emplace_back(std::fabs(((float)v - off) - med), hist[v]);
+    std::sort(dev.begin(), dev.end());
+    auto kth_d = [&](long long r) -> float {
+        long long c = 0;
+        for (const auto &e : dev) {
+            c += (long long)e.second;
+            if (r < c) return e.first;
+        }
+        return dev.back().first;
+    };
+    const float mad = (kth_d((n - 1) / 2) + kth_d(n / 2)) / 2.0f + 1e-6f;
+    const float sigma = 1.4826f * mad;
+    return med + k * sigma;
+}
+
+int b4d_foreground_mask_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t shape[3],
+                            const float *offsets, float k, int dilate, uint8_t *out, int in_on_device,
+                            int out_on_device) {
+    if (!h || !in || !out || !shape || !offsets) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (n < 1) return fail(B4D_ERR_INVALID, "n must be >= 1");
+    for (int a = 0; a < 3; ++a)
+        if (shape[a] < 1 || shape[a] > INT32_MAX) return fail(B4D_ERR_INVALID, "bad shape");
+    if (dilate < 0 || dilate > 8) return fail(B4D_ERR_INVALID, "dilate must be in [0, 8]");
+    if (!std::isfinite(k)) return fail(B4D_ERR_INVALID, "k must be finite");
+    const long long V = shape[0] * shape[1] * shape[2];
+    if (V > INT32_MAX) return fail(B4D_ERR_TOO_LARGE, "a patch may hold at most 2^31 - 1 voxels");
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    constexpr int G = 32;  // patches per histogram round trip
+    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, CHUNK_VOXELS / V));
+    std::vector<unsigned long long> hist((size_t)G * 65536);
+    for (int64_t i0 = 0; i0 < n; i0 += per) {
+        const int64_t nb = std::min<int64_t>(per, n - i0);
+        const long long TV = V * nb;
+        const uint16_t *d_in = in + i0 * V;
+        if (!in_on_device) {
+            B4D_TRY(h->in.ensure((size_t)TV * sizeof(uint16_t)));
+            CU_TRY(copy_in(h, h->in.p, in + i0 * V, (size_t)TV * sizeof(uint16_t), 0, s));
+            d_in = h->in.as<uint16_t>();
+        }
+        std::vector<float> thr((size_t)nb);
+        B4D_TRY(h->hist.ensure((size_t)G * 65536 * sizeof(unsigned long long)));
+        for (int64_t g0 = 0; g0 < nb; g0 += G) {
+            const int64_t ng = std::min<int64_t>(G, nb - g0);
+            CU_TRY(cudaMemsetAsync(h->hist.p, 0, (size_t)ng * 65536 * sizeof(unsigned long long), s));
+            for (int64_t g = 0; g < ng; ++g)
+                b4d_launch_hist(d_in + (g0 + g) * V, V, h->hist.as<unsigned long long>() + g * 65536, s);
+            CU_TRY(cudaGetLastError());
+            CU_TRY(copy_out(h, hist.data(), h->hist.p, (size_t)ng * 65536 * sizeof(unsigned long long), 0, s));
+            CU_TRY(cudaStreamSynchronize(s));
+            for (int64_t g = 0; g < ng; ++g) {
+                if (!std::isfinite(offsets[i0 + g0 + g])) return fail(B4D_ERR_INVALID, "offsets must be finite");
+                thr[(size_t)(g0 + g)] = robust_threshold(hist.data() + g * 65536, V, offsets[i0 + g0 + g], k);
+            }
+        }
+        B4D_TRY(h->partial.ensure((size_t)nb * 2 * sizeof(float)));
+        float *d_off = h->partial.as<float>(), *d_thr = d_off + nb;
+        CU_TRY(cudaMemcpyAsync(d_off, offsets + i0, (size_t)nb * sizeof(float), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(d_thr, thr.data(), (size_t)nb * sizeof(float), cudaMemcpyHostToDevice, s));
+        uint8_t *d_out = out + i0 * V;
+        if (!out_on_device) {
+            B4D_TRY(h->u16.ensure((size_t)TV + 16));
+            d_out = h->u16.as<uint8_t>();
+        }
+        b4d_launch_fg_mask(d_in, d_off, d_thr, (int)shape[0], (int)shape[1], (int)shape[2], TV, dilate, d_out, s);
+        CU_TRY(cudaGetLastError());
+        if (!out_on_device) CU_TRY(copy_out(h, out + i0 * V, d_out, (size_t)TV, 0, s));
+        CU_TRY(cudaStreamSynchronize(s));  // thr / offsets staging is reused by the next chunk
+    }
+    return 0;
+}
+
 int b4d_chunk_shuffle_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], const int64_t chunk[3],
                           uint8_t *out, uint32_t *hist, int in_on_device, int out_on_device) {
     if (!h || !in || !shape || !chunk) return fail(B4D_ERR_INVALID, "NULL argument");

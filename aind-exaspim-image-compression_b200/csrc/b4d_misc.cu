@@ -337,6 +337,40 @@ __global__ void __launch_bounds__(256) k_chunk_shuffle(const uint16_t *__restric
     }
 }
 
+// ------------------------------------------------------- foreground mask ----
+// make_foreground_mask (metrics.py:58-60) once the robust threshold is known: mask = raw > thr with
+// raw = float32(u16) - offset (data_handling.py:353-354), then `dilate` iterations of binary dilation
+// with the 6-neighbour structuring element and border value 0 — i.e. the L1 ball of radius `dilate`,
+// clipped at the patch faces.  One thread per voxel; thr / off are per patch.
+__global__ void __launch_bounds__(256) k_fg_mask(const uint16_t *__restrict__ in, const float *__restrict__ off,
+                                                 const float *__restrict__ thr, int D, int H, int W, long long n,
+                                                 int dilate, uint8_t *__restrict__ out) {
+    const long long V = (long long)D * H * W;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long pi = i / V;
+        const int r = (int)(i - pi * V);
+        const int z = r / (H * W), y = (r / W) % H, x = r % W;
+        const float o = __ldg(off + pi), t = __ldg(thr + pi);
+        const uint16_t *vol = in + pi * V;
+        bool m = false;
+        for (int dz = -dilate; dz <= dilate && !m; ++dz) {
+            const int zz = z + dz;
+            if (zz < 0 || zz >= D) continue;
+            const int ry = dilate - abs(dz);
+            for (int dy = -ry; dy <= ry && !m; ++dy) {
+                const int yy = y + dy;
+                if (yy < 0 || yy >= H) continue;
+                const int rx = ry - abs(dy);
+                const int x0 = max(0, x - rx), x1 = min(W - 1, x + rx);
+                const uint16_t *row = vol + ((long long)zz * H + yy) * W;
+                for (int xx = x0; xx <= x1; ++xx) m = m || (__fsub_rn((float)row[xx], o) > t);
+            }
+        }
+        out[i] = m ? 1 : 0;
+    }
+}
+
 // ------------------------------------------------------------- histogram ----
 // K8: exact 65536-bin histogram of a uint16 tile.  Bins below HOT live in a
 // per-CTA shared-memory histogram (ExaSPIM background sits there), the rest go
@@ -347,12 +381,17 @@ __global__ void __launch_bounds__(512) k_hist(const uint16_t *__restrict__ in, l
     __shared__ unsigned int sh[HOT];
     for (int i = threadIdx.x; i < HOT; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
-    const long long nv = n >> 3;
     const long long stride = (long long)gridDim.x * blockDim.x;
     auto add = [&](uint32_t v) {
         if (v < HOT) atomicAdd(&sh[v], 1u);
         else atomicAdd(&hist[v], 1ull);
     };
+    // elements before the first 16-byte boundary (a patch inside a batch may start anywhere)
+    const long long head = min(n, (long long)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(in) & 15u)) & 15u) >> 1));
+    if (blockIdx.x == 0 && threadIdx.x < head) add(in[threadIdx.x]);
+    in += head;
+    n -= head;
+    const long long nv = n >> 3;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
         const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(in) + i);
         add(v.x & 0xFFFFu);
@@ -482,6 +521,10 @@ void b4d_launch_chunk_shuffle(const uint16_t *in, int D, int H, int W, int cz, i
                               uint32_t *hist, cudaStream_t s) {
     const long long nchunks = (long long)((D + cz - 1) / cz) * ((H + cy - 1) / cy) * ((W + cx - 1) / cx);
     k_chunk_shuffle<<<grid_for(nchunks * 256, 256, 8), 256, 0, s>>>(in, D, H, W, cz, cy, cx, out, hist);
+}
+void b4d_launch_fg_mask(const uint16_t *in, const float *off, const float *thr, int D, int H, int W, long long n,
+                        int dilate, uint8_t *out, cudaStream_t s) {
+    k_fg_mask<<<grid_for(n, 256, 8), 256, 0, s>>>(in, off, thr, D, H, W, n, dilate, out);
 }
 void b4d_launch_hist(const uint16_t *in, long long n, unsigned long long *hist, cudaStream_t s) {
     k_hist<<<grid_for(n >> 3, 512, 2), 512, 0, s>>>(in, n, hist);

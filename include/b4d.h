@@ -163,6 +163,19 @@ int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub
                      float offset_add, float step, uint16_t *out, int in_on_device,
                      int out_on_device);
 
+/* Intensity foreground mask of `n` equal-shape uint16 patches — make_foreground_mask
+ * (machine_learning/metrics.py:32-61), the mask both datasets fall back to when a patch has no
+ * annotation (data_handling.py:444, :928-929), on raw = float32(in) - offsets[i]
+ * (data_handling.py:353-354):
+ *     med = median(raw); mad = median(|raw - med|) + 1e-6; sigma = 1.4826 * mad      (float32)
+ *     mask = raw > med + k * sigma, then `dilate` iterations of 6-neighbour binary dilation
+ * `offsets` is a HOST array of n floats; `out` receives n * voxels bytes of 0 / 1.
+ * The medians are exact (65 536-bin histogram per patch); the result equals the reference's
+ * function bit for bit under NumPy 2 scalar rules (tests/golden/reference_masks.npz). */
+int b4d_foreground_mask_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t shape[3],
+                            const float *offsets, float k, int dilate, uint8_t *out,
+                            int in_on_device, int out_on_device);
+
 /* K9 — chunking + byte shuffle ahead of the chunk codec (first step).
  * The volume is cut the way compute_cratio does (utils/img_util.py:427-438): a C-order grid of
  * `chunk`-shaped pieces, ragged at the far faces, each piece made contiguous.  Each piece is then

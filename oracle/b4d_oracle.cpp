@@ -895,6 +895,51 @@ int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *,
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }
 void *b4d_stream(b4d_handle *) { return nullptr; }
+// restatement of make_foreground_mask (metrics.py:54-61) on raw = float32(u16) - offset
+// (data_handling.py:353-354): plain float32 arrays, medians by selection, dilation by repeated
+// 6-neighbour passes with border value 0 (scipy.ndimage.binary_dilation's default structure).
+static float median_f32(std::vector<float> v) {
+    const size_t n = v.size(), hi = n / 2;
+    std::nth_element(v.begin(), v.begin() + hi, v.end());
+    const float b = v[hi];
+    if (n & 1) return b;
+    const float a = *std::max_element(v.begin(), v.begin() + hi);
+    return (a + b) / 2.0f;  // np.mean of the two middle float32 values
+}
+int b4d_foreground_mask_u16(b4d_handle *, const uint16_t *in, int64_t n, const int64_t shape[3],
+                            const float *offsets, float k, int dilate, uint8_t *out, int, int) {
+    if (!in || !shape || !offsets || !out || n < 1 || dilate < 0) return fail(B4D_ERR_INVALID, "bad argument");
+    const int64_t D = shape[0], H = shape[1], W = shape[2], V = D * H * W;
+    std::vector<float> raw((size_t)V), dev((size_t)V);
+    std::vector<uint8_t> cur((size_t)V), nxt((size_t)V);
+    for (int64_t i = 0; i < n; ++i) {
+        for (int64_t v = 0; v < V; ++v) raw[v] = (float)in[i * V + v] - offsets[i];
+        const float med = median_f32(raw);
+        for (int64_t v = 0; v < V; ++v) dev[v] = std::fabs(raw[v] - med);
+        const float mad = median_f32(dev) + 1e-6f;
+        const float sigma = 1.4826f * mad;
+        const float thr = med + k * sigma;
+        for (int64_t v = 0; v < V; ++v) cur[v] = raw[v] > thr;
+        for (int it = 0; it < dilate; ++it) {
+            for (int64_t z = 0; z < D; ++z)
+                for (int64_t y = 0; y < H; ++y)
+                    for (int64_t x = 0; x < W; ++x) {
+                        const int64_t c = (z * H + y) * W + x;
+                        uint8_t m = cur[c];
+                        if (z > 0) m |= cur[c - H * W];
+                        if (z + 1 < D) m |= cur[c + H * W];
+                        if (y > 0) m |= cur[c - W];
+                        if (y + 1 < H) m |= cur[c + W];
+                        if (x > 0) m |= cur[c - 1];
+                        if (x + 1 < W) m |= cur[c + 1];
+                        nxt[c] = m;
+                    }
+            cur.swap(nxt);
+        }
+        std::memcpy(out + i * V, cur.data(), (size_t)V);
+    }
+    return 0;
+}
 int b4d_chunk_shuffle_u16(b4d_handle *, const uint16_t *in, const int64_t shape[3], const int64_t chunk[3],
                           uint8_t *out, uint32_t *hist, int, int) {
     // restatement of the chunk loop of compute_cratio (img_util.py:427-438) + Blosc SHUFFLE, typesize 2

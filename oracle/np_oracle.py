@@ -69,6 +69,27 @@ def quantize_truncating(x):
     return np.ascontiguousarray(np.maximum(x, 0).astype(int), dtype=np.uint16)
 
 
+def make_foreground_mask_reference(raw, k=6.0, dilate=1):
+    """Intensity foreground mask (metrics.py:54-61): median + k * (1.4826 * MAD) threshold in float32,
+    then `dilate` iterations of binary dilation with the 6-neighbour structuring element and border
+    value 0 (what scipy.ndimage.binary_dilation does by default), written with array shifts."""
+    raw = np.asarray(raw, dtype=np.float32)
+    med = np.median(raw)
+    mad = np.median(np.abs(raw - med)) + 1e-6
+    sigma = 1.4826 * mad
+    mask = raw > (med + k * sigma)
+    for _ in range(int(dilate)):
+        grown = mask.copy()
+        for ax in range(mask.ndim):
+            lo = [slice(None)] * mask.ndim
+            hi = [slice(None)] * mask.ndim
+            lo[ax], hi[ax] = slice(0, -1), slice(1, None)
+            grown[tuple(lo)] |= mask[tuple(hi)]
+            grown[tuple(hi)] |= mask[tuple(lo)]
+        mask = grown
+    return mask
+
+
 def chunk_shuffle_reference(img, patch_shape=(64, 64, 64)):
     """The chunk loop of compute_cratio (utils/img_util.py:427-438) with Blosc's byte shuffle for
     2-byte items applied to each piece instead of the codec call: returns (bytes of all pieces back

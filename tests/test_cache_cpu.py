@@ -19,6 +19,14 @@ def _oracle_targets(oracle_lib):
     return fn
 
 
+def _oracle_fg(oracle_lib):
+    def fn(raw_u16, offsets):
+        off = np.asarray(offsets, np.float32)
+        return np.stack([oracle_lib.make_foreground_mask_reference(oracle_lib.read_counts(r, o)) for r, o in zip(raw_u16, off)])
+
+    return fn
+
+
 def test_cache_layout_matches_reference_contract(tmp_path, oracle_lib):
     from b4d import cache, synth
 
@@ -55,18 +63,21 @@ def test_cache_resume_skips_finished_patches(tmp_path, oracle_lib):
             raise RuntimeError("interrupted")
         return base(raw_u16, offsets, sigma, max_count)
 
+    fgf = _oracle_fg(oracle_lib)
     with pytest.raises(RuntimeError):
-        cache.write_patch_cache(d, patches, 37.0, 24.0, targets_fn=flaky, batch=2, split="val")
+        cache.write_patch_cache(d, patches, 37.0, 24.0, targets_fn=flaky, fg_fn=fgf, batch=2, split="val")
     first = np.load(os.path.join(d, "teacher.npy"))[:2].copy()
     assert not os.path.exists(os.path.join(d, "transform.json"))  # stamped last: cache not loadable yet
     with pytest.raises(ValueError):
         cache.load_patch_cache(d)
-    n = cache.write_patch_cache(d, patches, 37.0, 24.0, targets_fn=base, batch=2, split="val")
+    n = cache.write_patch_cache(d, patches, 37.0, 24.0, targets_fn=base, fg_fn=fgf, batch=2, split="val")
     assert n == 2  # only the unfinished half
     raw, teacher, fgm, _ = cache.load_patch_cache(d)
-    assert np.array_equal(teacher[:2], first) and np.abs(teacher[2:]).sum() > 0 and fgm.sum() == 0
+    assert np.array_equal(teacher[:2], first) and np.abs(teacher[2:]).sum() > 0
+    # no annotation mask supplied: the reference's fallback, make_foreground_mask(raw) (data_handling.py:444)
+    assert np.array_equal(fgm.astype(bool), fgf(patches, np.full(4, 37.0, np.float32)))
     # a different configuration starts over
-    assert cache.write_patch_cache(d, patches, 37.0, 10.0, targets_fn=base, batch=4) == 4
+    assert cache.write_patch_cache(d, patches, 37.0, 10.0, targets_fn=base, fg_fn=fgf, batch=4) == 4
 
 
 def test_cache_rejects_bad_input(tmp_path):

@@ -280,6 +280,9 @@ def test_patch_cache_written_by_the_gpu_path(tmp_path, b4d_mod, oracle_lib):
     for i in (0, 2, 4):
         want = np.clip(o.denoise(oracle_lib.read_counts(patches[i], float(offs[i])), 24.0), 0, 65535)
         assert np.array_equal(teacher[i], want)
+        # no annotation mask supplied -> the reference's fallback make_foreground_mask(raw) (data_handling.py:444)
+        assert np.array_equal(fg[i].astype(bool),
+                              oracle_lib.make_foreground_mask_reference(oracle_lib.read_counts(patches[i], offs[i])))
     assert cache.write_patch_cache(d, patches, offs, 24.0, batch=3) == 0  # resume: nothing left
 
 
@@ -446,3 +449,27 @@ def test_cratio_of_shuffled_pieces_round_trips(dn, b4d_mod):
     r_den = b4d_mod.compute_cratio(den)
     assert r_noisy == round(r_noisy, 2) and r_den > r_noisy > 1.0
     assert b4d_mod.estimate_cratio(dn.chunk_shuffle(den, want_bytes=False)[1]) > b4d_mod.estimate_cratio(hist)
+
+
+def test_foreground_mask_matches_reference_golden(dn, b4d_mod, oracle_lib):
+    """make_foreground_mask on the device (exact histogram medians, float32 statistic on the host,
+    threshold + L1-ball dilation kernel) against the masks the live reference produced
+    (tests/golden/reference_masks.npz), and a mixed batch against the restatement."""
+    import os
+
+    from b4d import synth
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_masks.npz"))
+    for i in range(int(g["count"][0])):
+        ci, off, k, dil = g["par%d" % i]
+        u = g["u%d" % int(ci)]
+        want = np.unpackbits(g["m%d" % i])[: u.size].astype(bool).reshape(u.shape)
+        got = dn.foreground_mask(u, float(off), float(k), int(dil))
+        assert got.dtype == np.bool_ and np.array_equal(got, want), (i, off, k, dil)
+    batch = np.stack([synth.vol(15, 17, 19, seed=s) for s in range(40)])  # odd voxel count: unaligned patches
+    batch[3, 4:9, 5:9, 6:12] += 3000
+    offs = np.linspace(0.0, 40.0, 40).astype(np.float32)
+    got = b4d_mod.make_foreground_mask(batch, offs)
+    for i in (0, 3, 17, 39):
+        assert np.array_equal(got[i], oracle_lib.make_foreground_mask_reference(oracle_lib.read_counts(batch[i], offs[i])))
+    assert got[3].any()

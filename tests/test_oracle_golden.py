@@ -61,6 +61,36 @@ def test_mad_sigma_matches_reference_mask(gold, oracle_lib):
             assert np.array_equal(got, want)
 
 
+def _mask_cases():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_masks.npz"))
+    for i in range(int(g["count"][0])):
+        ci, off, k, dil = g["par%d" % i]
+        u = g["u%d" % int(ci)]
+        want = np.unpackbits(g["m%d" % i])[: u.size].astype(bool).reshape(u.shape)
+        yield u, float(off), float(k), int(dil), want
+
+
+def test_foreground_mask_restatements_match_the_reference(oracle_lib):
+    """make_foreground_mask (metrics.py:32-61) run live by tests/golden/make_golden_masks.py on
+    raw = uint16 - offset: the NumPy restatement (shift-based dilation) and the C++ one behind the
+    oracle's C ABI (selection medians, 6-neighbour passes) both reproduce its masks exactly."""
+    import ctypes
+
+    lib = oracle_lib.load()
+    n = 0
+    for u, off, k, dil, want in _mask_cases():
+        raw = oracle_lib.read_counts(u, np.float32(off))
+        assert np.array_equal(oracle_lib.make_foreground_mask_reference(raw, k, dil), want)
+        out = np.empty(u.shape, np.uint8)
+        offs = np.array([off], np.float32)
+        rc = lib.b4d_foreground_mask_u16(None, ctypes.c_void_p(u.ctypes.data), ctypes.c_int64(1),
+                                         (ctypes.c_int64 * 3)(*u.shape), ctypes.c_void_p(offs.ctypes.data),
+                                         ctypes.c_float(k), ctypes.c_int(dil), ctypes.c_void_p(out.ctypes.data), 0, 0)
+        assert rc == 0 and np.array_equal(out.astype(bool), want)
+        n += 1
+    assert n == 45
+
+
 def test_truncating_variant(oracle_lib):
     x = np.array([-3.2, 0.0, 0.9, 1.5, 2.5, 65535.9], dtype=np.float32)
     assert oracle_lib.quantize_truncating(x).tolist() == [0, 0, 0, 1, 2, 65535]
