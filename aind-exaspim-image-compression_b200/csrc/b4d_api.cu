@@ -34,7 +34,7 @@ int fail(int code, const std::string &msg) {
     } while (0)
 
 constexpr int L = 4;
-constexpr long long CHUNK_VOXELS = 1342177280ll;  // 1.25 Gi voxels of scratch per pass
+constexpr long long CHUNK_VOXELS = 1342177280ll;  // default: 1.25 Gi voxels per pass (about 45 B of scratch each)
 
 struct DevBuf {
     void *p = nullptr;
@@ -75,6 +75,7 @@ struct b4d_handle {
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
     unsigned long long match_stats[4];
+    long long pass_voxels = CHUNK_VOXELS;  // voxels per pass (b4d_set_pass_voxels)
     HostMover mover;  // pageable host arrays <-> device (pinned ring + copy threads)
     // state between b4d_slab_stage1_u16 and b4d_slab_stage2
     bool slab_open = false;
@@ -599,7 +600,7 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
     if (n < 1) return fail(B4D_ERR_INVALID, "n must be >= 1");
     reset_timings(h);
     const long long V = shape[0] * shape[1] * shape[2];
-    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, CHUNK_VOXELS / V));
+    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, h->pass_voxels / V));
     cudaStream_t s = h->stream;
     Plan pl;
     pl.D = (int)shape[0];
@@ -729,8 +730,53 @@ int64_t b4d_num_refs(const int64_t shape[3]) {
            (int64_t)ref_origins(shape[2]).size();
 }
 
+int b4d_set_pass_voxels(b4d_handle *h, int64_t voxels) {
+    if (!h || voxels < 0) return fail(B4D_ERR_INVALID, "bad argument");
+    h->pass_voxels = voxels == 0 ? CHUNK_VOXELS : std::max<long long>(voxels, 4096);
+    return 0;
+}
+
+// One uint16 volume larger than a pass: z-slabs with the no-exchange halo, one after the other on this
+// GPU (b4d_denoise_slab_u16); equal to the one-pass result bit for bit, like the multi-GPU slabs.
+static int denoise_oversize_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], float sigma, float *out,
+                                int in_on_device, int out_on_device) {
+    const int64_t D = shape[0], P = shape[1] * shape[2];
+    const int64_t halo = (h->prof.search_ht + 2) + (h->prof.stages == 2 ? h->prof.search_wie + 2 : 0);
+    const int64_t planes = h->pass_voxels / P;
+    if (planes < 2 * halo + 4)
+        return fail(B4D_ERR_TOO_LARGE, "a pass cannot hold two halos of this plane size: raise b4d_set_pass_voxels "
+                                       "or shard the volume in y / x");
+    const int64_t nslab = (D + (planes - 2 * halo) - 1) / (planes - 2 * halo);
+    const int64_t own = (D + nslab - 1) / nslab;
+    float t_ms[B4D_T_COUNT] = {};
+    int64_t launches[B4D_T_COUNT] = {};
+    unsigned long long stats[4] = {};
+    for (int64_t ob = 0; ob < D; ob += own) {
+        const int64_t oe = std::min(D, ob + own), zb = std::max<int64_t>(0, ob - halo), ze = std::min(D, oe + halo);
+        const int64_t sshape[3] = {ze - zb, shape[1], shape[2]};
+        B4D_TRY(b4d_denoise_slab_u16(h, in + zb * P, sshape, zb, D, ob, oe, sigma, out + ob * P, in_on_device,
+                                     out_on_device));
+        for (int i = 0; i < B4D_T_COUNT; ++i) {
+            t_ms[i] += h->t_ms[i];
+            launches[i] += h->launches[i];
+        }
+        for (int i = 0; i < 4; ++i) stats[i] += h->match_stats[i];
+    }
+    for (int i = 0; i < B4D_T_COUNT; ++i) {
+        h->t_ms[i] = t_ms[i];
+        h->launches[i] = launches[i];
+    }
+    for (int i = 0; i < 4; ++i) h->match_stats[i] = stats[i];
+    return 0;
+}
+
 int b4d_denoise_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t shape[3], float sigma, float *out,
                     int in_on_device, int out_on_device) {
+    if (h && in && out && shape && n == 1 && shape[0] > 0 && shape[1] > 0 && shape[2] > 0 &&
+        shape[0] * shape[1] * shape[2] > h->pass_voxels) {
+        B4D_TRY(common_checks(h, in, out, shape, sigma));
+        return denoise_oversize_u16(h, in, shape, sigma, out, in_on_device, out_on_device);
+    }
     return denoise_batch<uint16_t>(h, in, n, shape, sigma, out, in_on_device, out_on_device);
 }
 int b4d_denoise_f32(b4d_handle *h, const float *in, int64_t n, const int64_t shape[3], float sigma, float *out,
@@ -746,7 +792,7 @@ int b4d_targets_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t 
     if (h->prof.stages != 2) return fail(B4D_ERR_INVALID, "target generation needs stages = 2");
     reset_timings(h);
     const long long V = shape[0] * shape[1] * shape[2];
-    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, CHUNK_VOXELS / V));
+    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, h->pass_voxels / V));
     cudaStream_t s = h->stream;
     Plan pl;
     pl.D = (int)shape[0];
@@ -1159,7 +1205,7 @@ int b4d_foreground_mask_u16(b4d_handle *h, const uint16_t *in, int64_t n, const 
     CU_TRY(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     constexpr int G = 32;  // patches per histogram round trip
-    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, CHUNK_VOXELS / V));
+    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, h->pass_voxels / V));
     std::vector<unsigned long long> hist((size_t)G * 65536);
     for (int64_t i0 = 0; i0 < n; i0 += per) {
         const int64_t nb = std::min<int64_t>(per, n - i0);

@@ -108,6 +108,13 @@ int b4d_denoise_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t 
 int b4d_denoise_f32(b4d_handle *h, const float *in, int64_t n, const int64_t shape[3],
                     float sigma, float *out, int in_on_device, int out_on_device);
 
+/* Voxels the handle processes per pass (default 1.25 Gi; scratch is about 45 bytes per voxel, so
+ * the default needs ~60 GB of the 180 GB).  Batches are cut into passes of whole patches; ONE uint16
+ * volume larger than a pass is denoised as consecutive z-slabs with halos on the same GPU
+ * (b4d_denoise_u16 does this itself; the result equals the one-pass result bit for bit).
+ * 0 restores the default. */
+int b4d_set_pass_voxels(b4d_handle *h, int64_t voxels);
+
 /* Training targets for `n` equal-shape uint16 patches in one call — the core of
  * `_sample_counts` (data_handling.py:315-354) batched:
  *     raw     = float32(in) - offsets[i]                 data_handling.py:353-354

@@ -473,3 +473,25 @@ def test_foreground_mask_matches_reference_golden(dn, b4d_mod, oracle_lib):
     for i in (0, 3, 17, 39):
         assert np.array_equal(got[i], oracle_lib.make_foreground_mask_reference(oracle_lib.read_counts(batch[i], offs[i])))
     assert got[3].any()
+
+
+def test_volume_larger_than_a_pass_is_slabbed_on_one_gpu(b4d_mod):
+    """A uint16 volume that exceeds the per-pass scratch budget is denoised as consecutive z-slabs with
+    halos on the same GPU (b4d_set_pass_voxels): same bytes as the one-pass result, timings summed."""
+    from b4d import synth
+
+    vol = synth.vol(100, 24, 28, seed=21)
+    d = b4d_mod.Denoiser(0)
+    whole = d.denoise(vol, 24.0)
+    one = sum(v[1] for v in d.last_timings().values())
+    d.set_pass_voxels(60 * 24 * 28)  # 60 planes per pass, 52 of them halo: 13 slabs of 8 planes
+    assert np.array_equal(d.denoise(vol, 24.0), whole)
+    assert sum(v[1] for v in d.last_timings().values()) > 5 * one
+    d.set_pass_voxels(80 * 24 * 28)
+    assert np.array_equal(d.denoise(vol, 24.0), whole)
+    d.set_pass_voxels(40 * 24 * 28)  # two halos do not fit
+    with pytest.raises(ValueError):
+        d.denoise(vol, 24.0)
+    d.set_pass_voxels(0)
+    assert np.array_equal(d.denoise(vol, 24.0), whole)
+    d.close()
