@@ -25,6 +25,7 @@ EXPORTS = (
     "b4d_denoise_f32",
     "b4d_targets_u16",
     "b4d_set_pass_voxels",
+    "b4d_set_pipeline_min_voxels",
     "b4d_chunk_shuffle_u16",
     "b4d_foreground_mask_u16",
     "b4d_denoise_slab_u16",

@@ -402,6 +402,10 @@ class Denoiser:
         pass is denoised as consecutive z-slabs with halos; the result does not change."""
         _lib.check(self.lib.b4d_set_pass_voxels(self._h, ctypes.c_int64(int(voxels))))
 
+    def set_pipeline_min_voxels(self, voxels):
+        """Volume size from which host transfers are pipelined against the kernels (default 2^26)."""
+        _lib.check(self.lib.b4d_set_pipeline_min_voxels(self._h, ctypes.c_int64(int(voxels))))
+
     def foreground_mask(self, raw_u16, offsets=0.0, k=6.0, dilate=1):
         """make_foreground_mask (metrics.py:32-61) of uint16 patches after the offset subtraction
         (data_handling.py:353-354): (D,H,W) or (N,D,H,W) uint16 -> bool mask of the same shape."""

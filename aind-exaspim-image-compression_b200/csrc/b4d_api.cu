@@ -76,6 +76,7 @@ struct b4d_handle {
     int64_t launches[B4D_T_COUNT];
     unsigned long long match_stats[4];
     long long pass_voxels = CHUNK_VOXELS;  // voxels per pass (b4d_set_pass_voxels)
+    long long pipeline_min_voxels = 1ll << 26;  // host transfers are pipelined from this volume size up
     HostMover mover;  // pageable host arrays <-> device (pinned ring + copy threads)
     // state between b4d_slab_stage1_u16 and b4d_slab_stage2
     bool slab_open = false;
@@ -290,8 +291,11 @@ struct HostSource {
     int ishift = 0;          // centre shift of the stage-2 matching image (from the data range)
 };
 constexpr int UPLOAD_CHUNKS = 8;
-bool can_stream_upload(const Plan &pl) {
-    return pl.nvol == 1 && ((long long)pl.H * pl.W) % 8 == 0 && pl.D >= 16 * UPLOAD_CHUNKS;
+// Chunked launches under-fill the GPU on small volumes (a 128^3 patch ran 1.5x slower in 8 chunks and its
+// whole upload takes 0.1 ms), so the transfers are pipelined only from `pipeline_min_voxels` up.
+bool can_stream_upload(const b4d_handle *h, const Plan &pl) {
+    return pl.nvol == 1 && ((long long)pl.H * pl.W) % 8 == 0 && pl.D >= 16 * UPLOAD_CHUNKS &&
+           (long long)pl.D * pl.H * pl.W >= h->pipeline_min_voxels;
 }
 
 // phase 0 = both stages; 1 = stage 1 only (basic estimate left in h->basic); 2 = stage 2 only
@@ -364,7 +368,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     if (phase != 2) {
     // ---- stage 1: hard thresholding
     B4D_TRY(zero_acc());
-    const bool streamed = src && src->host && can_stream_upload(pl) && R1 > 0;
+    const bool streamed = src && src->host && can_stream_upload(h, pl) && R1 > 0;
     if (!streamed) b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 2);
     mp.g = g1;
@@ -472,7 +476,9 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.Ns = p.search_wie;
     const long long P = (long long)pl.H * pl.W;
     constexpr int NCH = 8;
-    const int nseg_ch = (sink && sink->host && pl.nvol == 1 && R2 > 0 && (P & 3) == 0) ? b4d_filter_segments(fp, NCH) : 0;
+    const int nseg_ch = (sink && sink->host && pl.nvol == 1 && R2 > 0 && (P & 3) == 0 && TV >= h->pipeline_min_voxels)
+                            ? b4d_filter_segments(fp, NCH)
+                            : 0;
     if (nseg_ch >= NCH && nseg_ch % NCH == 0) {
         // chunked: launch everything on the compute stream first (events between the chunks), then
         // queue normalise + copy of the planes each chunk finishes on the copy stream
@@ -618,7 +624,7 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
         B4D_TRY(h->in.ensure((size_t)TV * sizeof(T)));
         HostSource src;
         // one uint16 volume from host memory: uploaded in chunks behind the stage-1 matcher
-        const bool stream_in = sizeof(T) == 2 && !in_dev && nb == 1 && can_stream_upload(pl);
+        const bool stream_in = sizeof(T) == 2 && !in_dev && nb == 1 && can_stream_upload(h, pl);
         if (stream_in) src.host = reinterpret_cast<const uint16_t *>(in + i0 * V);
         else
             CU_TRY(copy_in(h, h->in.p, in + i0 * V, (size_t)TV * sizeof(T), in_dev, s));
@@ -728,6 +734,12 @@ int64_t b4d_num_refs(const int64_t shape[3]) {
     if (!shape || check_shape(shape)) return -1;
     return (int64_t)ref_origins(shape[0]).size() * (int64_t)ref_origins(shape[1]).size() *
            (int64_t)ref_origins(shape[2]).size();
+}
+
+int b4d_set_pipeline_min_voxels(b4d_handle *h, int64_t voxels) {
+    if (!h || voxels < 0) return fail(B4D_ERR_INVALID, "bad argument");
+    h->pipeline_min_voxels = voxels;
+    return 0;
 }
 
 int b4d_set_pass_voxels(b4d_handle *h, int64_t voxels) {
@@ -880,7 +892,7 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
     StageClock clk(h);
     MatchMap mm;
     HostSource src;
-    if (!in_on_device && can_stream_upload(pl) && !pl.rz1.empty()) {
+    if (!in_on_device && can_stream_upload(h, pl) && !pl.rz1.empty()) {
         src.host = in;  // uploaded in chunks behind the stage-1 matcher (run_pipeline)
         clk.mark(-1, 0);
     } else {
@@ -940,7 +952,7 @@ int b4d_slab_stage1_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3
     StageClock clk(h);
     MatchMap mm;
     HostSource src;
-    if (!in_on_device && can_stream_upload(pl) && !pl.rz1.empty()) {
+    if (!in_on_device && can_stream_upload(h, pl) && !pl.rz1.empty()) {
         src.host = in;  // uploaded in chunks behind the stage-1 matcher (run_pipeline)
         clk.mark(-1, 0);
     } else {

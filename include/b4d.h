@@ -115,6 +115,12 @@ int b4d_denoise_f32(b4d_handle *h, const float *in, int64_t n, const int64_t sha
  * 0 restores the default. */
 int b4d_set_pass_voxels(b4d_handle *h, int64_t voxels);
 
+/* Volume size (voxels) from which the host transfers of one volume or slab are pipelined against
+ * the kernels (chunked upload behind the stage-1 matcher, chunked stage 2 with copy-out of the
+ * finished planes).  Default 2^26: below it the chunked launches under-fill the GPU and the
+ * transfers are negligible.  The result never depends on it. */
+int b4d_set_pipeline_min_voxels(b4d_handle *h, int64_t voxels);
+
 /* Training targets for `n` equal-shape uint16 patches in one call — the core of
  * `_sample_counts` (data_handling.py:315-354) batched:
  *     raw     = float32(in) - offsets[i]                 data_handling.py:353-354

@@ -895,7 +895,8 @@ int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *,
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }
 void *b4d_stream(b4d_handle *) { return nullptr; }
-int b4d_set_pass_voxels(b4d_handle *, int64_t) { return 0; }  // the CPU restatement has no passes
+int b4d_set_pass_voxels(b4d_handle *, int64_t) { return 0; }
+int b4d_set_pipeline_min_voxels(b4d_handle *, int64_t) { return 0; }  // the CPU restatement has no passes
 // restatement of make_foreground_mask (metrics.py:54-61) on raw = float32(u16) - offset
 // (data_handling.py:353-354): plain float32 arrays, medians by selection, dilation by repeated
 // 6-neighbour passes with border value 0 (scipy.ndimage.binary_dilation's default structure).

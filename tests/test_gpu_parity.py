@@ -370,6 +370,7 @@ def test_pipelined_host_transfers_equal_device_result(b4d_mod):
 
     vol = synth.vol(208, 16, 20, seed=12)  # 69 reference planes: enough for 8 chunks
     d = b4d_mod.Denoiser(0)
+    d.set_pipeline_min_voxels(0)  # pipelined at any size (default: only from 2^26 voxels up)
     dev = d.denoise(torch.from_numpy(vol).cuda(), 24.0).cpu().numpy()  # device in/out: unchunked
     assert np.array_equal(d.denoise(vol, 24.0), dev)                   # host in/out: chunked
     part = d.denoise_slab(vol[30:208], 30, 208, 60, 200, 24.0)         # slab, host out
@@ -399,9 +400,11 @@ def test_pageable_and_pinned_host_arrays_give_the_same_bytes(dn, b4d_mod, oracle
     st = dn.tile_stats(want)
     assert st["n"] == want.size and st["vmax"] == float(want.max())
     vol = synth.vol(208, 40, 52, seed=5)
+    dn.set_pipeline_min_voxels(0)
     a = dn.denoise(vol, 24.0)                                                      # pageable, chunked pipeline
     b = dn.denoise(torch.from_numpy(vol).pin_memory(), 24.0).numpy()               # pinned, chunked pipeline
-    assert np.array_equal(a, b)
+    dn.set_pipeline_min_voxels(1 << 26)
+    assert np.array_equal(a, b) and np.array_equal(a, dn.denoise(vol, 24.0))       # == the unchunked path
 
 
 @pytest.mark.parametrize(
