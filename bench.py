@@ -155,6 +155,14 @@ def workload_config(S, halo, exchange=False):
     }
 
 
+def xform_roofline(mac_per_voxel, voxels, ms, peaks):
+    if not ms or not peaks.get("ffma"):
+        return None
+    ach = mac_per_voxel * voxels / (ms * 1e-3)
+    return {"bound": "fp32", "achieved": ach / 1e12, "peak": peaks["ffma"] / 1e12, "unit": "TMAC/s",
+            "frac": ach / peaks["ffma"], "ms_per_launch": ms}
+
+
 def traffic_per_launch(size, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_match launch, from the committed
     `ncu --set full` capture of this workload (profiles/traffic.json), or None."""
@@ -421,6 +429,11 @@ def main():
                               "bytes_only_ms": cb_ms, "bytes_only_frac": 4.0 * q_vox / (cb_ms * 1e-3) / 1e9 / hbm_peak},
             "filter_ht_ms": fam.get("filter1", 0.0) / args.steps,
             "filter_wiener_ms": fam.get("filter2", 0.0) / args.steps,
+            # dense-matrix MAC count of the transforms, K (2*768 + 4*64) / 27 per voxel (hard threshold)
+            # and K (3*768 + 6*64) / 27 (Wiener), against the measured FFMA issue rate.  The Haar stage needs no
+            # multiplies and the kernels are bound by shuffles / shared-memory reductions, so this is a low bar.
+            "filter_ht": xform_roofline(K_HT * (2 * 768 + 4 * 64) / 27.0, slab_vox, fam.get("filter1", 0.0) / args.steps, peaks),
+            "filter_wiener": xform_roofline(K_WIE * (3 * 768 + 6 * 64) / 27.0, slab_vox, fam.get("filter2", 0.0) / args.steps, peaks),
         }
         line = {
             "metric": "bm4d_denoise_voxels_per_s",
