@@ -71,6 +71,7 @@ struct b4d_handle {
     cudaStream_t copy_stream = nullptr;  // normalise + device-to-host of finished planes, overlapped with stage 2
     b4d_profile prof;
     DevBuf in, u16, zf, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2, cells, tcls;
+    DevBuf alt_in, alt_zf, alt_out, alt_partial, alt_sink;  // second buffer set of b4d_targets_u16
     cudaEvent_t ev[B4D_T_COUNT + 1];
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
@@ -237,6 +238,22 @@ void fill_geom(const Plan &pl, const std::vector<int> &rz, const int *d_refs, B4
     g->refs_per_vol = (long long)g->nrz * g->nry * g->nrx;
 }
 
+// Ordering events owned for the duration of one call: destroyed on every exit path.
+struct EventSet {
+    std::vector<cudaEvent_t> evs;
+    EventSet() = default;
+    EventSet(const EventSet &) = delete;
+    EventSet &operator=(const EventSet &) = delete;
+    ~EventSet() {
+        for (auto e : evs) cudaEventDestroy(e);
+    }
+    cudaError_t make(cudaEvent_t *out) {
+        const cudaError_t e = cudaEventCreateWithFlags(out, cudaEventDisableTiming);
+        if (e == cudaSuccess) evs.push_back(*out);
+        return e;
+    }
+};
+
 // One stage boundary timing: we record an event after each kernel family and
 // resolve all of them after the final synchronise.
 struct StageClock {
@@ -244,6 +261,11 @@ struct StageClock {
     std::vector<cudaEvent_t> evs;
     std::vector<std::pair<int, int>> tags;  // (slot, launches) for interval i -> i+1
     explicit StageClock(b4d_handle *hh) : h(hh) {}
+    StageClock(const StageClock &) = delete;
+    StageClock &operator=(const StageClock &) = delete;
+    ~StageClock() {  // an error return before resolve()
+        for (auto e : evs) cudaEventDestroy(e);
+    }
     void mark(int slot, int launches) {
         cudaEvent_t e;
         cudaEventCreate(&e);
@@ -388,6 +410,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         B4D_TRY(h->sink.ensure(64));
         const unsigned init[2] = {0xFFFFu, 0u};
         CU_TRY(cudaMemcpyAsync(h->sink.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+        EventSet owned;
         cudaEvent_t evs[UPLOAD_CHUNKS];
         int zprev = 0, odone = 0, cdone = 0, tdone = 0;
         for (int k = 0; k < UPLOAD_CHUNKS; ++k) {
@@ -395,7 +418,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
             zu = std::min(zu, pl.D);
             CU_TRY(copy_in(h, d_u + zprev * P, src->host + zprev * P, (size_t)(zu - zprev) * P * sizeof(uint16_t), 0,
                            h->copy_stream));
-            CU_TRY(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+            CU_TRY(owned.make(&evs[k]));
             CU_TRY(cudaEventRecord(evs[k], h->copy_stream));
             CU_TRY(cudaStreamWaitEvent(s, evs[k], 0));
             // planes [0, zu) are on the device: everything that needs no plane beyond zu - 1
@@ -416,7 +439,6 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         unsigned got[2] = {0, 0};
         CU_TRY(cudaMemcpyAsync(got, h->sink.p, sizeof(got), cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaStreamSynchronize(s));
-        for (int k = 0; k < UPLOAD_CHUNKS; ++k) cudaEventDestroy(evs[k]);
         mm.ishift = centre_shift((double)got[0], (double)got[1]);
         src->ishift = mm.ishift;
         src->used = true;
@@ -483,10 +505,11 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         // chunked: launch everything on the compute stream first (events between the chunks), then
         // queue normalise + copy of the planes each chunk finishes on the copy stream
         const int spc = nseg_ch / NCH, r2 = p.search_wie / 2;
+        EventSet owned;
         cudaEvent_t evs[NCH];
         for (int c = 0; c < NCH; ++c) {
             b4d_launch_filter_segments(fp, true, nseg_ch, c * spc, spc, s);
-            CU_TRY(cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming));
+            CU_TRY(owned.make(&evs[c]));
             CU_TRY(cudaEventRecord(evs[c], s));
         }
         clk.mark(B4D_T_FILTER2, NCH);
@@ -511,7 +534,6 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
             }
         }
         CU_TRY(cudaStreamSynchronize(h->copy_stream));
-        for (int c = 0; c < NCH; ++c) cudaEventDestroy(evs[c]);
         clk.mark(B4D_T_NORM2, NCH);
         sink->done = true;
         CU_TRY(cudaGetLastError());
@@ -715,7 +737,8 @@ void b4d_destroy(b4d_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->numq, &h->denq, &h->basic, &h->out, &h->widx, &h->cnt,
-                      &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2, &h->cells, &h->tcls})
+                      &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2, &h->cells, &h->tcls,
+                      &h->alt_in, &h->alt_zf, &h->alt_out, &h->alt_partial, &h->alt_sink})
         b->release();
     for (auto &ev : h->ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -804,8 +827,11 @@ int b4d_targets_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t 
     if (h->prof.stages != 2) return fail(B4D_ERR_INVALID, "target generation needs stages = 2");
     reset_timings(h);
     const long long V = shape[0] * shape[1] * shape[2];
-    const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, h->pass_voxels / V));
-    cudaStream_t s = h->stream;
+    int64_t per = std::max<int64_t>(1, std::min<int64_t>(n, h->pass_voxels / V));
+    // With host buffers a pass is cut into four chunks on two buffer sets: while chunk c computes, the
+    // teacher of chunk c - 1 and the raw of chunk c go back and chunk c + 1 comes up on the copy stream.
+    if ((!in_on_device || !out_on_device) && per >= 8 && V * per >= h->pipeline_min_voxels) per = (per + 3) / 4;
+    cudaStream_t s = h->stream, cs = h->copy_stream;
     Plan pl;
     pl.D = (int)shape[0];
     pl.H = (int)shape[1];
@@ -814,25 +840,41 @@ int b4d_targets_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t 
     pl.ry = ref_origins(shape[1]);
     pl.rx = ref_origins(shape[2]);
     StageClock clk(h);
-    for (int64_t i0 = 0; i0 < n; i0 += per) {
+    EventSet owned;
+    DevBuf *b_in[2] = {&h->in, &h->alt_in}, *b_zf[2] = {&h->zf, &h->alt_zf}, *b_out[2] = {&h->out, &h->alt_out};
+    DevBuf *b_par[2] = {&h->partial, &h->alt_partial}, *b_sink[2] = {&h->sink, &h->alt_sink};
+    int64_t prev_i0 = -1, prev_nb = 0;
+    int prev_set = 0;
+    cudaEvent_t prev_done = nullptr;
+    auto teacher_back = [&]() -> int {  // teacher of the previous chunk, once its clip has run
+        if (prev_i0 < 0) return 0;
+        CU_TRY(cudaStreamWaitEvent(cs, prev_done, 0));
+        CU_TRY(copy_out(h, teacher_out + prev_i0 * V, b_out[prev_set]->p, (size_t)(V * prev_nb) * sizeof(float),
+                        out_on_device, cs));
+        return 0;
+    };
+    int64_t c = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += per, ++c) {
+        const int set = (int)(c & 1);
         const int64_t nb = std::min<int64_t>(per, n - i0);
         const long long TV = V * nb;
         pl.nvol = (int)nb;
-        B4D_TRY(h->in.ensure((size_t)TV * sizeof(uint16_t)));
-        B4D_TRY(h->zf.ensure((size_t)TV * sizeof(float)));
-        B4D_TRY(h->out.ensure((size_t)TV * sizeof(float)));
-        B4D_TRY(h->partial.ensure((size_t)nb * sizeof(float)));
-        B4D_TRY(h->sink.ensure(64));
-        CU_TRY(copy_in(h, h->in.p, in + i0 * V, (size_t)TV * sizeof(uint16_t), in_on_device, s));
-        CU_TRY(cudaMemcpyAsync(h->partial.p, offsets + i0, (size_t)nb * sizeof(float), cudaMemcpyHostToDevice, s));
+        B4D_TRY(b_in[set]->ensure((size_t)TV * sizeof(uint16_t)));
+        B4D_TRY(b_zf[set]->ensure((size_t)TV * sizeof(float)));
+        B4D_TRY(b_out[set]->ensure((size_t)TV * sizeof(float)));
+        B4D_TRY(b_par[set]->ensure((size_t)nb * sizeof(float)));
+        B4D_TRY(b_sink[set]->ensure(64));
+        // copy stream: counts up, raw = float32(counts) - offset, range of the counts.  In stream order this
+        // follows the copy-out of chunk c - 2, the last reader of this buffer set.
+        CU_TRY(copy_in(h, b_in[set]->p, in + i0 * V, (size_t)TV * sizeof(uint16_t), in_on_device, cs));
+        CU_TRY(cudaMemcpyAsync(b_par[set]->p, offsets + i0, (size_t)nb * sizeof(float), cudaMemcpyHostToDevice, cs));
         const unsigned init[2] = {0xFFFFu, 0u};
-        CU_TRY(cudaMemcpyAsync(h->sink.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
-        clk.mark(-1, 0);
-        b4d_launch_u16_sub_offset(h->in.as<uint16_t>(), h->partial.as<float>(), h->zf.as<float>(), V, TV,
-                                  h->sink.as<unsigned>(), s);
+        CU_TRY(cudaMemcpyAsync(b_sink[set]->p, init, sizeof(init), cudaMemcpyHostToDevice, cs));
+        b4d_launch_u16_sub_offset(b_in[set]->as<uint16_t>(), b_par[set]->as<float>(), b_zf[set]->as<float>(), V, TV,
+                                  b_sink[set]->as<unsigned>(), cs);
         unsigned got[2] = {0, 0};
-        CU_TRY(cudaMemcpyAsync(got, h->sink.p, sizeof(got), cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaStreamSynchronize(s));
+        CU_TRY(cudaMemcpyAsync(got, b_sink[set]->p, sizeof(got), cudaMemcpyDeviceToHost, cs));
+        CU_TRY(cudaStreamSynchronize(cs));
         float omin = offsets[i0], omax = offsets[i0];
         for (int64_t k = 0; k < nb; ++k) {
             omin = std::min(omin, offsets[i0 + k]);
@@ -846,22 +888,28 @@ int b4d_targets_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t 
         mm.scale = 1.0f;
         mm.cf = 0.0f;
         mm.ishift = centre_shift((double)got[0] - std::ceil((double)omax), (double)got[1] - std::floor((double)omin));
-        clk.mark(B4D_T_PREP, 1);
-        cudaEvent_t ev_raw;
-        CU_TRY(cudaEventCreateWithFlags(&ev_raw, cudaEventDisableTiming));
-        CU_TRY(cudaEventRecord(ev_raw, s));
-        B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk));
-        b4d_launch_clip(h->out.as<float>(), TV, max_count, s);
-        // the whole chunk is queued: raw goes back on the copy stream while the matcher and the filters run
-        CU_TRY(cudaStreamWaitEvent(h->copy_stream, ev_raw, 0));
+        // compute stream: the chunk's two stages and the clip (its inputs are complete: the copy stream was
+        // synchronised above)
+        clk.mark(-1, 0);
+        B4D_TRY(run_pipeline(h, pl, b_zf[set]->as<float>(), b_in[set]->as<uint16_t>(), mm, sigma,
+                             b_out[set]->as<float>(), clk));
+        b4d_launch_clip(b_out[set]->as<float>(), TV, max_count, s);
+        cudaEvent_t done;
+        CU_TRY(owned.make(&done));
+        CU_TRY(cudaEventRecord(done, s));
+        // copy stream again, while this chunk computes: teacher of the previous chunk, raw of this one
+        B4D_TRY(teacher_back());
         if (raw_out)
-            CU_TRY(copy_out(h, raw_out + i0 * V, h->zf.p, (size_t)TV * sizeof(float), out_on_device, h->copy_stream));
-        CU_TRY(copy_out(h, teacher_out + i0 * V, h->out.p, (size_t)TV * sizeof(float), out_on_device, s));
-        CU_TRY(cudaStreamSynchronize(h->copy_stream));
-        CU_TRY(cudaStreamSynchronize(s));
-        cudaEventDestroy(ev_raw);
-        clk.resolve();
+            CU_TRY(copy_out(h, raw_out + i0 * V, b_zf[set]->p, (size_t)TV * sizeof(float), out_on_device, cs));
+        prev_i0 = i0;
+        prev_nb = nb;
+        prev_set = set;
+        prev_done = done;
     }
+    B4D_TRY(teacher_back());
+    CU_TRY(cudaStreamSynchronize(cs));
+    CU_TRY(cudaStreamSynchronize(s));
+    clk.resolve();
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -163,6 +163,15 @@ def test_batch_equals_per_patch_and_precompute_targets(b4d_mod, oracle_lib):
         assert np.array_equal(raw[i], ri)
         assert np.array_equal(teacher[i], np.clip(o.denoise(ri, 24.0), 0, 65535))
         assert np.array_equal(teacher[i], np.clip(b4d_mod.bm4d(ri, 24.0), 0, 65535))
+    # four chunks on two buffer sets (host transfers pipelined against the kernels): same bytes
+    big = np.concatenate([batch] * 4)[:11]
+    boffs = np.resize(np.asarray(offs, np.float32), 11)
+    h = b4d_mod.get_denoiser()
+    h.set_pipeline_min_voxels(0)
+    praw, pteach = b4d_mod.precompute_targets(big, boffs, 24.0)
+    h.set_pipeline_min_voxels(1 << 26)
+    for i in range(11):
+        assert np.array_equal(praw[i], raw[i % 3]) and np.array_equal(pteach[i], teacher[i % 3])
     _, low = b4d_mod.precompute_targets(batch[:1], 37.0, 24.0, max_count=150.0)
     assert low.max() <= 150.0 and np.array_equal(low[0], np.minimum(teacher[0], 150.0))
 
