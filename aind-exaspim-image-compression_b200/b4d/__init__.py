@@ -20,6 +20,7 @@ from .api import (  # noqa: F401
 from .cache import load_patch_cache, write_patch_cache  # noqa: F401
 from .codec import chunk_grid, chunk_shuffle, compute_cratio, entropy_bytes, estimate_cratio  # noqa: F401
 from .sharding import (  # noqa: F401
+    bind_to_gpu_numa,
     denoise_slab_exchange,
     denoise_volume_sharded,
     exchange_halo,
@@ -42,6 +43,7 @@ __all__ = [
     "quantize",
     "tile_stats",
     "slab_plan",
+    "bind_to_gpu_numa",
     "denoise_volume_sharded",
     "merge_histograms",
     "denoise_slab_exchange",

@@ -116,6 +116,33 @@ def denoise_volume_sharded(get_slab, z_total, sigma, denoiser, world=1, rank=0, 
     return own_begin, own_end, out
 
 
+def bind_to_gpu_numa(device):
+    """Pin this process (and the threads it starts later) to the CPUs next to GPU `device`, so that pinned
+    host buffers and the copy threads of the library sit on the GPU's NUMA node — with one process per
+    GPU on a multi-socket host, PCIe copies from the far socket are the first thing to slow down.
+    Call it before allocating host buffers.  Returns the number of CPUs bound to, or None when NVML or
+    the topology is unavailable (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(int(device))
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = os.sched_getaffinity(0)
+        if not after:
+            os.sched_setaffinity(0, before)
+            return None
+        return len(after)
+    except Exception:
+        return None
+
+
 def merge_histograms(hist, group=None):
     """All-gather + sum of per-rank 65536-bin histograms (the path's only
     collective).  `hist` is an int64 torch tensor on the rank's device (NCCL) or

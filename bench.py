@@ -263,6 +263,7 @@ def main():
         return 2
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = b4d.bind_to_gpu_numa(local) if world > 1 else None  # before any host buffer exists
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -455,6 +456,7 @@ def main():
             ),
             "e2e": {"value": V * args.steps / dt_e2e, "unit": "voxels/s",
                     "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1])},
+            "cpus_bound_to_gpu_numa_node": numa_cpus,
             "gpu_launches": int(h2d[2]),
             "clocks": clocks,
             "roofline": {"bound": "int32", "achieved": achieved / 1e12, "peak": peaks["sub_mad"] / 1e12,
