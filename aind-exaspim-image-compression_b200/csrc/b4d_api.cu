@@ -68,11 +68,10 @@ struct DevBuf {
 struct b4d_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // normalise + device-to-host of finished planes, overlapped with stage 2
+    cudaStream_t copy_stream = nullptr;  // host transfers (and the normalise of finished planes) overlapped with kernels
     b4d_profile prof;
     DevBuf in, u16, zf, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2, cells, tcls;
     DevBuf alt_in, alt_zf, alt_out, alt_partial, alt_sink;  // second buffer set of b4d_targets_u16
-    cudaEvent_t ev[B4D_T_COUNT + 1];
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
     unsigned long long match_stats[4];
@@ -725,8 +724,12 @@ int b4d_create(int device, const b4d_profile *profile, b4d_handle **out) {
         delete h;
         return fail(B4D_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(es));
     }
-    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    es = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (es != cudaSuccess) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return fail(B4D_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(es));
+    }
     reset_timings(h);
     std::memset(h->match_stats, 0, sizeof(h->match_stats));
     *out = h;
@@ -740,7 +743,6 @@ void b4d_destroy(b4d_handle *h) {
                       &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2, &h->cells, &h->tcls,
                       &h->alt_in, &h->alt_zf, &h->alt_out, &h->alt_partial, &h->alt_sink})
         b->release();
-    for (auto &ev : h->ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
