@@ -101,11 +101,33 @@ __global__ void __launch_bounds__(256) k_u16_sub_offset(const uint16_t *__restri
                                                         unsigned *__restrict__ minmax) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     unsigned mn = 0xFFFFu, mx = 0u;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned e = in[i];
-        mn = min(mn, e);
-        mx = max(mx, e);
-        out[i] = __fsub_rn((float)e, __ldg(off + i / vol_stride));
+    if ((vol_stride & 7) == 0) {
+        // 8 voxels per thread and iteration (they belong to one volume): one 16-byte load, two 16-byte stores
+        const long long nv = n >> 3, vs8 = vol_stride >> 3;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(in) + i);
+            const float o = __ldg(off + i / vs8);
+            const unsigned e[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
+                                   v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                mn = min(mn, e[k]);
+                mx = max(mx, e[k]);
+            }
+            __stcs(reinterpret_cast<float4 *>(out) + 2 * i,
+                   make_float4(__fsub_rn((float)e[0], o), __fsub_rn((float)e[1], o), __fsub_rn((float)e[2], o),
+                               __fsub_rn((float)e[3], o)));
+            __stcs(reinterpret_cast<float4 *>(out) + 2 * i + 1,
+                   make_float4(__fsub_rn((float)e[4], o), __fsub_rn((float)e[5], o), __fsub_rn((float)e[6], o),
+                               __fsub_rn((float)e[7], o)));
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const unsigned e = in[i];
+            mn = min(mn, e);
+            mx = max(mx, e);
+            out[i] = __fsub_rn((float)e, __ldg(off + i / vol_stride));
+        }
     }
     mn = __reduce_min_sync(0xFFFFFFFFu, mn);
     mx = __reduce_max_sync(0xFFFFFFFFu, mx);
@@ -117,7 +139,16 @@ __global__ void __launch_bounds__(256) k_u16_sub_offset(const uint16_t *__restri
 // teacher = clip(x, 0, max_count) in place (data_handling.py:333)
 __global__ void __launch_bounds__(256) k_clip(float *__restrict__ x, long long n, float hi) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    const long long nv = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        float4 v = reinterpret_cast<float4 *>(x)[i];
+        v.x = fminf(fmaxf(v.x, 0.0f), hi);
+        v.y = fminf(fmaxf(v.y, 0.0f), hi);
+        v.z = fminf(fmaxf(v.z, 0.0f), hi);
+        v.w = fminf(fmaxf(v.w, 0.0f), hi);
+        reinterpret_cast<float4 *>(x)[i] = v;
+    }
+    for (long long i = (nv << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         x[i] = fminf(fmaxf(x[i], 0.0f), hi);
 }
 
@@ -164,19 +195,25 @@ __global__ void __launch_bounds__(256) k_quantize(const float *__restrict__ in, 
                                                   long long n, float osub, float oadd, float step) {
     const bool unit = (step == 1.0f);
     const float hi = __fdiv_rn(65535.0f, step);
-    const long long nv = n >> 3;
+    // 16 voxels per thread and iteration: four 16-byte loads in flight, two 16-byte stores
+    const long long nv = n >> 4;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-        const float4 a = __ldcs(reinterpret_cast<const float4 *>(in) + 2 * i);
-        const float4 b = __ldcs(reinterpret_cast<const float4 *>(in) + 2 * i + 1);
-        uint4 o;
-        o.x = quant1(a.x, osub, oadd, step, hi, unit) | (quant1(a.y, osub, oadd, step, hi, unit) << 16);
-        o.y = quant1(a.z, osub, oadd, step, hi, unit) | (quant1(a.w, osub, oadd, step, hi, unit) << 16);
-        o.z = quant1(b.x, osub, oadd, step, hi, unit) | (quant1(b.y, osub, oadd, step, hi, unit) << 16);
-        o.w = quant1(b.z, osub, oadd, step, hi, unit) | (quant1(b.w, osub, oadd, step, hi, unit) << 16);
-        __stcs(reinterpret_cast<uint4 *>(out) + i, o);
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldcs(reinterpret_cast<const float4 *>(in) + 4 * i + k);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float4 a = v[2 * k], b = v[2 * k + 1];
+            uint4 o;
+            o.x = quant1(a.x, osub, oadd, step, hi, unit) | (quant1(a.y, osub, oadd, step, hi, unit) << 16);
+            o.y = quant1(a.z, osub, oadd, step, hi, unit) | (quant1(a.w, osub, oadd, step, hi, unit) << 16);
+            o.z = quant1(b.x, osub, oadd, step, hi, unit) | (quant1(b.y, osub, oadd, step, hi, unit) << 16);
+            o.w = quant1(b.z, osub, oadd, step, hi, unit) | (quant1(b.w, osub, oadd, step, hi, unit) << 16);
+            __stcs(reinterpret_cast<uint4 *>(out) + 2 * i + k, o);
+        }
     }
-    for (long long i = (nv << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    for (long long i = (nv << 4) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = (uint16_t)quant1(in[i], osub, oadd, step, hi, unit);
 }
 
@@ -500,10 +537,10 @@ void b4d_launch_u16_to_f32(const uint16_t *in, float *out, long long n, unsigned
 }
 void b4d_launch_u16_sub_offset(const uint16_t *in, const float *off, float *out, long long vol_stride, long long n,
                                unsigned *minmax, cudaStream_t s) {
-    k_u16_sub_offset<<<grid_for(n, 256, 8), 256, 0, s>>>(in, off, out, vol_stride, n, minmax);
+    k_u16_sub_offset<<<grid_for((vol_stride & 7) ? n : (n >> 3), 256, 8), 256, 0, s>>>(in, off, out, vol_stride, n, minmax);
 }
 void b4d_launch_clip(float *x, long long n, float hi, cudaStream_t s) {
-    k_clip<<<grid_for(n, 256, 8), 256, 0, s>>>(x, n, hi);
+    k_clip<<<grid_for(n >> 2, 256, 8), 256, 0, s>>>(x, n, hi);
 }
 void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, float scale, int ishift,
                          cudaStream_t s) {
@@ -515,7 +552,7 @@ void b4d_launch_normalise_det(const long long *numq, const long long *denq, cons
 }
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s) {
-    k_quantize<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, offset_sub, offset_add, step);
+    k_quantize<<<grid_for(n >> 4, 256, 8), 256, 0, s>>>(in, out, n, offset_sub, offset_add, step);
 }
 void b4d_launch_chunk_shuffle(const uint16_t *in, int D, int H, int W, int cz, int cy, int cx, uint8_t *out,
                               uint32_t *hist, cudaStream_t s) {

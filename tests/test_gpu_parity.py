@@ -172,6 +172,12 @@ def test_batch_equals_per_patch_and_precompute_targets(b4d_mod, oracle_lib):
     h.set_pipeline_min_voxels(1 << 26)
     for i in range(11):
         assert np.array_equal(praw[i], raw[i % 3]) and np.array_equal(pteach[i], teacher[i % 3])
+    # a patch size that is not a multiple of 8 voxels (the scalar form of the offset kernel)
+    odd = np.stack([synth.vol(9, 10, 11, seed=s) for s in (5, 6, 7)])
+    oraw, oteach = b4d_mod.precompute_targets(odd, [1.5, 37.0, 36.37], 24.0)
+    for i, o in enumerate((1.5, 37.0, 36.37)):
+        ri = oracle_lib.read_counts(odd[i], np.float32(o))
+        assert np.array_equal(oraw[i], ri) and np.array_equal(oteach[i], np.clip(b4d_mod.bm4d(ri, 24.0), 0, 65535))
     _, low = b4d_mod.precompute_targets(batch[:1], 37.0, 24.0, max_count=150.0)
     assert low.max() <= 150.0 and np.array_equal(low[0], np.minimum(teacher[0], 150.0))
 
