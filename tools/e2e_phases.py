@@ -4,7 +4,7 @@ the neighbour exchange and stage 2 per step, resident against host buffers.  Dev
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "aind-exaspim-image-compression_b200")); sys.path.insert(0, ROOT)
-import numpy as np, torch, torch.distributed as dist
+import torch, torch.distributed as dist
 import b4d, bench
 from b4d.sharding import exchange_halo, exchange_planes, slab_plan
 

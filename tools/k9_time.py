@@ -3,7 +3,7 @@ three kinds: raw counts, denoised step-1 counts, coarsely quantized counts.  Dev
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "aind-exaspim-image-compression_b200")); sys.path.insert(0, ROOT)
-import numpy as np, torch
+import torch
 import b4d
 from b4d import synth
 dev = torch.device("cuda", 0)
