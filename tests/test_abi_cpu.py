@@ -105,3 +105,29 @@ def test_bm4d_import_name_shim():
     import b4d
 
     assert shim.bm4d is b4d.bm4d and hasattr(shim, "BM4DProfile") and hasattr(shim, "BM4DStages")
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: no file of the package (Python or CUDA/C++) may import,
+    include, load or name it, and libb4d.so must not depend on liboracle.so."""
+    import os
+    import re
+    import subprocess
+
+    from b4d import _lib
+
+    pkg = os.path.dirname(os.path.dirname(os.path.abspath(_lib.__file__)))
+    pat = re.compile(r"\b(np_oracle|liboracle|b4d_oracle)\b|(^|\s)(from|import)\s+oracle\b|[\"'/]oracle/")
+    offenders = []
+    for root, _dirs, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) and f != "Makefile":
+                continue
+            path = os.path.join(root, f)
+            for ln, line in enumerate(open(path, errors="replace"), 1):
+                code = line.split("#", 1)[0] if (f.endswith(".py") or f == "Makefile") else line.split("//", 1)[0]
+                if pat.search(code):
+                    offenders.append("%s:%d: %s" % (os.path.relpath(path, pkg), ln, line.strip()))
+    assert not offenders, offenders
+    needed = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in needed
