@@ -809,10 +809,27 @@ static int denoise_oversize_u16(b4d_handle *h, const uint16_t *in, const int64_t
 
 int b4d_denoise_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t shape[3], float sigma, float *out,
                     int in_on_device, int out_on_device) {
-    if (h && in && out && shape && n == 1 && shape[0] > 0 && shape[1] > 0 && shape[2] > 0 &&
+    if (h && in && out && shape && n >= 1 && shape[0] > 0 && shape[1] > 0 && shape[2] > 0 &&
         shape[0] * shape[1] * shape[2] > h->pass_voxels) {
         B4D_TRY(common_checks(h, in, out, shape, sigma));
-        return denoise_oversize_u16(h, in, shape, sigma, out, in_on_device, out_on_device);
+        const int64_t V = shape[0] * shape[1] * shape[2];
+        float t_ms[B4D_T_COUNT] = {};
+        int64_t launches[B4D_T_COUNT] = {};
+        unsigned long long stats[4] = {};
+        for (int64_t i = 0; i < n; ++i) {  // every volume of the batch is larger than a pass
+            B4D_TRY(denoise_oversize_u16(h, in + i * V, shape, sigma, out + i * V, in_on_device, out_on_device));
+            for (int k = 0; k < B4D_T_COUNT; ++k) {
+                t_ms[k] += h->t_ms[k];
+                launches[k] += h->launches[k];
+            }
+            for (int k = 0; k < 4; ++k) stats[k] += h->match_stats[k];
+        }
+        for (int k = 0; k < B4D_T_COUNT; ++k) {
+            h->t_ms[k] = t_ms[k];
+            h->launches[k] = launches[k];
+        }
+        for (int k = 0; k < 4; ++k) h->match_stats[k] = stats[k];
+        return 0;
     }
     return denoise_batch<uint16_t>(h, in, n, shape, sigma, out, in_on_device, out_on_device);
 }

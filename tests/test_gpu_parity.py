@@ -507,6 +507,8 @@ def test_volume_larger_than_a_pass_is_slabbed_on_one_gpu(b4d_mod):
     assert sum(v[1] for v in d.last_timings().values()) > 5 * one
     d.set_pass_voxels(80 * 24 * 28)
     assert np.array_equal(d.denoise(vol, 24.0), whole)
+    two = d.denoise(np.stack([vol, vol[::-1].copy()]), 24.0)  # a batch of oversize volumes: one after the other
+    assert np.array_equal(two[0], whole) and np.array_equal(two[1], b4d_mod.bm4d(vol[::-1].copy(), 24.0))
     d.set_pass_voxels(40 * 24 * 28)  # two halos do not fit
     with pytest.raises(ValueError):
         d.denoise(vol, 24.0)
