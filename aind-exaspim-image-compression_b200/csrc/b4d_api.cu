@@ -173,6 +173,7 @@ B4dTables make_tables(const b4d_profile &p, float sigma) {
                 bessel_i0((double)p.kaiser_beta);
         }
         kf[n] = (float)w;
+        t.kf[n] = kf[n];
     }
     for (int z = 0; z < 4; ++z)
         for (int y = 0; y < 4; ++y)
@@ -380,7 +381,8 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         return 0;
     };
     auto normalise = [&](const float *fb, float *dst) {
-        b4d_launch_normalise_det(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, TV, 1.0f / mm.scale, s);
+        b4d_launch_normalise_wm(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, pl.D, pl.H, pl.W, pl.nvol,
+                                0, pl.D, 1.0f / mm.scale, tab.kf, s);
     };
 
     float *d_basic = (p.stages == 1 && phase == 0) ? d_out : h->basic.as<float>();
@@ -522,9 +524,9 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
             }
             CU_TRY(cudaStreamWaitEvent(h->copy_stream, evs[c], 0));
             if (zfin > zdone) {
-                const long long off = zdone * P, n = (zfin - zdone) * P;
-                b4d_launch_normalise_det(h->numq.as<long long>() + off, h->denq.as<long long>() + off, d_basic + off,
-                                         d_out + off, n, 1.0f / mm.scale, h->copy_stream);
+                // origins below zfin are final as well: a block touches its own origin plane
+                b4d_launch_normalise_wm(h->numq.as<long long>(), h->denq.as<long long>(), d_basic, d_out, pl.D, pl.H,
+                                        pl.W, 1, (int)zdone, (int)zfin, 1.0f / mm.scale, tab.kf, h->copy_stream);
                 const long long a = std::max(zdone, sink->p0), b = std::min(zfin, sink->p1);
                 if (b > a)
                     CU_TRY(copy_out(h, sink->host + (a - sink->p0) * P, d_out + a * P, (size_t)(b - a) * P * sizeof(float),

@@ -26,6 +26,7 @@ struct B4dGeom {
 // once, exactly as oracle/b4d_oracle.cpp make_tables() does.
 struct B4dTables {
     float win[B4D_LV];   // (w[z]*w[y])*w[x], float32 products
+    float kf[4];         // per-axis Kaiser factors w[n]: the normalise kernel convolves the weight map with them
     float tht[16];       // lambda*sigma*2^(m/2)
     float gs[8];         // 2^(-l/2)
     float c1, c3;        // DCT-II-4
@@ -85,8 +86,10 @@ void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, 
 void b4d_launch_u16_sub_offset(const uint16_t *in, const float *off, float *out, long long vol_stride, long long n,
                                unsigned *minmax, cudaStream_t s);
 void b4d_launch_clip(float *x, long long n, float hi, cudaStream_t s);
-void b4d_launch_normalise_det(const long long *numq, const long long *denq, const float *fallback, float *out,
-                              long long n, float inv_qscale, cudaStream_t s);
+// weight-map contract: den = G (*) (kf x kf x kf) over planes [z0, z1) of every volume, out = num / den / qscale
+void b4d_launch_normalise_wm(const long long *numq, const long long *gmap, const float *fallback, float *out, int D,
+                             int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4],
+                             cudaStream_t s);
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s);
 void b4d_launch_hist(const uint16_t *in, long long n, unsigned long long *hist, cudaStream_t s);

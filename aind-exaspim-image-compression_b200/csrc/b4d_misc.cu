@@ -153,33 +153,66 @@ __global__ void __launch_bounds__(256) k_clip(float *__restrict__ x, long long n
 }
 
 // ------------------------------------------------------------- normalise ----
-// K3 / K6: out = num / den / qscale (den > 0), else the fallback value.  Accumulators are
-// fixed point (int64): 16 B read + 4 B fallback + 4 B write per voxel.
-__device__ __forceinline__ float norm1(long long nq, long long dq, float fb, double inv) {
-    return dq > 0 ? (float)(((double)nq / (double)dq) * inv) : fb;
-}
-__global__ void __launch_bounds__(256) k_normalise_det(const long long *__restrict__ numq,
-                                                       const long long *__restrict__ denq,
-                                                       const float *__restrict__ fb, float *__restrict__ out,
-                                                       long long n, float inv_qscale) {
+// K3 / K6 (weight-map contract): the filter kernels leave, per block origin o, the integer G[o] = sum of the
+// group weights qg of the blocks that sit there.  den(v) = sum over d in [0,4)^3 of G[v - d] kf[dz] kf[dy] kf[dx],
+// evaluated as three 4-tap passes (x, then y, then z), each an fma chain over d = 0..3 in float64 — the order of
+// oracle den_from_weight_map, so the result is identical bit for bit.  Origins outside the volume hold 0, and
+// fma(k, 0, acc) == acc, so the tile halo needs no special cases.  out = num / den / qscale, else the fallback.
+constexpr int WM_TZ = 4, WM_TY = 8, WM_TX = 32;
+constexpr int WM_EZ = WM_TZ + 3, WM_EY = WM_TY + 3, WM_EX = WM_TX + 3;
+__global__ void __launch_bounds__(256) k_normalise_wm(const long long *__restrict__ numq,
+                                                      const long long *__restrict__ gmap,
+                                                      const float *__restrict__ fb, float *__restrict__ out, int D,
+                                                      int H, int W, int nvol, int z0, int z1, float inv_qscale,
+                                                      float kf0, float kf1, float kf2, float kf3) {
+    __shared__ double sa[WM_EZ][WM_EY][WM_EX];
+    __shared__ double sb[WM_EZ][WM_EY][WM_EX];
+    const double k[4] = {(double)kf0, (double)kf1, (double)kf2, (double)kf3};
     const double inv = (double)inv_qscale;
-    const long long nv = n >> 2;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-        const longlong2 n0 = __ldcs(reinterpret_cast<const longlong2 *>(numq) + 2 * i);
-        const longlong2 n1 = __ldcs(reinterpret_cast<const longlong2 *>(numq) + 2 * i + 1);
-        const longlong2 d0 = __ldcs(reinterpret_cast<const longlong2 *>(denq) + 2 * i);
-        const longlong2 d1 = __ldcs(reinterpret_cast<const longlong2 *>(denq) + 2 * i + 1);
-        const float4 f = reinterpret_cast<const float4 *>(fb)[i];
-        float4 o;
-        o.x = norm1(n0.x, d0.x, f.x, inv);
-        o.y = norm1(n0.y, d0.y, f.y, inv);
-        o.z = norm1(n1.x, d1.x, f.z, inv);
-        o.w = norm1(n1.y, d1.y, f.w, inv);
-        reinterpret_cast<float4 *>(out)[i] = o;
+    const int tx = (W + WM_TX - 1) / WM_TX, ty = (H + WM_TY - 1) / WM_TY, tz = (z1 - z0 + WM_TZ - 1) / WM_TZ;
+    const long long tiles = (long long)nvol * tz * ty * tx;
+    const long long V = (long long)D * H * W;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int ix = (int)(t % tx), iy = (int)((t / tx) % ty), iz = (int)((t / ((long long)tx * ty)) % tz);
+        const long long vol = t / ((long long)tx * ty * tz);
+        const int X0 = ix * WM_TX, Y0 = iy * WM_TY, Z0 = z0 + iz * WM_TZ;
+        const long long *g = gmap + vol * V;
+        for (int i = threadIdx.x; i < WM_EZ * WM_EY * WM_EX; i += blockDim.x) {
+            const int lx = i % WM_EX, ly = (i / WM_EX) % WM_EY, lz = i / (WM_EX * WM_EY);
+            const int gz = Z0 - 3 + lz, gy = Y0 - 3 + ly, gx = X0 - 3 + lx;
+            const bool in = (unsigned)gz < (unsigned)D && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+            sa[lz][ly][lx] = in ? (double)g[((long long)gz * H + gy) * W + gx] : 0.0;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < WM_EZ * WM_EY * WM_TX; i += blockDim.x) {  // x pass: sa -> sb
+            const int lx = 3 + i % WM_TX, ly = (i / WM_TX) % WM_EY, lz = i / (WM_TX * WM_EY);
+            double acc = 0.0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) acc = fma(k[d], sa[lz][ly][lx - d], acc);
+            sb[lz][ly][lx] = acc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < WM_EZ * WM_TY * WM_TX; i += blockDim.x) {  // y pass: sb -> sa
+            const int lx = 3 + i % WM_TX, ly = 3 + (i / WM_TX) % WM_TY, lz = i / (WM_TX * WM_TY);
+            double acc = 0.0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) acc = fma(k[d], sb[lz][ly - d][lx], acc);
+            sa[lz][ly][lx] = acc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < WM_TZ * WM_TY * WM_TX; i += blockDim.x) {  // z pass and the division
+            const int lx = 3 + i % WM_TX, ly = 3 + (i / WM_TX) % WM_TY, lz = 3 + i / (WM_TX * WM_TY);
+            const int gz = Z0 + lz - 3, gy = Y0 + ly - 3, gx = X0 + lx - 3;
+            if (gz < z1 && gy < H && gx < W) {
+                double den = 0.0;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) den = fma(k[d], sa[lz - d][ly][lx], den);
+                const long long a = vol * V + ((long long)gz * H + gy) * W + gx;
+                out[a] = den > 0.0 ? (float)(((double)numq[a] / den) * inv) : fb[a];
+            }
+        }
+        __syncthreads();
     }
-    for (long long i = (nv << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = norm1(numq[i], denq[i], fb[i], inv);
 }
 
 // -------------------------------------------------------------- quantize ----
@@ -546,9 +579,14 @@ void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, 
                          cudaStream_t s) {
     k_to_match<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, cf, scale, ishift);
 }
-void b4d_launch_normalise_det(const long long *numq, const long long *denq, const float *fallback, float *out,
-                              long long n, float inv_qscale, cudaStream_t s) {
-    k_normalise_det<<<grid_for(n >> 2, 256, 8), 256, 0, s>>>(numq, denq, fallback, out, n, inv_qscale);
+void b4d_launch_normalise_wm(const long long *numq, const long long *gmap, const float *fallback, float *out, int D,
+                             int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4],
+                             cudaStream_t s) {
+    if (z1 <= z0) return;
+    const long long tiles = (long long)nvol * ((z1 - z0 + WM_TZ - 1) / WM_TZ) * ((H + WM_TY - 1) / WM_TY) *
+                            ((W + WM_TX - 1) / WM_TX);
+    k_normalise_wm<<<grid_for(tiles * 256, 256, 4), 256, 0, s>>>(numq, gmap, fallback, out, D, H, W, nvol, z0, z1,
+                                                                inv_qscale, kf[0], kf[1], kf[2], kf[3]);
 }
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s) {

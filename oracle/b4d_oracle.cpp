@@ -384,6 +384,7 @@ void filter_f64(const float *zf, const double *basic, const Geom &g, const Match
 // =====================================================================
 struct MirrorTables {
     float win[LV];       // (w[z]*w[y])*w[x] in float32
+    float kf[4];         // the per-axis factors w[n] (float32): the denominator convolves with them separably
     float tht[16];       // tht[m] = float(lambda*sigma*2^(m/2)), m = 6 - n + l
     float gs[6];         // gs[l] = float(2^(-l/2)): group normalisation
     float c1, c3;        // DCT-II-4 constants
@@ -395,6 +396,7 @@ MirrorTables make_tables(const b4d_profile &p, float sigma) {
     kaiser4(p.kaiser_beta, kw);
     float kf[4];
     for (int i = 0; i < 4; ++i) kf[i] = (float)kw[i];
+    for (int i = 0; i < 4; ++i) t.kf[i] = kf[i];
     for (int z = 0; z < 4; ++z)
         for (int y = 0; y < 4; ++y)
             for (int x = 0; x < 4; ++x) t.win[(z * 4 + y) * 4 + x] = (kf[z] * kf[y]) * kf[x];
@@ -592,23 +594,60 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
             ghaar_inv(noisy, kp);
             for (int k = 0; k < kp; ++k) xf3_inv<true>(noisy + k * LV, t);
         }
-        for (int k = 0; k < kp; ++k)
+        // Weight-map contract: the group weight is quantised once, qg = rint(w * 2^20); the numerator
+        // term of a voxel uses the float32 weight float(qg) * win[v] (limb format as before), the
+        // denominator is NOT accumulated per voxel: G[origin] += qg once per grouped block, and
+        // den = G (*) window is evaluated by the normalise step (den_from_weight_map).
+        const int64_t qg = (int64_t)lrintf(weight * W_SCALE);
+        for (int k = 0; k < kp; ++k) {
+#pragma omp atomic
+            denq[cz[k] * sz + cy[k] * sy + cx[k]] += qg;
             for (int z = 0; z < 4; ++z)
                 for (int y = 0; y < 4; ++y)
                     for (int x = 0; x < 4; ++x) {
                         const int v = (z * 4 + y) * 4 + x;
                         const int64_t a = (cz[k] + z) * sz + (cy[k] + y) * sy + cx[k] + x;
-                        const float ww = weight * t.win[v];
-                        const int64_t qd = (int64_t)lrintf(ww * W_SCALE);
-                        const float wqf = (float)qd * qscale;
+                        const float wqf = ((float)qg * t.win[v]) * qscale;
                         const float tq = fminf(fmaxf(wqf * noisy[k * LV + v], -Q_LIMIT), Q_LIMIT);
                         const int64_t qn = llrintf(tq);
 #pragma omp atomic
                         numq[a] += qn;
-#pragma omp atomic
-                        denq[a] += qd;
                     }
+        }
     }
+}
+
+// den(v) = sum over block origins o = v - (dz, dy, dx), 0 <= d < 4, of G[o] * kf[dz] * kf[dy] * kf[dx]:
+// three 4-tap passes (x, then y, then z) in float64, each an fma chain over d = 0..3 in that order —
+// the order the normalise kernel has to follow.
+void den_from_weight_map(const std::vector<int64_t> &G, const Geom &g, const MirrorTables &t, std::vector<double> &den) {
+    const int D = g.D, H = g.H, W = g.W;
+    const int64_t V = (int64_t)D * H * W;
+    std::vector<double> a((size_t)V), b((size_t)V);
+    const double k[4] = {(double)t.kf[0], (double)t.kf[1], (double)t.kf[2], (double)t.kf[3]};
+#pragma omp parallel for
+    for (int64_t zy = 0; zy < (int64_t)D * H; ++zy)
+        for (int x = 0; x < W; ++x) {
+            double acc = 0.0;
+            for (int d = 0; d < 4 && d <= x; ++d) acc = std::fma(k[d], (double)G[zy * W + x - d], acc);
+            a[zy * W + x] = acc;
+        }
+#pragma omp parallel for
+    for (int z = 0; z < D; ++z)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                double acc = 0.0;
+                for (int d = 0; d < 4 && d <= y; ++d) acc = std::fma(k[d], a[((int64_t)z * H + y - d) * W + x], acc);
+                b[((int64_t)z * H + y) * W + x] = acc;
+            }
+    den.assign((size_t)V, 0.0);
+#pragma omp parallel for
+    for (int z = 0; z < D; ++z)
+        for (int64_t yx = 0; yx < (int64_t)H * W; ++yx) {
+            double acc = 0.0;
+            for (int d = 0; d < 4 && d <= z; ++d) acc = std::fma(k[d], b[(int64_t)(z - d) * H * W + yx], acc);
+            den[(int64_t)z * H * W + yx] = acc;
+        }
 }
 
 // ----------------------------------------------------- matching image ------
@@ -718,9 +757,10 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     std::vector<int64_t> numq(V, 0), denq(V, 0);
     std::vector<float> basic(V);
     const double inv_q = 1.0 / (double)mm.scale;
+    std::vector<double> den;
     filter_mirror<false>(zf.data(), nullptr, g1, m, p.search_ht, t, mm.scale, numq, denq);
-    for (int64_t i = 0; i < V; ++i)
-        basic[i] = denq[i] > 0 ? (float)(((double)numq[i] / (double)denq[i]) * inv_q) : zf[i];
+    den_from_weight_map(denq, g1, t, den);
+    for (int64_t i = 0; i < V; ++i) basic[i] = den[i] > 0 ? (float)(((double)numq[i] / den[i]) * inv_q) : zf[i];
     if (p.stages == 1) {
         std::memcpy(out, basic.data(), V * sizeof(float));
         return 0;
@@ -730,8 +770,8 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     std::fill(numq.begin(), numq.end(), 0);
     std::fill(denq.begin(), denq.end(), 0);
     filter_mirror<true>(zf.data(), basic.data(), g2, m, p.search_wie, t, mm.scale, numq, denq);
-    for (int64_t i = 0; i < V; ++i)
-        out[i] = denq[i] > 0 ? (float)(((double)numq[i] / (double)denq[i]) * inv_q) : basic[i];
+    den_from_weight_map(denq, g2, t, den);
+    for (int64_t i = 0; i < V; ++i) out[i] = den[i] > 0 ? (float)(((double)numq[i] / den[i]) * inv_q) : basic[i];
     return 0;
 }
 
