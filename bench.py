@@ -31,6 +31,12 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank.  Rank 0 runs the CPU legs (cpu_baseline,
+# --impl reference) on all the host cores it may use, so the OpenMP runtime has to see that count BEFORE any
+# library that carries one (NumPy, torch, liboracle.so) is loaded; oracle_threads() reports what was used.
+if int(os.environ.get("RANK", "0")) == 0:
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+    os.environ.pop("OMP_THREAD_LIMIT", None)
 for _p in (os.path.join(ROOT, "aind-exaspim-image-compression_b200"), ROOT):
     if _p not in sys.path:
         sys.path.insert(0, _p)
@@ -173,6 +179,14 @@ def traffic_per_launch(size, world):
         return None
 
 
+def oracle_threads():
+    """Pin the oracle's OpenMP team to the cores this process may run on and return the team size
+    actually used (omp_get_max_threads after the call) — never os.cpu_count()."""
+    from oracle import np_oracle
+
+    return np_oracle.set_threads(len(os.sched_getaffinity(0)))
+
+
 def cpu_port_throughput(sample_shape, repeats=1):
     """voxels/s of the CPU oracle (float32 path, OpenMP over all host cores)."""
     from oracle import np_oracle
@@ -193,7 +207,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     shape = (128, 192, 192)
-    cores = os.cpu_count() or 1
+    cores = oracle_threads()
     real = probe_real_bm4d()
     from oracle import np_oracle
 
@@ -386,10 +400,31 @@ def main():
     barrier()
     dt_e2e = ev0.elapsed_time(ev1) * 1e-3
 
-    times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=dev)
+    # ---- the same with ordinary (pageable) NumPy arrays, what the reference's callers hand over: the
+    # library stages them through its pinned ring (HostMover).  Wall clock between barriers (the call
+    # returns when the output array is complete).
+    slab_np = np.array(slab_pin.numpy(), copy=True)
+    out_np = np.empty(tuple(out_pin.shape), dtype=np.float32)
+
+    def step_pageable():
+        if exchange:
+            denoise_slab_exchange(dn, slab_np, zb, S, own_b, own_e, SIGMA, rank, world, device=dev, out=out_np)
+        else:
+            dn.denoise_slab(slab_np, zb, S, own_b, own_e, SIGMA, out=out_np)
+
+    step_pageable()
+    barrier()
+    t_pg = time.perf_counter()
+    for _ in range(args.steps):
+        step_pageable()
+    barrier()
+    dt_pg = time.perf_counter() - t_pg
+    del slab_np, out_np
+
+    times = torch.tensor([dt, dt_e2e, dt_pg], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt, dt_e2e = float(times[0]), float(times[1])
+    dt, dt_e2e, dt_pg = float(times[0]), float(times[1]), float(times[2])
     h2d = torch.tensor([slab_pin.numel() * 2, out_pin.numel() * 4, launches], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
@@ -415,10 +450,12 @@ def main():
             "match": {"bound": "int32", "achieved": achieved / 1e12, "peak": peaks["sub_mad"] / 1e12, "unit": "TOP/s",
                       "frac": achieved / peaks["sub_mad"] if peaks["sub_mad"] else None,
                       "ms_per_launch": t_match * 1e3},
-            # 2 x int64 accumulators + float32 fallback read, float32 written: 24 B/voxel
-            "normalise": {"bound": "hbm", "achieved": 24.0 * slab_vox / t_norm / 1e9 if t_norm > 0 else None,
+            # K3 / K6 count 8 B read + 4 B write per voxel (the kernel itself moves more: int64
+            # numerator, uint32 weight map, float32 fallback, float32 out = 20 B/voxel)
+            "normalise": {"bound": "hbm", "achieved": 12.0 * slab_vox / t_norm / 1e9 if t_norm > 0 else None,
                           "peak": hbm_peak, "unit": "GB/s",
-                          "frac": 24.0 * slab_vox / t_norm / 1e9 / hbm_peak if t_norm > 0 else None,
+                          "frac": 12.0 * slab_vox / t_norm / 1e9 / hbm_peak if t_norm > 0 else None,
+                          "moved_bytes_per_voxel": 20.0,
                           "ms_per_launch": t_norm * 1e3},
             # K7: float32 read + uint16 write = 6 B/voxel
             "quantize": {"bound": "hbm", "achieved": 6.0 * q_vox / (q_ms * 1e-3) / 1e9, "peak": hbm_peak,
@@ -455,7 +492,11 @@ def main():
                 timing="CUDA events on the library stream around the K steps, between barrier + synchronize, max over ranks",
             ),
             "e2e": {"value": V * args.steps / dt_e2e, "unit": "voxels/s",
-                    "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1])},
+                    "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1]),
+                    "host_buffers": "pinned"},
+            "e2e_pageable": {"value": V * args.steps / dt_pg, "unit": "voxels/s",
+                             "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1]),
+                             "host_buffers": "pageable NumPy arrays (the reference's call surface), wall clock"},
             "cpus_bound_to_gpu_numa_node": numa_cpus,
             "gpu_launches": int(h2d[2]),
             "clocks": clocks,
@@ -472,11 +513,12 @@ def main():
             "match_stats": mstats,
             "tile_stats": stats,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (the other ranks would idle in a barrier)
             shape = (192, 256, 256)
+            threads = oracle_threads()
             v, secs = cpu_port_throughput(shape)
             line["cpu_baseline"] = {
-                "value": v, "unit": "voxels/s", "cores": os.cpu_count() or 1, "kind": "port",
+                "value": v, "unit": "voxels/s", "cores": threads, "kind": "port",
                 "sample": "%dx%dx%d sub-volume of the same seeded volume, one pass (%.1f s); CPU restatement, not the closed bm4d binary" % (shape + (secs,)),
             }
         print(json.dumps(line), flush=True)

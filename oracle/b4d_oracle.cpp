@@ -36,6 +36,8 @@
 #include <string>
 #include <vector>
 
+#include <omp.h>
+
 #include "../include/b4d.h"
 
 namespace {
@@ -832,6 +834,13 @@ int b4d_oracle_set_arith(b4d_handle *hh, int arith) {
     if (!h || (arith != 0 && arith != 1)) return fail(B4D_ERR_INVALID, "arith must be 0 or 1");
     h->arith = arith;
     return 0;
+}
+
+// oracle-only: size of the OpenMP team (n <= 0 leaves it alone); returns the team size in effect.
+// torch.distributed.run exports OMP_NUM_THREADS=1, so bench.py sets the count explicitly and reports this value.
+int b4d_oracle_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
 }
 
 int64_t b4d_num_refs(const int64_t shape[3]) {

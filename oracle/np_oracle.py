@@ -168,6 +168,11 @@ def load():
     return _lib
 
 
+def set_threads(n=0):
+    """Set the oracle's OpenMP team size (n <= 0: leave it) and return the size in effect."""
+    return int(load().b4d_oracle_set_threads(int(n)))
+
+
 def _check(rc):
     if rc != 0:
         raise RuntimeError("oracle: %s (status %d)" % (load().b4d_last_error().decode(), rc))
