@@ -40,6 +40,7 @@ EXPORTS = (
     "b4d_stream",
     "b4d_last_match_stats",
     "b4d_measure_pipe_peaks",
+    "b4d_debug_accumulators",
 )
 
 

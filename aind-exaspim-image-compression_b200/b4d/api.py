@@ -122,6 +122,15 @@ class Denoiser:
         except Exception:
             pass
 
+    def debug_accumulators(self, n):
+        """(numq, wmap) int64 arrays: the fixed-point aggregation state the last filter stage of the last
+        single-volume call left on the device (b4d_debug_accumulators; diagnostics for the parity tests)."""
+        numq = np.empty(n, dtype=np.int64)
+        wmap = np.empty(n, dtype=np.int64)
+        _lib.check(self.lib.b4d_debug_accumulators(self._h, numq.ctypes.data_as(ctypes.c_void_p),
+                                                   wmap.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n)))
+        return numq, wmap
+
     def set_profile(self, profile=None, stages=2):
         """Switch algorithm constants (no-op when nothing changes)."""
         prof = _profile_from_arg(profile)

@@ -70,7 +70,7 @@ struct b4d_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // host transfers (and the normalise of finished planes) overlapped with kernels
     b4d_profile prof;
-    DevBuf in, u16, zf, numq, denq, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2, cells, tcls;
+    DevBuf in, u16, zf, numq, gmap, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2, cells, tcls;
     DevBuf alt_in, alt_zf, alt_out, alt_partial, alt_sink;  // second buffer set of b4d_targets_u16
     float t_ms[B4D_T_COUNT];
     int64_t launches[B4D_T_COUNT];
@@ -186,9 +186,14 @@ B4dTables make_tables(const b4d_profile &p, float sigma) {
         const double s = std::ldexp(1.0, m / 2) * ((m & 1) ? M_SQRT2 : 1.0);
         t.tht[m] = (float)((double)p.lambda_ht * (double)sigma * s);
     }
-    for (int l = 0; l < 8; ++l) t.gs[l] = (float)(std::ldexp(1.0, -(l / 2)) * ((l & 1) ? M_SQRT1_2 : 1.0));
-    t.c1 = (float)(std::cos(M_PI / 8.0) * M_SQRT1_2);
-    t.c3 = (float)(std::cos(3.0 * M_PI / 8.0) * M_SQRT1_2);
+    const double c3 = std::cos(3.0 * M_PI / 8.0) * M_SQRT1_2;
+    for (int n = 0; n < 4; ++n)
+        for (int l = 0; l < 6; ++l) {
+            const double sn = std::ldexp(1.0, -(3 - n)) * std::pow(c3, n);
+            t.wa[n * 6 + l] = (float)(sn * std::ldexp(1.0, -(l / 2)) * ((l & 1) ? M_SQRT1_2 : 1.0));
+            t.wb[n * 6 + l] = (float)(sn * sn * std::ldexp(1.0, -l));
+        }
+    t.tq = (float)(1.0 + M_SQRT2);
     volatile float s2 = sigma * sigma;
     t.sigma2 = s2;
     return t;
@@ -370,18 +375,18 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     // that feeds the stage-2 matching (a discontinuous decision) is reproducible.
     // profile.deterministic is kept in the ABI and is always honoured.
     B4D_TRY(h->numq.ensure((size_t)TV * sizeof(long long)));
-    B4D_TRY(h->denq.ensure((size_t)TV * sizeof(long long)));
+    B4D_TRY(h->gmap.ensure((size_t)TV * sizeof(uint32_t)));
     const B4dTables tab = make_tables(p, sigma);
     b4d_upload_tables(tab, s);
     if (phase != 2) CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
 
     auto zero_acc = [&]() -> int {
         CU_TRY(cudaMemsetAsync(h->numq.p, 0, (size_t)TV * sizeof(long long), s));
-        CU_TRY(cudaMemsetAsync(h->denq.p, 0, (size_t)TV * sizeof(long long), s));
+        CU_TRY(cudaMemsetAsync(h->gmap.p, 0, (size_t)TV * sizeof(uint32_t), s));
         return 0;
     };
     auto normalise = [&](const float *fb, float *dst) {
-        b4d_launch_normalise_wm(h->numq.as<long long>(), h->denq.as<long long>(), fb, dst, pl.D, pl.H, pl.W, pl.nvol,
+        b4d_launch_normalise_wm(h->numq.as<long long>(), h->gmap.as<uint32_t>(), fb, dst, pl.D, pl.H, pl.W, pl.nvol,
                                 0, pl.D, 1.0f / mm.scale, tab.kf, s);
     };
 
@@ -457,7 +462,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.nseg = 1;
     fp.qscale = mm.scale;  // data * scale spans at most the 16-bit matching range: terms stay below 2^39
     fp.numq = h->numq.as<long long>();
-    fp.denq = h->denq.as<long long>();
+    fp.gmap = h->gmap.as<uint32_t>();
     if (R1 > 0) b4d_launch_filter(fp, false, s);
     clk.mark(B4D_T_FILTER1, 1);
     normalise(d_zf, d_basic);
@@ -480,7 +485,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         fp.nseg = 1;
         fp.qscale = mm.scale;
         fp.numq = h->numq.as<long long>();
-        fp.denq = h->denq.as<long long>();
+        fp.gmap = h->gmap.as<uint32_t>();
     }
 
     // ---- stage 2: Wiener, matching on the basic estimate
@@ -525,7 +530,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
             CU_TRY(cudaStreamWaitEvent(h->copy_stream, evs[c], 0));
             if (zfin > zdone) {
                 // origins below zfin are final as well: a block touches its own origin plane
-                b4d_launch_normalise_wm(h->numq.as<long long>(), h->denq.as<long long>(), d_basic, d_out, pl.D, pl.H,
+                b4d_launch_normalise_wm(h->numq.as<long long>(), h->gmap.as<uint32_t>(), d_basic, d_out, pl.D, pl.H,
                                         pl.W, 1, (int)zdone, (int)zfin, 1.0f / mm.scale, tab.kf, h->copy_stream);
                 const long long a = std::max(zdone, sink->p0), b = std::min(zfin, sink->p1);
                 if (b > a)
@@ -741,7 +746,7 @@ int b4d_create(int device, const b4d_profile *profile, b4d_handle **out) {
 void b4d_destroy(b4d_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->numq, &h->denq, &h->basic, &h->out, &h->widx, &h->cnt,
+    for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->numq, &h->gmap, &h->basic, &h->out, &h->widx, &h->cnt,
                       &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2, &h->cells, &h->tcls,
                       &h->alt_in, &h->alt_zf, &h->alt_out, &h->alt_partial, &h->alt_sink})
         b->release();
@@ -1450,6 +1455,19 @@ void *b4d_stream(b4d_handle *h) { return h ? (void *)h->stream : nullptr; }
 int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]) {
     if (!h || !out) return fail(B4D_ERR_INVALID, "NULL argument");
     for (int i = 0; i < 4; ++i) out[i] = h->match_stats[i];
+    return 0;
+}
+
+int b4d_debug_accumulators(b4d_handle *h, int64_t *numq, int64_t *wmap, int64_t n) {
+    if (!h || !numq || !wmap || n < 1) return fail(B4D_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(h->device));
+    if (h->numq.cap < (size_t)n * sizeof(long long) || h->gmap.cap < (size_t)n * sizeof(uint32_t))
+        return fail(B4D_ERR_INVALID, "no accumulators of that size");
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaMemcpy(numq, h->numq.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> g((size_t)n);
+    CU_TRY(cudaMemcpy(g.data(), h->gmap.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) wmap[i] = (int64_t)g[(size_t)i];
     return 0;
 }
 

@@ -28,8 +28,11 @@ struct B4dTables {
     float win[B4D_LV];   // (w[z]*w[y])*w[x], float32 products
     float kf[4];         // per-axis Kaiser factors w[n]: the normalise kernel convolves the weight map with them
     float tht[16];       // lambda*sigma*2^(m/2)
-    float gs[8];         // 2^(-l/2)
-    float c1, c3;        // DCT-II-4
+    // Wiener stage, unnormalised DCT butterflies: a raw coefficient with n odd positions (of x, y, z) at
+    // group level l has the true value raw * S_n * 2^(-l/2), S_n = (1/2)^(3-n) c3^n, c3 = cos(3 pi/8)/sqrt 2.
+    float wa[24];        // [n][l] = S_n 2^(-l/2): raw -> true (input of the attenuation)
+    float wb[24];        // [n][l] = S_n^2 2^(-l): raw * W -> input of the unnormalised inverse butterflies
+    float tq;            // 1 + sqrt 2 = c1 / c3
     float sigma2;
 };
 
@@ -60,8 +63,11 @@ struct FilterParams {
     int nseg;                    // z segments per column (set by the launcher)
     int seg0, nseg_launch;       // segments [seg0, seg0 + nseg_launch) belong to this launch
     float qscale;                // power of two: numerator terms are rint(wq * qscale * x), |.| < 2^39
-    long long *numq, *denq;      // fixed-point accumulators (order independent): sum of numerator
-                                 // terms / sum of the 20-bit weights wq
+    long long *numq;             // fixed-point numerator (order independent): sum of rint(wq * qscale * x)
+    uint32_t *gmap;              // weight map: per block origin, the sum of the 20-bit group weights qg
+#ifdef B4D_DEBUG_DUMP
+    long long dbg_ref;           // developer builds: the Wiener-stage reference whose intermediates are printed
+#endif
 };
 
 void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s);
@@ -87,7 +93,7 @@ void b4d_launch_u16_sub_offset(const uint16_t *in, const float *off, float *out,
                                unsigned *minmax, cudaStream_t s);
 void b4d_launch_clip(float *x, long long n, float hi, cudaStream_t s);
 // weight-map contract: den = G (*) (kf x kf x kf) over planes [z0, z1) of every volume, out = num / den / qscale
-void b4d_launch_normalise_wm(const long long *numq, const long long *gmap, const float *fallback, float *out, int D,
+void b4d_launch_normalise_wm(const long long *numq, const uint32_t *gmap, const float *fallback, float *out, int D,
                              int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4],
                              cudaStream_t s);
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,

@@ -158,60 +158,91 @@ __global__ void __launch_bounds__(256) k_clip(float *__restrict__ x, long long n
 // evaluated as three 4-tap passes (x, then y, then z), each an fma chain over d = 0..3 in float64 — the order of
 // oracle den_from_weight_map, so the result is identical bit for bit.  Origins outside the volume hold 0, and
 // fma(k, 0, acc) == acc, so the tile halo needs no special cases.  out = num / den / qscale, else the fallback.
-constexpr int WM_TZ = 4, WM_TY = 8, WM_TX = 32;
-constexpr int WM_EZ = WM_TZ + 3, WM_EY = WM_TY + 3, WM_EX = WM_TX + 3;
+//
+// One CTA owns an 8 x 32 (y, x) tile and marches along z over NZ planes: per plane the uint32 map tile (+3 halo in
+// y and x) goes through shared memory for the x and y passes, the z pass runs on a rolling window of four
+// xy-convolved values in registers.  Algorithmic traffic: int64 numerator 8 B + map 4 B + result 4 B per voxel (the
+// fallback is read only where the denominator is zero, which a complete block grid never produces).
+// Optional fused outputs: the uint16 matching image of the next stage (K3: saves the separate conversion pass) and
+// the quantized uint16 volume (K6 + K7 fused: float32 result never written).
+constexpr int WM_TY = 8, WM_TX = 32, WM_NZ = 32;
+constexpr int WM_EY = WM_TY + 3, WM_EX = WM_TX + 3;
+struct NormOut {
+    float *out;          // float32 result (may be null when q16 is set)
+    uint16_t *match;     // optional: clamp(rint(y * mscale) + ishift, 0, 65535)
+    uint16_t *q16;       // optional: K7 of the result
+    float mscale;
+    int ishift;
+    float q_sub, q_add, q_step, q_hi;
+    int q_unit, q_trunc;
+};
+__device__ __forceinline__ uint32_t quant1(float x, float osub, float oadd, float step, float hi, bool unit);
+__device__ __forceinline__ uint32_t quant1_trunc(float x, float osub, float oadd, float step, float hi, bool unit);
 __global__ void __launch_bounds__(256) k_normalise_wm(const long long *__restrict__ numq,
-                                                      const long long *__restrict__ gmap,
-                                                      const float *__restrict__ fb, float *__restrict__ out, int D,
-                                                      int H, int W, int nvol, int z0, int z1, float inv_qscale,
-                                                      float kf0, float kf1, float kf2, float kf3) {
-    __shared__ double sa[WM_EZ][WM_EY][WM_EX];
-    __shared__ double sb[WM_EZ][WM_EY][WM_EX];
+                                                      const uint32_t *__restrict__ gmap,
+                                                      const float *__restrict__ fb, NormOut o, int D, int H, int W,
+                                                      int nvol, int z0, int z1, float inv_qscale, float kf0, float kf1,
+                                                      float kf2, float kf3) {
+    __shared__ double sa[2][WM_EY][WM_EX + 1];
+    __shared__ double sb[2][WM_EY][WM_TX];
     const double k[4] = {(double)kf0, (double)kf1, (double)kf2, (double)kf3};
     const double inv = (double)inv_qscale;
-    const int tx = (W + WM_TX - 1) / WM_TX, ty = (H + WM_TY - 1) / WM_TY, tz = (z1 - z0 + WM_TZ - 1) / WM_TZ;
-    const long long tiles = (long long)nvol * tz * ty * tx;
-    const long long V = (long long)D * H * W;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int ix = (int)(t % tx), iy = (int)((t / tx) % ty), iz = (int)((t / ((long long)tx * ty)) % tz);
-        const long long vol = t / ((long long)tx * ty * tz);
-        const int X0 = ix * WM_TX, Y0 = iy * WM_TY, Z0 = z0 + iz * WM_TZ;
-        const long long *g = gmap + vol * V;
-        for (int i = threadIdx.x; i < WM_EZ * WM_EY * WM_EX; i += blockDim.x) {
-            const int lx = i % WM_EX, ly = (i / WM_EX) % WM_EY, lz = i / (WM_EX * WM_EY);
-            const int gz = Z0 - 3 + lz, gy = Y0 - 3 + ly, gx = X0 - 3 + lx;
-            const bool in = (unsigned)gz < (unsigned)D && (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-            sa[lz][ly][lx] = in ? (double)g[((long long)gz * H + gy) * W + gx] : 0.0;
+    const int ntx = (W + WM_TX - 1) / WM_TX, nty = (H + WM_TY - 1) / WM_TY, ntz = (z1 - z0 + WM_NZ - 1) / WM_NZ;
+    long long t = blockIdx.x;
+    const int ix = (int)(t % ntx);
+    t /= ntx;
+    const int iy = (int)(t % nty);
+    t /= nty;
+    const int iz = (int)(t % ntz);
+    const long long vol = t / ntz;
+    const long long P = (long long)H * W, V = P * D;
+    const int X0 = ix * WM_TX, Y0 = iy * WM_TY, Za = z0 + iz * WM_NZ, Zb = min(Za + WM_NZ, z1);
+    const uint32_t *g = gmap + vol * V;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int gy = Y0 + ty, gx = X0 + tx;
+    const bool mine = gy < H && gx < W;
+    double w1 = 0.0, w2 = 0.0, w3 = 0.0;  // xy-convolved map of the three previous planes
+    for (int z = Za - 3; z < Zb; ++z) {
+        const int buf = z & 1;
+        // map tile of plane z (zeros outside the volume)
+        for (int i = threadIdx.x; i < WM_EY * WM_EX; i += 256) {
+            const int lx = i % WM_EX, ly = i / WM_EX;
+            const int yy = Y0 - 3 + ly, xx = X0 - 3 + lx;
+            const bool in = z >= 0 && (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W;
+            sa[buf][ly][lx] = in ? (double)__ldg(g + (long long)z * P + (long long)yy * W + xx) : 0.0;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < WM_EZ * WM_EY * WM_TX; i += blockDim.x) {  // x pass: sa -> sb
-            const int lx = 3 + i % WM_TX, ly = (i / WM_TX) % WM_EY, lz = i / (WM_TX * WM_EY);
+        for (int i = threadIdx.x; i < WM_EY * WM_TX; i += 256) {  // x pass
+            const int lx = i % WM_TX, ly = i / WM_TX;
             double acc = 0.0;
 #pragma unroll
-            for (int d = 0; d < 4; ++d) acc = fma(k[d], sa[lz][ly][lx - d], acc);
-            sb[lz][ly][lx] = acc;
+            for (int d = 0; d < 4; ++d) acc = fma(k[d], sa[buf][ly][lx + 3 - d], acc);
+            sb[buf][ly][lx] = acc;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < WM_EZ * WM_TY * WM_TX; i += blockDim.x) {  // y pass: sb -> sa
-            const int lx = 3 + i % WM_TX, ly = 3 + (i / WM_TX) % WM_TY, lz = i / (WM_TX * WM_TY);
-            double acc = 0.0;
+        double w0 = 0.0;  // y pass
 #pragma unroll
-            for (int d = 0; d < 4; ++d) acc = fma(k[d], sb[lz][ly - d][lx], acc);
-            sa[lz][ly][lx] = acc;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < WM_TZ * WM_TY * WM_TX; i += blockDim.x) {  // z pass and the division
-            const int lx = 3 + i % WM_TX, ly = 3 + (i / WM_TX) % WM_TY, lz = 3 + i / (WM_TX * WM_TY);
-            const int gz = Z0 + lz - 3, gy = Y0 + ly - 3, gx = X0 + lx - 3;
-            if (gz < z1 && gy < H && gx < W) {
-                double den = 0.0;
-#pragma unroll
-                for (int d = 0; d < 4; ++d) den = fma(k[d], sa[lz - d][ly][lx], den);
-                const long long a = vol * V + ((long long)gz * H + gy) * W + gx;
-                out[a] = den > 0.0 ? (float)(((double)numq[a] / den) * inv) : fb[a];
+        for (int d = 0; d < 4; ++d) w0 = fma(k[d], sb[buf][ty + 3 - d][tx], w0);
+        if (z >= Za && mine) {
+            double den = fma(k[0], w0, 0.0);
+            den = fma(k[1], w1, den);
+            den = fma(k[2], w2, den);
+            den = fma(k[3], w3, den);
+            const long long a = vol * V + (long long)z * P + (long long)gy * W + gx;
+            const float y = den > 0.0 ? (float)(((double)__ldcs(numq + a) / den) * inv) : fb[a];
+            if (o.out) o.out[a] = y;
+            if (o.match) {
+                long long q = __float2ll_rn(__fmul_rn(y, o.mscale)) + (long long)o.ishift;
+                q = q < 0 ? 0 : (q > 65535 ? 65535 : q);
+                o.match[a] = (uint16_t)q;
             }
+            if (o.q16)
+                o.q16[a] = (uint16_t)(o.q_trunc ? quant1_trunc(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0)
+                                                : quant1(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0));
         }
-        __syncthreads();
+        w3 = w2;
+        w2 = w1;
+        w1 = w0;
     }
 }
 
@@ -223,6 +254,15 @@ __device__ __forceinline__ uint32_t quant1(float x, float osub, float oadd, floa
     if (!unit) v = __fdiv_rn(v, step);
     v = fminf(fmaxf(v, 0.0f), hi);
     return (uint32_t)__float2int_rn(v);
+}
+// truncating variant: np.maximum(x, 0).astype(int) (evaluate.py:202) followed by the uint16 cast of
+// compute_cratio (utils/img_util.py:420-423): toward zero, no upper clip, int64 -> uint16 wraps modulo 2^16
+__device__ __forceinline__ uint32_t quant1_trunc(float x, float osub, float oadd, float step, float hi, bool unit) {
+    (void)hi;
+    float v = __fadd_rn(__fsub_rn(x, osub), oadd);
+    if (!unit) v = __fdiv_rn(v, step);
+    v = fmaxf(v, 0.0f);  // NaN -> 0
+    return (uint32_t)(__float2ll_rz(v) & 0xFFFFll);
 }
 __global__ void __launch_bounds__(256) k_quantize(const float *__restrict__ in, uint16_t *__restrict__ out,
                                                   long long n, float osub, float oadd, float step) {
@@ -579,14 +619,30 @@ void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, 
                          cudaStream_t s) {
     k_to_match<<<grid_for(n >> 3, 256, 8), 256, 0, s>>>(in, out, n, cf, scale, ishift);
 }
-void b4d_launch_normalise_wm(const long long *numq, const long long *gmap, const float *fallback, float *out, int D,
+static void launch_norm(const long long *numq, const uint32_t *gmap, const float *fallback, const NormOut &o, int D,
+                        int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4], cudaStream_t s) {
+    if (z1 <= z0) return;
+    const long long tiles = (long long)nvol * ((z1 - z0 + WM_NZ - 1) / WM_NZ) * ((H + WM_TY - 1) / WM_TY) *
+                            ((W + WM_TX - 1) / WM_TX);
+    k_normalise_wm<<<(unsigned)tiles, 256, 0, s>>>(numq, gmap, fallback, o, D, H, W, nvol, z0, z1, inv_qscale, kf[0],
+                                                  kf[1], kf[2], kf[3]);
+}
+void b4d_launch_normalise_wm(const long long *numq, const uint32_t *gmap, const float *fallback, float *out, int D,
                              int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4],
                              cudaStream_t s) {
-    if (z1 <= z0) return;
-    const long long tiles = (long long)nvol * ((z1 - z0 + WM_TZ - 1) / WM_TZ) * ((H + WM_TY - 1) / WM_TY) *
-                            ((W + WM_TX - 1) / WM_TX);
-    k_normalise_wm<<<grid_for(tiles * 256, 256, 4), 256, 0, s>>>(numq, gmap, fallback, out, D, H, W, nvol, z0, z1,
-                                                                inv_qscale, kf[0], kf[1], kf[2], kf[3]);
+    NormOut o{};
+    o.out = out;
+    launch_norm(numq, gmap, fallback, o, D, H, W, nvol, z0, z1, inv_qscale, kf, s);
+}
+void b4d_launch_normalise_match(const long long *numq, const uint32_t *gmap, const float *fallback, float *out,
+                                uint16_t *match, float mscale, int ishift, int D, int H, int W, int nvol,
+                                float inv_qscale, const float kf[4], cudaStream_t s) {
+    NormOut o{};
+    o.out = out;
+    o.match = match;
+    o.mscale = mscale;
+    o.ishift = ishift;
+    launch_norm(numq, gmap, fallback, o, D, H, W, nvol, 0, D, inv_qscale, kf, s);
 }
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s) {

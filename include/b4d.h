@@ -236,6 +236,12 @@ int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]);
  *   out[3] = FFMA lane-ops/s.                                                */
 int b4d_measure_pipe_peaks(b4d_handle *h, double out[4]);
 
+/* Diagnostics: the fixed-point aggregation state the LAST filter stage of the last single-volume call left
+ * behind, copied to host arrays of n = D*H*W entries: numq = sum of the rounded numerator terms per voxel,
+ * wmap = sum of the 20-bit group weights per block origin.  The tests compare both with the oracle mirror's,
+ * integer for integer, which localises a difference to a reference block.  No reference-side counterpart. */
+int b4d_debug_accumulators(b4d_handle *h, int64_t *numq, int64_t *wmap, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

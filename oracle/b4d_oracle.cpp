@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -55,6 +56,7 @@ struct b4d_handle_impl {
     b4d_profile prof;
     int arith;  // 0 = mirror (float32, CUDA op order), 1 = f64 plain restatement
     int threads;
+    mutable std::vector<int64_t> last_numq, last_wmap;  // mirror: accumulators of the last filter stage
 };
 
 // ---------------------------------------------------------------- profile ---
@@ -388,8 +390,11 @@ struct MirrorTables {
     float win[LV];       // (w[z]*w[y])*w[x] in float32
     float kf[4];         // the per-axis factors w[n] (float32): the denominator convolves with them separably
     float tht[16];       // tht[m] = float(lambda*sigma*2^(m/2)), m = 6 - n + l
-    float gs[6];         // gs[l] = float(2^(-l/2)): group normalisation
-    float c1, c3;        // DCT-II-4 constants
+    // Wiener stage, unnormalised DCT butterflies: a raw coefficient with n odd positions (of x, y, z) at group
+    // level l has the true value raw * S_n * 2^(-l/2), S_n = (1/2)^(3-n) c3^n, c3 = cos(3 pi/8)/sqrt 2
+    float wa[24];        // [n][l] = float(S_n 2^(-l/2))
+    float wb[24];        // [n][l] = float(S_n^2 2^(-l))
+    float tq;            // float(1 + sqrt 2) = c1 / c3
     float sigma2;        // float(sigma)*float(sigma)
 };
 MirrorTables make_tables(const b4d_profile &p, float sigma) {
@@ -406,9 +411,14 @@ MirrorTables make_tables(const b4d_profile &p, float sigma) {
         double s = std::ldexp(1.0, m / 2) * ((m & 1) ? M_SQRT2 : 1.0);
         t.tht[m] = (float)((double)p.lambda_ht * (double)sigma * s);
     }
-    for (int l = 0; l < 6; ++l) t.gs[l] = (float)(std::ldexp(1.0, -(l / 2)) * ((l & 1) ? M_SQRT1_2 : 1.0));
-    t.c1 = (float)(std::cos(M_PI / 8.0) * M_SQRT1_2);
-    t.c3 = (float)(std::cos(3.0 * M_PI / 8.0) * M_SQRT1_2);
+    const double c3 = std::cos(3.0 * M_PI / 8.0) * M_SQRT1_2;
+    for (int n = 0; n < 4; ++n)
+        for (int l = 0; l < 6; ++l) {
+            const double sn = std::ldexp(1.0, -(3 - n)) * std::pow(c3, n);
+            t.wa[n * 6 + l] = (float)(sn * std::ldexp(1.0, -(l / 2)) * ((l & 1) ? M_SQRT1_2 : 1.0));
+            t.wb[n * 6 + l] = (float)(sn * sn * std::ldexp(1.0, -l));
+        }
+    t.tq = (float)(1.0 + M_SQRT2);
     t.sigma2 = sigma * sigma;
     return t;
 }
@@ -428,16 +438,18 @@ inline void haar4_inv(float *v, int s) {
     v[2 * s] = q + y3;
     v[3 * s] = q - y3;
 }
-inline void dct4_fwd(float *v, int s, float c1, float c3) {
+// DCT-II-4 in unnormalised even/odd form: X0 = a + b, X2 = a - b, X1 = t c + d, X3 = c - t d, t = 1 + sqrt 2;
+// true values 1/2 X0, 1/2 X2, c3 X1, c3 X3.  The inverse expects coefficients pre-scaled by the same factors.
+inline void dct4_fwd(float *v, int s, float tq) {
     float a = v[0] + v[3 * s], b = v[s] + v[2 * s], c = v[0] - v[3 * s], d = v[s] - v[2 * s];
-    v[0] = fmaf(0.5f, a, 0.5f * b);
-    v[2 * s] = fmaf(-0.5f, b, 0.5f * a);
-    v[s] = fmaf(c1, c, c3 * d);
-    v[3 * s] = fmaf(-c1, d, c3 * c);
+    v[0] = a + b;
+    v[2 * s] = a - b;
+    v[s] = fmaf(tq, c, d);
+    v[3 * s] = fmaf(-tq, d, c);
 }
-inline void dct4_inv(float *v, int s, float c1, float c3) {
-    float a = fmaf(0.5f, v[0], 0.5f * v[2 * s]), b = fmaf(-0.5f, v[2 * s], 0.5f * v[0]);
-    float c = fmaf(c1, v[s], c3 * v[3 * s]), d = fmaf(-c1, v[3 * s], c3 * v[s]);
+inline void dct4_inv(float *v, int s, float tq) {
+    float a = v[0] + v[2 * s], b = v[0] - v[2 * s];
+    float c = fmaf(tq, v[s], v[3 * s]), d = fmaf(-tq, v[3 * s], v[s]);
     v[0] = a + c;
     v[3 * s] = a - c;
     v[s] = b + d;
@@ -445,19 +457,17 @@ inline void dct4_inv(float *v, int s, float c1, float c3) {
 }
 template <bool DCT>
 inline void xf3_fwd(float *b, const MirrorTables &t) {
-    for (int i = 0; i < 16; ++i) DCT ? dct4_fwd(b + 4 * i, 1, t.c1, t.c3) : haar4_fwd(b + 4 * i, 1);
+    for (int i = 0; i < 16; ++i) DCT ? dct4_fwd(b + 4 * i, 1, t.tq) : haar4_fwd(b + 4 * i, 1);
     for (int z = 0; z < 4; ++z)
-        for (int x = 0; x < 4; ++x)
-            DCT ? dct4_fwd(b + 16 * z + x, 4, t.c1, t.c3) : haar4_fwd(b + 16 * z + x, 4);
-    for (int i = 0; i < 16; ++i) DCT ? dct4_fwd(b + i, 16, t.c1, t.c3) : haar4_fwd(b + i, 16);
+        for (int x = 0; x < 4; ++x) DCT ? dct4_fwd(b + 16 * z + x, 4, t.tq) : haar4_fwd(b + 16 * z + x, 4);
+    for (int i = 0; i < 16; ++i) DCT ? dct4_fwd(b + i, 16, t.tq) : haar4_fwd(b + i, 16);
 }
 template <bool DCT>
 inline void xf3_inv(float *b, const MirrorTables &t) {
-    for (int i = 0; i < 16; ++i) DCT ? dct4_inv(b + i, 16, t.c1, t.c3) : haar4_inv(b + i, 16);
+    for (int i = 0; i < 16; ++i) DCT ? dct4_inv(b + i, 16, t.tq) : haar4_inv(b + i, 16);
     for (int z = 0; z < 4; ++z)
-        for (int x = 0; x < 4; ++x)
-            DCT ? dct4_inv(b + 16 * z + x, 4, t.c1, t.c3) : haar4_inv(b + 16 * z + x, 4);
-    for (int i = 0; i < 16; ++i) DCT ? dct4_inv(b + 4 * i, 1, t.c1, t.c3) : haar4_inv(b + 4 * i, 1);
+        for (int x = 0; x < 4; ++x) DCT ? dct4_inv(b + 16 * z + x, 4, t.tq) : haar4_inv(b + 16 * z + x, 4);
+    for (int i = 0; i < 16; ++i) DCT ? dct4_inv(b + 4 * i, 1, t.tq) : haar4_inv(b + 4 * i, 1);
 }
 // in-place unnormalised Haar along the group, element k of block-major stack
 inline void ghaar_fwd(float *st, int kp) {
@@ -489,15 +499,8 @@ inline int spatial_class(int v) { return ((v & 3) >= 2) + (((v >> 2) & 3) >= 2) 
 constexpr float W_SCALE = 1048576.0f;  // 2^20
 constexpr float Q_LIMIT = 5.49e11f;    // < 2^39
 
-// Which DCT coefficient (cz*16 + cy*4 + cx) lane (zh, y, x), register rr of the
-// CUDA filter kernel holds after the forward transform (csrc/b4d_filter.cu):
-// along x and y lane position 0,1,2,3 holds output 0,2,3,1; along z (zh, rr) holds
-// output 2*zh + rr.
-inline int wiener_coeff(int lane, int rr) {
-    static const int pos2out[4] = {0, 2, 3, 1};
-    const int x = lane & 3, y = (lane >> 2) & 3, zh = lane >> 4;
-    return (2 * zh + rr) * 16 + pos2out[y] * 4 + pos2out[x];
-}
+// number of odd positions of a DCT coefficient index v = (z*4 + y)*4 + x: its scale class
+inline int dct_class(int v) { return (v & 1) + ((v >> 2) & 1) + ((v >> 4) & 1); }
 
 template <bool WIENER>
 void filter_mirror(const float *zf, const float *basic, const Geom &g, const Matches &m, int Ns,
@@ -527,10 +530,12 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
                         if (WIENER) est[k * LV + (z * 4 + y) * 4 + x] = basic[a];
                     }
         }
+        // Operation order of csrc/b4d_filter.cu: Haar along the GROUP first (layout A of the kernel), then the
+        // separable 3-D transform of every coefficient block (layout B), shrinkage, and back the same way.
         float weight;
         if (!WIENER) {
-            for (int k = 0; k < kp; ++k) xf3_fwd<false>(noisy + k * LV, t);
             ghaar_fwd(noisy, kp);
+            for (int k = 0; k < kp; ++k) xf3_fwd<false>(noisy + k * LV, t);
             int kept = 0;
             for (int k = 0; k < kp; ++k) {
                 const int l = group_level(k, lg);
@@ -547,54 +552,61 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
                 }
             }
             weight = 1.0f / (float)std::max(kept, 1);
-            ghaar_inv(noisy, kp);
             for (int k = 0; k < kp; ++k) xf3_inv<false>(noisy + k * LV, t);
+            ghaar_inv(noisy, kp);
         } else {
-            // basic-estimate stack first (gives the Wiener attenuation), then the noisy stack
-            for (int k = 0; k < kp; ++k) xf3_fwd<true>(est + k * LV, t);
             ghaar_fwd(est, kp);
-            for (int k = 0; k < kp; ++k) xf3_fwd<true>(noisy + k * LV, t);
+            for (int k = 0; k < kp; ++k) xf3_fwd<true>(est + k * LV, t);
             ghaar_fwd(noisy, kp);
-            // Wiener attenuation, elementwise; sum of W^2 in the kernel's order: lane
-            // (zh, y, x) of a warp owns two coefficients of every slot and chains
-            // fma over (slot ascending, register 0 then 1); the 32 partial sums meet in
-            // an xor butterfly.  Coefficient held by (lane, register): see wiener_coeff().
-            float wgt[32 * LV];
+            for (int k = 0; k < kp; ++k) xf3_fwd<true>(noisy + k * LV, t);
+            const bool dump = getenv("B4D_DUMP_REF") && atoll(getenv("B4D_DUMP_REF")) == ri;  // developer aid
+            auto dump_f = [&](int sec, const float *a) {
+                for (int k = 0; k < kp; ++k)
+                    for (int v = 0; v < LV; ++v) {
+                        uint32_t b;
+                        std::memcpy(&b, &a[k * LV + v], 4);
+                        printf("D %d %d %d %08x\n", sec, k, v, b);
+                    }
+            };
+            if (dump) {
+                dump_f(0, est);
+                dump_f(1, noisy);
+            }
+            // Wiener attenuation, elementwise.  Sum of W^2 in the kernel's order: lane k owns coefficient block
+            // k and chains fma over its 64 coefficients as 32 packed pairs — for z, for y: the pair of x positions
+            // (0, 2), then (1, 3) — low halves in one chain, high halves in the other; the two chains are added,
+            // and the 32 lane sums meet in an xor butterfly (16, 8, 4, 2, 1).
+            float part[32];
+            for (int k = 0; k < 32; ++k) part[k] = 0.0f;
             for (int k = 0; k < kp; ++k) {
                 const int l = group_level(k, lg);
-                for (int v = 0; v < LV; ++v) {
-                    const float yn = est[k * LV + v] * t.gs[l];
-                    const float y2 = yn * yn;
-                    const float w = y2 / (y2 + t.sigma2);
-                    wgt[k * LV + v] = w;
-                    noisy[k * LV + v] = ldexpf(noisy[k * LV + v] * w, -l);
-                }
-            }
-            // one chain per 16-slot half of the group (the kernel gives each half to one warp
-            // of a pair when the group has 32 blocks); halves are added last
-            float half_sum[2] = {0.0f, 0.0f};
-            for (int h = 0; h * 16 < kp; ++h) {
-                float part[32];
-                for (int lane = 0; lane < 32; ++lane) {
-                    float acc = 0.0f;
-                    for (int k = h * 16; k < std::min(kp, h * 16 + 16); ++k)
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const float w = wgt[k * LV + wiener_coeff(lane, rr)];
-                            acc = fmaf(w, w, acc);
+                float acc_lo = 0.0f, acc_hi = 0.0f;
+                for (int zy = 0; zy < 16; ++zy)
+                    for (int o = 0; o < 2; ++o)
+                        for (int h = 0; h < 2; ++h) {
+                            const int v = zy * 4 + o + 2 * h;  // x position: (0 | 2) for o = 0, (1 | 3) for o = 1
+                            const int n = dct_class(v);
+                            const float yn = est[k * LV + v] * t.wa[n * 6 + l];
+                            const float y2 = yn * yn;
+                            const float nd = (-t.sigma2) - y2;
+                            const float w = y2 / (-nd);
+                            if (h == 0) acc_lo = fmaf(w, w, acc_lo);
+                            else acc_hi = fmaf(w, w, acc_hi);
+                            noisy[k * LV + v] = (noisy[k * LV + v] * w) * t.wb[n * 6 + l];
                         }
-                    part[lane] = acc;
-                }
-                for (int mm = 16; mm >= 1; mm >>= 1) {  // xor-butterfly reduction, as __shfl_xor does
-                    float nx[32];
-                    for (int k = 0; k < 32; ++k) nx[k] = part[k] + part[k ^ mm];
-                    std::memcpy(part, nx, sizeof(nx));
-                }
-                half_sum[h] = part[0];
+                part[k] = acc_lo + acc_hi;
             }
-            const float sumw = kp > 16 ? half_sum[0] + half_sum[1] : half_sum[0];
-            weight = 1.0f / fmaxf(sumw, 1.0f);
-            ghaar_inv(noisy, kp);
+            for (int mm = 16; mm >= 1; mm >>= 1) {  // xor-butterfly reduction, as __shfl_xor does
+                float nx[32];
+                for (int k = 0; k < 32; ++k) nx[k] = part[k] + part[k ^ mm];
+                std::memcpy(part, nx, sizeof(nx));
+            }
+            weight = 1.0f / fmaxf(part[0], 1.0f);
+            if (dump) dump_f(2, noisy);
             for (int k = 0; k < kp; ++k) xf3_inv<true>(noisy + k * LV, t);
+            if (dump) dump_f(5, noisy);
+            ghaar_inv(noisy, kp);
+            if (dump) dump_f(3, noisy);
         }
         // Weight-map contract: the group weight is quantised once, qg = rint(w * 2^20); the numerator
         // term of a voxel uses the float32 weight float(qg) * win[v] (limb format as before), the
@@ -612,6 +624,12 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
                         const float wqf = ((float)qg * t.win[v]) * qscale;
                         const float tq = fminf(fmaxf(wqf * noisy[k * LV + v], -Q_LIMIT), Q_LIMIT);
                         const int64_t qn = llrintf(tq);
+                        if (WIENER && getenv("B4D_DUMP_REF") && atoll(getenv("B4D_DUMP_REF")) == ri) {
+                            uint32_t b0, b1;
+                            std::memcpy(&b0, &tq, 4);
+                            std::memcpy(&b1, &wqf, 4);
+                            printf("D 6 %d %d %08x\nD 7 %d %d %08x\n", k, v, b0, k, v, b1);
+                        }
 #pragma omp atomic
                         numq[a] += qn;
                     }
@@ -763,6 +781,8 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     filter_mirror<false>(zf.data(), nullptr, g1, m, p.search_ht, t, mm.scale, numq, denq);
     den_from_weight_map(denq, g1, t, den);
     for (int64_t i = 0; i < V; ++i) basic[i] = den[i] > 0 ? (float)(((double)numq[i] / den[i]) * inv_q) : zf[i];
+    h->last_numq = numq;
+    h->last_wmap = denq;
     if (p.stages == 1) {
         std::memcpy(out, basic.data(), V * sizeof(float));
         return 0;
@@ -774,6 +794,8 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     filter_mirror<true>(zf.data(), basic.data(), g2, m, p.search_wie, t, mm.scale, numq, denq);
     den_from_weight_map(denq, g2, t, den);
     for (int64_t i = 0; i < V; ++i) out[i] = den[i] > 0 ? (float)(((double)numq[i] / den[i]) * inv_q) : basic[i];
+    h->last_numq = numq;
+    h->last_wmap = denq;
     return 0;
 }
 
@@ -1052,6 +1074,14 @@ int b4d_last_timings(b4d_handle *, float *, int64_t *) {
 }
 int b4d_measure_pipe_peaks(b4d_handle *, double *) {
     return fail(B4D_ERR_UNSUPPORTED, "no device in the oracle");
+}
+int b4d_debug_accumulators(b4d_handle *hh, int64_t *numq, int64_t *wmap, int64_t n) {
+    auto *h = reinterpret_cast<b4d_handle_impl *>(hh);
+    if (!h || !numq || !wmap || (int64_t)h->last_numq.size() != n)
+        return fail(B4D_ERR_INVALID, "no mirror accumulators of that size");
+    std::memcpy(numq, h->last_numq.data(), (size_t)n * sizeof(int64_t));
+    std::memcpy(wmap, h->last_wmap.data(), (size_t)n * sizeof(int64_t));
+    return 0;
 }
 
 }  // extern "C"

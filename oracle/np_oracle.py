@@ -241,6 +241,14 @@ class Oracle:
         )
         return out
 
+    def accumulators(self, n):
+        """(numq, wmap) int64 arrays of the last mirror filter stage (see b4d_debug_accumulators)."""
+        numq = np.empty(n, dtype=np.int64)
+        wmap = np.empty(n, dtype=np.int64)
+        _check(load().b4d_debug_accumulators(self._h, numq.ctypes.data_as(ctypes.c_void_p),
+                                             wmap.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n)))
+        return numq, wmap
+
     def denoise_slab(self, slab, z_begin, z_total, own_begin, own_end, sigma):
         slab = np.ascontiguousarray(slab, dtype=np.uint16)
         out = np.empty((own_end - own_begin,) + slab.shape[1:], dtype=np.float32)
