@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     noise_scaled_step,
     precompute_targets,
     quantize,
+    denoise_quantized,
     tile_stats,
 )
 from .cache import load_patch_cache, write_patch_cache  # noqa: F401
@@ -41,6 +42,7 @@ __all__ = [
     "noise_scaled_step",
     "precompute_targets",
     "quantize",
+    "denoise_quantized",
     "tile_stats",
     "slab_plan",
     "bind_to_gpu_numa",

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libb4d.so")
+# B4D_LIB: developer override (kernel variants built side by side for A/B timing); the default is the in-tree build
+LIB_PATH = os.environ.get("B4D_LIB") or os.path.join(_PKG, "libb4d.so")
 
 ABI_VERSION = 1
 T_NAMES = ("prep", "match1", "filter1", "norm1", "match2", "filter2", "norm2", "spare")
@@ -41,6 +42,10 @@ EXPORTS = (
     "b4d_last_match_stats",
     "b4d_measure_pipe_peaks",
     "b4d_debug_accumulators",
+    "b4d_quantize_trunc_u16",
+    "b4d_denoise_q16_u16",
+    "b4d_denoise_slab_q16_u16",
+    "b4d_slab_stage2_q16",
 )
 
 

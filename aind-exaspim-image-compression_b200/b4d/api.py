@@ -227,16 +227,19 @@ class Denoiser:
         )
         return outs[0], outs[1]
 
-    def denoise_slab(self, slab, z_begin, z_total, own_begin, own_end, sigma, out=None):
+    def denoise_slab(self, slab, z_begin, z_total, own_begin, own_end, sigma, out=None, quantize=None):
         """One z-slab (uint16, with halos) of a larger volume -> float32 owned planes.
-        `out` (NumPy path only) receives the result in place, e.g. a pinned buffer."""
+        `out` (NumPy path only) receives the result in place, e.g. a pinned buffer.
+        quantize = (offset_sub, offset_add, step[, truncate]): the fused denoise -> offset -> quantize path, the
+        result is the uint16 volume K7 would give on the float32 output (2 bytes per voxel leave the device)."""
+        odt_np, odt_t = (np.float32, "float32") if quantize is None else (np.uint16, "uint16")
         if _is_torch(slab):
             import torch
 
             sc = slab.contiguous()
             if sc.dtype != torch.uint16 or sc.ndim != 3:
                 raise ValueError("slab must be a 3-D uint16 tensor")
-            out = torch.empty((own_end - own_begin,) + tuple(sc.shape[1:]), dtype=torch.float32, device=sc.device)
+            out = torch.empty((own_end - own_begin,) + tuple(sc.shape[1:]), dtype=getattr(torch, odt_t), device=sc.device)
             on_dev = sc.is_cuda
             if on_dev:
                 torch.cuda.current_stream(sc.device).synchronize()
@@ -247,11 +250,22 @@ class Denoiser:
                 raise ValueError("slab must be a 3-D uint16 array")
             oshape = (own_end - own_begin,) + sc.shape[1:]
             if out is None:
-                out = np.empty(oshape, dtype=np.float32)
-            elif out.shape != oshape or out.dtype != np.float32 or not out.flags.c_contiguous:
-                raise ValueError("out must be a C-contiguous float32 array of shape %r" % (oshape,))
+                out = np.empty(oshape, dtype=odt_np)
+            elif out.shape != oshape or out.dtype != odt_np or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous %s array of shape %r" % (odt_t, oshape))
             on_dev = False
             in_ptr, out_ptr, shape = sc.ctypes.data, out.ctypes.data, sc.shape
+        if quantize is not None:
+            q = tuple(quantize) + (False,) * (4 - len(quantize))
+            _lib.check(
+                self.lib.b4d_denoise_slab_q16_u16(
+                    self._h, ctypes.c_void_p(in_ptr), _lib.shape3(shape), ctypes.c_int64(z_begin),
+                    ctypes.c_int64(z_total), ctypes.c_int64(own_begin), ctypes.c_int64(own_end), ctypes.c_float(sigma),
+                    ctypes.c_float(q[0]), ctypes.c_float(q[1]), ctypes.c_float(q[2]), int(bool(q[3])),
+                    ctypes.c_void_p(out_ptr), int(on_dev), int(on_dev),
+                )
+            )
+            return out
         _lib.check(
             self.lib.b4d_denoise_slab_u16(
                 self._h,
@@ -330,24 +344,38 @@ class Denoiser:
             _lib.check(self.lib.b4d_slab_basic_planes(self._h, ctypes.c_int64(plane0), ctypes.c_int64(n),
                                                       ctypes.c_void_p(ptr), 1, int(on_dev)))
 
-    def slab_stage2(self, own_begin, own_end, out=None, device=None):
+    def slab_stage2(self, own_begin, own_end, out=None, device=None, quantize=None):
         """Stage 2 on the completed basic estimate -> float32 owned planes (NumPy, or torch on
-        `device`; `out` may be a preallocated NumPy array, e.g. pinned)."""
+        `device`; `out` may be a preallocated NumPy array, e.g. pinned).  quantize = (offset_sub, offset_add,
+        step[, truncate]): uint16 output of the fused quantizer instead (see denoise_slab)."""
         oshape = (int(own_end - own_begin),) + self._slab_shape[1:]
+        odt_np, odt_t = (np.float32, "float32") if quantize is None else (np.uint16, "uint16")
         if device is not None:
             import torch
 
-            out = torch.empty(oshape, dtype=torch.float32, device=device)
+            out = torch.empty(oshape, dtype=getattr(torch, odt_t), device=device)
             ptr, on_dev = out.data_ptr(), True
         else:
             if out is None:
-                out = np.empty(oshape, dtype=np.float32)
-            elif out.shape != oshape or out.dtype != np.float32 or not out.flags.c_contiguous:
-                raise ValueError("out must be a C-contiguous float32 array of shape %r" % (oshape,))
+                out = np.empty(oshape, dtype=odt_np)
+            elif out.shape != oshape or out.dtype != odt_np or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous %s array of shape %r" % (odt_t, oshape))
             ptr, on_dev = out.ctypes.data, False
+        if quantize is not None:
+            q = tuple(quantize) + (False,) * (4 - len(quantize))
+            _lib.check(self.lib.b4d_slab_stage2_q16(self._h, ctypes.c_int64(own_begin), ctypes.c_int64(own_end),
+                                                    ctypes.c_float(q[0]), ctypes.c_float(q[1]), ctypes.c_float(q[2]),
+                                                    int(bool(q[3])), ctypes.c_void_p(ptr), int(on_dev)))
+            return out
         _lib.check(self.lib.b4d_slab_stage2(self._h, ctypes.c_int64(own_begin), ctypes.c_int64(own_end),
                                             ctypes.c_void_p(ptr), int(on_dev)))
         return out
+
+    def denoise_quantized(self, vol, sigma, offset_sub=0.0, offset_add=0.0, step=1.0, truncate=False, out=None):
+        """denoise -> offset -> quantize of one uint16 volume in one call (b4d_denoise_q16_u16): the uint16 volume
+        `quantize(denoise(vol, sigma), offset_sub, offset_add, step, truncate)` would give, bit for bit."""
+        D = int(vol.shape[0])
+        return self.denoise_slab(vol, 0, D, 0, D, sigma, out=out, quantize=(offset_sub, offset_add, step, truncate))
 
     def match_stage1(self, vol, sigma):
         """Instrumented stage-1 matcher: (idx[R,K] int32, ssd[R,K] uint64, count[R] int32)."""
@@ -373,8 +401,10 @@ class Denoiser:
         )
         return idx, ssd, cnt
 
-    def quantize(self, x, offset_sub=0.0, offset_add=0.0, step=1.0):
-        """K7: rint(clip((x - offset_sub + offset_add)/step, 0, 65535/step)) -> uint16."""
+    def quantize(self, x, offset_sub=0.0, offset_add=0.0, step=1.0, truncate=False):
+        """K7: rint(clip((x - offset_sub + offset_add)/step, 0, 65535/step)) -> uint16.
+        truncate=True: the evaluator's variant, np.maximum(v, 0).astype(int) cast to uint16 (evaluate.py:202,
+        utils/img_util.py:420-423): toward zero, no upper clip, wrapping modulo 2^16."""
         if _is_torch(x):
             import torch
 
@@ -391,8 +421,9 @@ class Denoiser:
             out = np.empty(xc.shape, dtype=np.uint16)
             on_dev = False
             in_ptr, out_ptr, n = xc.ctypes.data, out.ctypes.data, xc.size
+        fn = self.lib.b4d_quantize_trunc_u16 if truncate else self.lib.b4d_quantize_u16
         _lib.check(
-            self.lib.b4d_quantize_u16(
+            fn(
                 self._h,
                 ctypes.c_void_p(in_ptr),
                 ctypes.c_int64(n),
@@ -667,8 +698,13 @@ def make_foreground_mask(raw_u16, offset=0.0, k=6.0, dilate=1, device=None):
     return get_denoiser(device).foreground_mask(raw_u16, offset, k, dilate)
 
 
-def quantize(x, offset_sub=0.0, offset_add=0.0, step=1.0, device=None):
-    return get_denoiser(device).quantize(x, offset_sub, offset_add, step)
+def quantize(x, offset_sub=0.0, offset_add=0.0, step=1.0, device=None, truncate=False):
+    return get_denoiser(device).quantize(x, offset_sub, offset_add, step, truncate)
+
+
+def denoise_quantized(vol, sigma, offset_sub=0.0, offset_add=0.0, step=1.0, truncate=False, device=None):
+    """Denoise -> background-offset subtract -> (noise-scaled) quantize of one uint16 volume, fused on the device."""
+    return get_denoiser(device).denoise_quantized(vol, sigma, offset_sub, offset_add, step, truncate)
 
 
 def noise_scaled_step(sigma_tile, kappa):

@@ -64,10 +64,11 @@ def exchange_planes(send_down, send_up, recv_below, recv_above, rank, world, gro
 
 
 def denoise_slab_exchange(denoiser, slab, z_begin, z_total, own_begin, own_end, sigma, rank, world, device=None,
-                          out=None, group=None):
+                          out=None, group=None, quantize=None):
     """One rank's part of the exchange variant: stage 1 on the slab (halo `exchange_halo`), swap
     the exact basic-estimate planes next to each interior face with the neighbours, stage 2.
-    `device` = the rank's torch CUDA device (planes then travel device to device)."""
+    `device` = the rank's torch CUDA device (planes then travel device to device).
+    quantize = (offset_sub, offset_add, step[, truncate]): uint16 output of the fused quantizer."""
     import torch
 
     denoiser.slab_stage1(slab, z_begin, z_total, sigma)
@@ -92,7 +93,7 @@ def denoise_slab_exchange(denoiser, slab, z_begin, z_total, own_begin, own_end, 
         denoiser.slab_set_basic(0, recv_below if device is not None else recv_below.numpy())
     if recv_above is not None:
         denoiser.slab_set_basic(o1, recv_above if device is not None else recv_above.numpy())
-    return denoiser.slab_stage2(own_begin, own_end, out=out, device=device if out is None else None)
+    return denoiser.slab_stage2(own_begin, own_end, out=out, device=device if out is None else None, quantize=quantize)
 
 
 def denoise_volume_sharded(get_slab, z_total, sigma, denoiser, world=1, rank=0, exchange=False, device=None):

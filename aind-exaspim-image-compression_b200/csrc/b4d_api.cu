@@ -303,9 +303,15 @@ struct StageClock {
 // finished planes is normalised and copied out on a second stream while the next chunks
 // still compute — the device-to-host copy (4 B/voxel over PCIe) hides behind the filter.
 struct HostSink {
-    float *host = nullptr;
+    void *host = nullptr;  // float32, or uint16 with a QuantSpec
     long long p0 = 0, p1 = 0;
     bool done = false;  // set when run_pipeline delivered the result itself
+};
+// Fused K6 + K7: the last normalise writes q = quantize(result) as uint16 instead of the float32 result
+// (d_out of run_pipeline then points at uint16 storage; 2 B/voxel leave the device instead of 4).
+struct QuantSpec {
+    float sub = 0.f, add = 0.f, step = 1.f;
+    int trunc = 0;
 };
 
 // Where the input comes from when it is a uint16 volume in HOST memory: it is uploaded in z
@@ -328,7 +334,8 @@ bool can_stream_upload(const b4d_handle *h, const Plan &pl) {
 // phase 0 = both stages; 1 = stage 1 only (basic estimate left in h->basic); 2 = stage 2 only
 // (h->basic holds the basic estimate, possibly completed by a neighbour exchange).
 int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u, const MatchMap &mm_in, float sigma,
-                 float *d_out, StageClock &clk, int phase = 0, HostSink *sink = nullptr, HostSource *src = nullptr) {
+                 float *d_out, StageClock &clk, int phase = 0, HostSink *sink = nullptr, HostSource *src = nullptr,
+                 const QuantSpec *q = nullptr) {
     const b4d_profile &p = h->prof;
     MatchMap mm = mm_in;
     const long long V = (long long)pl.D * pl.H * pl.W, TV = V * pl.nvol;
@@ -391,6 +398,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     };
 
     float *d_basic = (p.stages == 1 && phase == 0) ? d_out : h->basic.as<float>();
+    bool fused_match = false;
     MatchParams mp;
     FilterParams fp;
     if (phase != 2) {
@@ -465,7 +473,15 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.gmap = h->gmap.as<uint32_t>();
     if (R1 > 0) b4d_launch_filter(fp, false, s);
     clk.mark(B4D_T_FILTER1, 1);
-    normalise(d_zf, d_basic);
+    if (phase == 0 && p.stages == 2) {
+        // the normalise kernel also writes the matching image of stage 2 (rint(basic * scale) + shift): the
+        // separate conversion pass (4 B read + 2 B write per voxel) is not needed
+        b4d_launch_normalise_match(h->numq.as<long long>(), h->gmap.as<uint32_t>(), d_zf, d_basic, d_u, mm.scale,
+                                   mm.ishift, pl.D, pl.H, pl.W, pl.nvol, 1.0f / mm.scale, tab.kf, s);
+        fused_match = true;
+    } else {
+        normalise(d_zf, d_basic);
+    }
     clk.mark(B4D_T_NORM1, 1);
     CU_TRY(cudaGetLastError());
     }
@@ -489,7 +505,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     }
 
     // ---- stage 2: Wiener, matching on the basic estimate
-    b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
+    if (!fused_match) b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
     B4D_TRY(zero_acc());
     b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
     clk.mark(B4D_T_PREP, 3);
@@ -505,7 +521,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     const long long P = (long long)pl.H * pl.W;
     constexpr int NCH = 8;
     const int nseg_ch = (sink && sink->host && pl.nvol == 1 && R2 > 0 && (P & 3) == 0 && TV >= h->pipeline_min_voxels)
-                            ? b4d_filter_segments(fp, NCH)
+                            ? b4d_filter_segments(fp, true, NCH)
                             : 0;
     if (nseg_ch >= NCH && nseg_ch % NCH == 0) {
         // chunked: launch everything on the compute stream first (events between the chunks), then
@@ -530,12 +546,19 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
             CU_TRY(cudaStreamWaitEvent(h->copy_stream, evs[c], 0));
             if (zfin > zdone) {
                 // origins below zfin are final as well: a block touches its own origin plane
-                b4d_launch_normalise_wm(h->numq.as<long long>(), h->gmap.as<uint32_t>(), d_basic, d_out, pl.D, pl.H,
-                                        pl.W, 1, (int)zdone, (int)zfin, 1.0f / mm.scale, tab.kf, h->copy_stream);
+                if (q)
+                    b4d_launch_normalise_q16(h->numq.as<long long>(), h->gmap.as<uint32_t>(), d_basic,
+                                             reinterpret_cast<uint16_t *>(d_out), pl.D, pl.H, pl.W, 1, (int)zdone, (int)zfin,
+                                             1.0f / mm.scale, tab.kf, q->sub, q->add, q->step, q->trunc, h->copy_stream);
+                else
+                    b4d_launch_normalise_wm(h->numq.as<long long>(), h->gmap.as<uint32_t>(), d_basic, d_out, pl.D, pl.H,
+                                            pl.W, 1, (int)zdone, (int)zfin, 1.0f / mm.scale, tab.kf, h->copy_stream);
                 const long long a = std::max(zdone, sink->p0), b = std::min(zfin, sink->p1);
+                const size_t esz = q ? sizeof(uint16_t) : sizeof(float);
                 if (b > a)
-                    CU_TRY(copy_out(h, sink->host + (a - sink->p0) * P, d_out + a * P, (size_t)(b - a) * P * sizeof(float),
-                                    0, h->copy_stream));
+                    CU_TRY(copy_out(h, static_cast<char *>(sink->host) + (size_t)(a - sink->p0) * P * esz,
+                                    reinterpret_cast<char *>(d_out) + (size_t)a * P * esz, (size_t)(b - a) * P * esz, 0,
+                                    h->copy_stream));
                 zdone = zfin;
             }
         }
@@ -547,14 +570,24 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     }
     if (R2 > 0) b4d_launch_filter(fp, true, s);
     clk.mark(B4D_T_FILTER2, 1);
-    normalise(d_basic, d_out);
+    if (q)
+        b4d_launch_normalise_q16(h->numq.as<long long>(), h->gmap.as<uint32_t>(), d_basic,
+                                 reinterpret_cast<uint16_t *>(d_out), pl.D, pl.H, pl.W, pl.nvol, 0, pl.D, 1.0f / mm.scale,
+                                 tab.kf, q->sub, q->add, q->step, q->trunc, s);
+    else
+        normalise(d_basic, d_out);
     clk.mark(B4D_T_NORM2, 1);
     CU_TRY(cudaGetLastError());
     return 0;
 }
 
 // float32 input -> matching map (shift, scale); mirrors oracle derive_match_map.
-int derive_match_map(b4d_handle *h, const float *d_in, long long n, float sigma, MatchMap *mm) {
+// Float data whose magnitude (in matching steps) is far above its range — a large DC level — would push the
+// fixed-point numerator terms (20-bit weight x value) past their 2^39 clamp.  Such inputs are denoised on
+// z - c0 and c0 is added back at the end (BM4D is translation equivariant); *centre receives c0, or 0 when no
+// centring is needed: count-scale data (|z| <= 65535 at scale 1) never is, so the common paths are untouched.
+constexpr double CENTRE_LIMIT = 131072.0;  // 2^17 matching steps
+int derive_match_map(b4d_handle *h, const float *d_in, long long n, float sigma, MatchMap *mm, float *centre = nullptr) {
     cudaStream_t s = h->stream;
     float z0 = 0.f;
     CU_TRY(cudaMemcpyAsync(&z0, d_in, sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -566,29 +599,36 @@ int derive_match_map(b4d_handle *h, const float *d_in, long long n, float sigma,
     std::vector<double> part((size_t)nb * 6);
     CU_TRY(cudaMemcpyAsync(part.data(), h->partial.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
-    double dev = 0, lo = 1e300, hi = -1e300, zlo = 1e300, zhi = -1e300;
+    double dev = 0, lo = 1e300, hi = -1e300, zlo = 1e300, zhi = -1e300, nonfinite = 0;
     for (int b = 0; b < nb; ++b) {
         dev = std::max(dev, part[b * 6 + 0]);
         lo = std::min(lo, part[b * 6 + 1]);
         hi = std::max(hi, part[b * 6 + 2]);
         zlo = std::min(zlo, part[b * 6 + 3]);
         zhi = std::max(zhi, part[b * 6 + 4]);
+        nonfinite = std::max(nonfinite, part[b * 6 + 5]);
     }
-    if (!(std::isfinite(zlo) && std::isfinite(zhi))) return fail(B4D_ERR_INVALID, "input contains non-finite values");
+    if (nonfinite > 0 || !(std::isfinite(zlo) && std::isfinite(zhi)))
+        return fail(B4D_ERR_INVALID, "input contains non-finite values (NaN or infinity)");
     if (dev <= 1.0 / 64.0 && hi - lo <= 65535.0) {
         mm->integral = 1;
         mm->scale = 1.0f;
         mm->cf = (float)c;
         mm->ishift = centre_shift(lo, hi);
-        return 0;
+    } else {
+        const double range = std::max(zhi - zlo, 1e-30);
+        const int e_range = (int)std::floor(std::log2(65535.0 / range));
+        const int e_sigma = (int)std::floor(std::log2(64.0 / (double)sigma));
+        mm->integral = 0;
+        mm->scale = (float)std::ldexp(1.0, std::min(e_range, e_sigma));
+        mm->cf = 0.0f;
+        mm->ishift = centre_shift(std::floor(zlo * (double)mm->scale), std::ceil(zhi * (double)mm->scale));
     }
-    const double range = std::max(zhi - zlo, 1e-30);
-    const int e_range = (int)std::floor(std::log2(65535.0 / range));
-    const int e_sigma = (int)std::floor(std::log2(64.0 / (double)sigma));
-    mm->integral = 0;
-    mm->scale = (float)std::ldexp(1.0, std::min(e_range, e_sigma));
-    mm->cf = 0.0f;
-    mm->ishift = centre_shift(std::floor(zlo * (double)mm->scale), std::ceil(zhi * (double)mm->scale));
+    if (centre) {
+        const double peak = std::max(std::fabs(zlo), std::fabs(zhi)) * (double)mm->scale;
+        *centre = 0.0f;
+        if (peak > CENTRE_LIMIT) *centre = mm->integral ? (float)std::rint(0.5 * (lo + hi)) : (float)(0.5 * (zlo + zhi));
+    }
     return 0;
 }
 
@@ -665,6 +705,7 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
             d_out = h->out.as<float>();
         }
         MatchMap mm;
+        float centre = 0.0f;
         const float *d_zf = nullptr;
         uint16_t *d_u = h->u16.as<uint16_t>();
         clk.mark(-1, 0);
@@ -674,18 +715,23 @@ int denoise_batch(b4d_handle *h, const T *in, int64_t n, const int64_t shape[3],
             d_zf = h->zf.as<float>();
             d_u = h->in.as<uint16_t>();  // the staged copy doubles as the matching image
         } else {
-            B4D_TRY(derive_match_map(h, h->in.as<float>(), TV, sigma, &mm));
+            B4D_TRY(derive_match_map(h, h->in.as<float>(), TV, sigma, &mm, &centre));
+            if (centre != 0.0f) {  // large DC level: denoise z - c0 (in the scratch copy), add c0 back at the end
+                b4d_launch_add_scalar(h->in.as<float>(), TV, -centre, s);
+                B4D_TRY(derive_match_map(h, h->in.as<float>(), TV, sigma, &mm));
+            }
             b4d_launch_to_match(h->in.as<float>(), h->u16.as<uint16_t>(), TV, mm.cf, mm.scale, mm.ishift, s);
             d_zf = h->in.as<float>();
         }
         clk.mark(B4D_T_PREP, 2);
         HostSink sink;
-        if (!out_dev && nb == 1 && h->prof.stages == 2) {
+        if (!out_dev && nb == 1 && h->prof.stages == 2 && centre == 0.0f) {
             sink.host = out + i0 * V;
             sink.p0 = 0;
             sink.p1 = pl.D;
         }
         B4D_TRY(run_pipeline(h, pl, d_zf, d_u, mm, sigma, d_out, clk, 0, &sink, &src));
+        if (centre != 0.0f) b4d_launch_add_scalar(d_out, TV, centre, s);
         if (!sink.done && d_out != out + i0 * V)
             CU_TRY(copy_out(h, out + i0 * V, d_out, (size_t)TV * sizeof(float), out_dev, s));
         CU_TRY(cudaStreamSynchronize(s));
@@ -940,10 +986,13 @@ int b4d_targets_u16(b4d_handle *h, const uint16_t *in, int64_t n, const int64_t 
     return 0;
 }
 
-int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
-                         int64_t z_total, int64_t own_begin, int64_t own_end, float sigma, float *out,
-                         int in_on_device, int out_on_device) {
+static int denoise_slab_impl(b4d_handle *h, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
+                             int64_t z_total, int64_t own_begin, int64_t own_end, float sigma, void *out,
+                             int in_on_device, int out_on_device, const QuantSpec *q) {
     B4D_TRY(common_checks(h, in, out, shape, sigma));
+    if (q && h->prof.stages != 2) return fail(B4D_ERR_INVALID, "quantized output needs stages = 2");
+    if (q && !(q->step >= 1.0f)) return fail(B4D_ERR_INVALID, "step must be >= 1");
+    const size_t esz = q ? sizeof(uint16_t) : sizeof(float);
     if (z_begin < 0 || z_begin + shape[0] > z_total || own_begin < z_begin || own_end > z_begin + shape[0] ||
         own_begin >= own_end)
         return fail(B4D_ERR_INVALID, "slab / owned range inconsistent");
@@ -982,14 +1031,39 @@ int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[
         sink.p1 = own_end - z_begin;
     }
     B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, sigma, h->out.as<float>(), clk, 0, &sink,
-                         &src));
+                         &src, q));
     if (!sink.done)
-        CU_TRY(copy_out(h, out, h->out.as<float>() + (own_begin - z_begin) * P,
-                        (size_t)(own_end - own_begin) * P * sizeof(float), out_on_device, s));
+        CU_TRY(copy_out(h, out, h->out.as<char>() + (size_t)(own_begin - z_begin) * P * esz,
+                        (size_t)(own_end - own_begin) * P * esz, out_on_device, s));
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
+}
+int b4d_denoise_slab_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
+                         int64_t z_total, int64_t own_begin, int64_t own_end, float sigma, float *out,
+                         int in_on_device, int out_on_device) {
+    return denoise_slab_impl(h, in, shape, z_begin, z_total, own_begin, own_end, sigma, out, in_on_device,
+                             out_on_device, nullptr);
+}
+int b4d_denoise_slab_q16_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
+                             int64_t z_total, int64_t own_begin, int64_t own_end, float sigma, float offset_sub,
+                             float offset_add, float step, int truncate, uint16_t *out, int in_on_device,
+                             int out_on_device) {
+    QuantSpec q;
+    q.sub = offset_sub;
+    q.add = offset_add;
+    q.step = step;
+    q.trunc = truncate;
+    return denoise_slab_impl(h, in, shape, z_begin, z_total, own_begin, own_end, sigma, out, in_on_device,
+                             out_on_device, &q);
+}
+int b4d_denoise_q16_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], float sigma, float offset_sub,
+                        float offset_add, float step, int truncate, uint16_t *out, int in_on_device,
+                        int out_on_device) {
+    if (!shape) return fail(B4D_ERR_INVALID, "NULL argument");
+    return b4d_denoise_slab_q16_u16(h, in, shape, 0, shape[0], 0, shape[0], sigma, offset_sub, offset_add, step,
+                                    truncate, out, in_on_device, out_on_device);
 }
 
 static Plan slab_plan_of(const b4d_handle *h) {
@@ -1064,8 +1138,11 @@ int b4d_slab_basic_planes(b4d_handle *h, int64_t plane0, int64_t nplanes, float 
     return 0;
 }
 
-int b4d_slab_stage2(b4d_handle *h, int64_t own_begin, int64_t own_end, float *out, int out_on_device) {
+static int slab_stage2_impl(b4d_handle *h, int64_t own_begin, int64_t own_end, void *out, int out_on_device,
+                           const QuantSpec *q) {
     if (!h || !out) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (q && !(q->step >= 1.0f)) return fail(B4D_ERR_INVALID, "step must be >= 1");
+    const size_t esz = q ? sizeof(uint16_t) : sizeof(float);
     if (!h->slab_open) return fail(B4D_ERR_INVALID, "b4d_slab_stage1_u16 has not been called");
     const int64_t zb = h->slab_z_begin, D = h->slab_shape[0];
     if (own_begin < zb || own_end > zb + D || own_begin >= own_end)
@@ -1087,15 +1164,27 @@ int b4d_slab_stage2(b4d_handle *h, int64_t own_begin, int64_t own_end, float *ou
         sink.p1 = own_end - zb;
     }
     B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, h->slab_sigma, h->out.as<float>(), clk, 2,
-                         &sink));
+                         &sink, nullptr, q));
     if (!sink.done)
-        CU_TRY(copy_out(h, out, h->out.as<float>() + (own_begin - zb) * P,
-                        (size_t)(own_end - own_begin) * P * sizeof(float), out_on_device, s));
+        CU_TRY(copy_out(h, out, h->out.as<char>() + (size_t)(own_begin - zb) * P * esz,
+                        (size_t)(own_end - own_begin) * P * esz, out_on_device, s));
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     h->slab_open = false;
     return 0;
+}
+int b4d_slab_stage2(b4d_handle *h, int64_t own_begin, int64_t own_end, float *out, int out_on_device) {
+    return slab_stage2_impl(h, own_begin, own_end, out, out_on_device, nullptr);
+}
+int b4d_slab_stage2_q16(b4d_handle *h, int64_t own_begin, int64_t own_end, float offset_sub, float offset_add,
+                        float step, int truncate, uint16_t *out, int out_on_device) {
+    QuantSpec q;
+    q.sub = offset_sub;
+    q.add = offset_add;
+    q.step = step;
+    q.trunc = truncate;
+    return slab_stage2_impl(h, own_begin, own_end, out, out_on_device, &q);
 }
 
 int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], float sigma, int32_t *idx,
@@ -1182,8 +1271,8 @@ int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], 
     return 0;
 }
 
-int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub, float offset_add, float step,
-                     uint16_t *out, int in_on_device, int out_on_device) {
+static int quantize_impl(b4d_handle *h, const float *in, int64_t n, float offset_sub, float offset_add, float step,
+                         uint16_t *out, int in_on_device, int out_on_device, bool trunc) {
     if (!h || !in || !out || n < 0) return fail(B4D_ERR_INVALID, "NULL argument");
     if (!(step >= 1.0f)) return fail(B4D_ERR_INVALID, "step must be >= 1");
     CU_TRY(cudaSetDevice(h->device));
@@ -1200,12 +1289,21 @@ int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub
         B4D_TRY(h->u16.ensure((size_t)n * sizeof(uint16_t) + 16));
         d_out = h->u16.as<uint16_t>();
     }
-    b4d_launch_quantize(d_in, d_out, n, offset_sub, offset_add, step, s);
+    if (trunc) b4d_launch_quantize_trunc(d_in, d_out, n, offset_sub, offset_add, step, s);
+    else b4d_launch_quantize(d_in, d_out, n, offset_sub, offset_add, step, s);
     CU_TRY(cudaGetLastError());
     if (d_out != out)
         CU_TRY(copy_out(h, out, d_out, (size_t)n * sizeof(uint16_t), out_on_device, s));
     CU_TRY(cudaStreamSynchronize(s));
     return 0;
+}
+int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub, float offset_add, float step,
+                     uint16_t *out, int in_on_device, int out_on_device) {
+    return quantize_impl(h, in, n, offset_sub, offset_add, step, out, in_on_device, out_on_device, false);
+}
+int b4d_quantize_trunc_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub, float offset_add, float step,
+                           uint16_t *out, int in_on_device, int out_on_device) {
+    return quantize_impl(h, in, n, offset_sub, offset_add, step, out, in_on_device, out_on_device, true);
 }
 
 // Exact NumPy-2 semantics on float32 data (float32 virtual index, float32 lerp):

@@ -50,6 +50,7 @@ struct MatchParams {
     uint32_t *ssd_out;   // optional [R][K] exact SSDs (instrumented matcher)
     long long tile0;     // first tile of this launch (set by the launcher)
     unsigned long long *stats;  // optional: [0] fallback refs, [1] wide tiles
+    int use_tma;         // set by the launcher: the byte kernel stages its window with one TMA box load
 };
 
 struct FilterParams {
@@ -81,7 +82,7 @@ void b4d_launch_match_range(const MatchParams &p, int Ns, int cz0, int cz1, long
 void b4d_launch_filter(const FilterParams &p, bool wiener, cudaStream_t s);
 // the same in pieces: number of z segments (a multiple of `chunks` when the volume is deep enough,
 // else the default), and the launch of segments [seg0, seg0 + count)
-int b4d_filter_segments(const FilterParams &p, int chunks);
+int b4d_filter_segments(const FilterParams &p, bool wiener, int chunks);
 void b4d_launch_filter_segments(const FilterParams &p, bool wiener, int nseg, int seg0, int count, cudaStream_t s);
 void b4d_upload_tables(const B4dTables &t, cudaStream_t s);
 
@@ -92,12 +93,21 @@ void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, 
 void b4d_launch_u16_sub_offset(const uint16_t *in, const float *off, float *out, long long vol_stride, long long n,
                                unsigned *minmax, cudaStream_t s);
 void b4d_launch_clip(float *x, long long n, float hi, cudaStream_t s);
+void b4d_launch_add_scalar(float *x, long long n, float c, cudaStream_t s);
+void b4d_launch_normalise_match(const long long *numq, const uint32_t *gmap, const float *fallback, float *out,
+                                uint16_t *match, float mscale, int ishift, int D, int H, int W, int nvol,
+                                float inv_qscale, const float kf[4], cudaStream_t s);
 // weight-map contract: den = G (*) (kf x kf x kf) over planes [z0, z1) of every volume, out = num / den / qscale
 void b4d_launch_normalise_wm(const long long *numq, const uint32_t *gmap, const float *fallback, float *out, int D,
                              int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4],
                              cudaStream_t s);
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s);
+void b4d_launch_quantize_trunc(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
+                               float step, cudaStream_t s);
+void b4d_launch_normalise_q16(const long long *numq, const uint32_t *gmap, const float *fallback, uint16_t *q16, int D,
+                              int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4],
+                              float offset_sub, float offset_add, float step, int trunc, cudaStream_t s);
 void b4d_launch_hist(const uint16_t *in, long long n, unsigned long long *hist, cudaStream_t s);
 // make_foreground_mask after the statistic: threshold + L1-ball dilation, per patch thr / off
 void b4d_launch_fg_mask(const uint16_t *in, const float *off, const float *thr, int D, int H, int W, long long n,

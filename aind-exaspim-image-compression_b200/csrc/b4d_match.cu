@@ -50,6 +50,9 @@
 // rank-sorted at the end.  If the list overflows (adversarial key order) the warp
 // falls back to K rounds of "smallest key greater than the previous one".
 #include <algorithm>
+#include <cstring>
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 
 #include "b4d_common.cuh"
 
@@ -88,9 +91,18 @@ struct Geo {
     static constexpr int BWIN_WORDS = E * PSW;
     static constexpr int NWR = (NS + 9) / 4;   // row words a lane loads: bytes [a, a + NS + 3), a <= 3
     // byte kernel: byte window + the S2' table, whose space first holds the raw uint16 window
-    static constexpr size_t TAB_B =
+    static constexpr size_t TAB_B0 =
         (size_t)S2_WORDS * 4 > (size_t)WIN_ELEMS * 2 ? (size_t)S2_WORDS * 4 : (size_t)WIN_ELEMS * 2;
-    static constexpr size_t SMEM_B = (((size_t)BWIN_WORDS * 4 + 15) & ~(size_t)15) + TAB_B;
+    // TMA staging of the byte kernel: one 4-D box (BOXW x E x E x 1 uint16) lands DENSE in the table space; the byte
+    // conversion reads it from there.  Measured on B200 (tools/tma_check.cu): the innermost start coordinate has to be
+    // a multiple of 16 bytes (8 voxels) — an unaligned one raises "illegal instruction" — so the box starts at the
+    // aligned column below the window and is up to 7 columns wider, rounded to the 16-byte rule; 128-byte aligned
+    // destination; the barrier initialisation needs fence.proxy.async before the TMA unit may use it.
+    static constexpr int BOXW = (4 * RW + 7 + 7) & ~7;  // the conversion reads whole words of 4 voxels from column xb <= 7 on
+    static constexpr uint32_t BOX_BYTES = (uint32_t)BOXW * E * E * 2;
+    static constexpr size_t TAB_B = TAB_B0 > (size_t)BOX_BYTES ? TAB_B0 : (size_t)BOX_BYTES;
+    static constexpr size_t BWIN_BYTES = (((size_t)BWIN_WORDS * 4 + 127) & ~(size_t)127);
+    static constexpr size_t SMEM_B = BWIN_BYTES + TAB_B;
     // centre-out visiting order of the 32-unit groups: mc, mc+1, mc-1, mc+2, ...
     // packed 4 bits per entry so the device reads it with a shift and a mask
     static constexpr int order_at(int it) {
@@ -361,8 +373,39 @@ __device__ __forceinline__ void r8corr_row_rolled(const uint32_t *__restrict__ b
     }
 }
 
+// ---- TMA / mbarrier primitives (sm_90+): one elected thread issues the box load, everybody waits on the barrier
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // visible to the async proxy (the TMA unit)
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t mbar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 template <int NS, bool K32, bool BYTE>
-__global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchParams p) {
+__global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchParams p,
+                                                                    const __grid_constant__ CUtensorMap tmap) {
     using G = Geo<NS>;
     constexpr int R_ = G::R, E = G::E, EC = G::EC, KB = G::KB, UNITS = G::UNITS, ITERS = G::ITERS;
 
@@ -372,11 +415,10 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     const uint32_t tmin = cls & 0xFFFFu;
     const bool narrow = BYTE || ((cls >> 17) & 1u) != 0u;
 
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    extern __shared__ __align__(128) unsigned char s_raw[];
     uint16_t *s_win = reinterpret_cast<uint16_t *>(s_raw);
     uint32_t *s_bw = reinterpret_cast<uint32_t *>(s_raw);  // byte path: packed bytes
-    unsigned char *s_tab =
-        s_raw + (BYTE ? (((size_t)G::BWIN_WORDS * 4 + 15) & ~(size_t)15) : (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15));
+    unsigned char *s_tab = s_raw + (BYTE ? G::BWIN_BYTES : (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15));
     uint32_t *s_s2 = reinterpret_cast<uint32_t *>(s_tab);  // byte kernel: centred energies S2'
     uint2 *s_e = reinterpret_cast<uint2 *>(s_tab);         // general kernel: {S2 mod 2^32, S1 | S2hi << 24}
     __shared__ uint32_t s_surv[WARPS][CAP];
@@ -401,7 +443,51 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     const int xo = (BYTE || (g.W & 1)) ? 0 : (bx & 1);
 
     if (BYTE) {
-        if (!(g.W & 1)) {
+        if (p.use_tma) {
+            // (1) TMA: the (E x E x E) uint16 neighbourhood as ONE 4-D box load (x extent rounded up to BOXW), issued by
+            // one thread, zero fill outside the volume by the tensor map, completion on an mbarrier — no per-element
+            // address arithmetic, nothing on the LSU issue path.  It lands dense in the table space.
+            __shared__ __align__(8) unsigned long long s_mbar;
+            uint16_t *s_tmp = reinterpret_cast<uint16_t *>(s_tab);
+            const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+            if (threadIdx.x == 0) mbar_init(mbar, 1);
+            __syncthreads();
+            const int xb = bx & 7, bxa = bx - xb;  // box origin: the 16-byte aligned column at or below bx
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(mbar, G::BOX_BYTES);
+                tma_load_4d((uint32_t)__cvta_generic_to_shared(s_tmp), &tmap, mbar, bxa, by, bz, vol);
+            }
+            mbar_wait(mbar, 0);
+            // (2) bytes v - tile_min, four per word (columns past the window hold data no valid candidate reads)
+            for (int id = threadIdx.x; id < E * E * G::RW; id += WARPS * 32) {
+                const int row = id / G::RW, xw = id - row * G::RW;
+                const int z = row / E, y = row - z * E;
+                const uint16_t *src = s_tmp + row * G::BOXW + xb + 4 * xw;
+                const uint32_t b0 = (src[0] - tmin) & 0xFFu, b1 = (src[1] - tmin) & 0xFFu;
+                const uint32_t b2 = (src[2] - tmin) & 0xFFu, b3 = (src[3] - tmin) & 0xFFu;
+                s_bw[z * G::PSW + y * G::RSW + xw] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+            }
+            __syncthreads();
+            // (3) centred block energies from the byte window (as below)
+            for (int col = threadIdx.x; col < EC * EC; col += WARPS * 32) {
+                const int y = col / EC, x = col - y * EC;
+                const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(x & 3);
+                uint32_t r1 = 0u, r2 = 0u, r3 = 0u;
+                for (int z = 0; z < E; ++z) {
+                    uint32_t r0 = 0u;
+#pragma unroll
+                    for (int dy = 0; dy < 4; ++dy) {
+                        const uint32_t *w = s_bw + z * G::PSW + (y + dy) * G::RSW + (x >> 2);
+                        const uint32_t q = __byte_perm(w[0], w[1], sel);
+                        r0 = __dp4a(q, q, r0);
+                    }
+                    if (z >= 3) s_s2[(z - 3) * G::AC + y * G::BC + x] = r0 + r1 + r2 + r3;
+                    r3 = r2;
+                    r2 = r1;
+                    r1 = r0;
+                }
+            }
+        } else if (!(g.W & 1)) {
             // (1) raw uint16 window -> scratch (the S2' table's space) by cp.async, as in the
             // general kernel: even global x origin, zero fill outside the volume
             uint16_t *s_tmp = reinterpret_cast<uint16_t *>(s_tab);
@@ -758,17 +844,57 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     }
 }
 
+// Tensor map of the uint16 matching image as a 4-D tensor (x, y, z, volume); box = the staged neighbourhood of one
+// tile.  Needs row and plane pitches that are multiples of 16 bytes (W % 8 == 0); otherwise the kernels keep the
+// cp.async / plain-load staging.  The encoder comes from the driver through the runtime (no -lcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+template <int NS>
+bool make_window_map(const MatchParams &p, CUtensorMap *map) {
+    using G = Geo<NS>;
+    std::memset(map, 0, sizeof(*map));
+    const B4dGeom &g = p.g;
+    if ((g.W & 7) != 0 || getenv("B4D_NO_TMA")) return false;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.D, (cuuint64_t)g.nvol};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.W * 2, (cuuint64_t)g.W * g.H * 2, (cuuint64_t)g.vol_stride * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)G::BOXW, (cuuint32_t)G::E, (cuuint32_t)G::E, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint16_t *>(p.u), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NS, bool K32>
 void launch_k(const MatchParams &pin, long long tile0, long long tile1, cudaStream_t s) {
     using G = Geo<NS>;
     MatchParams p = pin;
     p.tile0 = tile0;
+    CUtensorMap tmap;
+    p.use_tma = make_window_map<NS>(p, &tmap) ? 1 : 0;
     const unsigned tiles = (unsigned)(tile1 - tile0);
     // byte tiles first (cheap), then everything else; each kernel exits at once on a foreign tile
     cudaFuncSetAttribute(k_match<NS, K32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_B);
-    k_match<NS, K32, true><<<tiles, WARPS * 32, G::SMEM_B, s>>>(p);
+    k_match<NS, K32, true><<<tiles, WARPS * 32, G::SMEM_B, s>>>(p, tmap);
     cudaFuncSetAttribute(k_match<NS, K32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-    k_match<NS, K32, false><<<tiles, WARPS * 32, G::SMEM, s>>>(p);
+    k_match<NS, K32, false><<<tiles, WARPS * 32, G::SMEM, s>>>(p, tmap);
 }
 // cell planes [cz0, cz1) (min/max table) and tiles [tile0, tile1) (classification + both matcher
 // kernels); the whole volume in one go is cz = [0, cd), tiles = [0, all)

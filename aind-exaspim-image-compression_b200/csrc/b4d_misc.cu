@@ -231,11 +231,7 @@ __global__ void __launch_bounds__(256) k_normalise_wm(const long long *__restric
             const long long a = vol * V + (long long)z * P + (long long)gy * W + gx;
             const float y = den > 0.0 ? (float)(((double)__ldcs(numq + a) / den) * inv) : fb[a];
             if (o.out) o.out[a] = y;
-            if (o.match) {
-                long long q = __float2ll_rn(__fmul_rn(y, o.mscale)) + (long long)o.ishift;
-                q = q < 0 ? 0 : (q > 65535 ? 65535 : q);
-                o.match[a] = (uint16_t)q;
-            }
+            if (o.match) o.match[a] = (uint16_t)to_match(y, 0.0f, o.mscale, o.ishift);
             if (o.q16)
                 o.q16[a] = (uint16_t)(o.q_trunc ? quant1_trunc(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0)
                                                 : quant1(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0));
@@ -264,6 +260,11 @@ __device__ __forceinline__ uint32_t quant1_trunc(float x, float osub, float oadd
     v = fmaxf(v, 0.0f);  // NaN -> 0
     return (uint32_t)(__float2ll_rz(v) & 0xFFFFll);
 }
+template <bool TRUNC>
+__device__ __forceinline__ uint32_t quantq(float x, float osub, float oadd, float step, float hi, bool unit) {
+    return TRUNC ? quant1_trunc(x, osub, oadd, step, hi, unit) : quant1(x, osub, oadd, step, hi, unit);
+}
+template <bool TRUNC>
 __global__ void __launch_bounds__(256) k_quantize(const float *__restrict__ in, uint16_t *__restrict__ out,
                                                   long long n, float osub, float oadd, float step) {
     const bool unit = (step == 1.0f);
@@ -279,15 +280,15 @@ __global__ void __launch_bounds__(256) k_quantize(const float *__restrict__ in, 
         for (int k = 0; k < 2; ++k) {
             const float4 a = v[2 * k], b = v[2 * k + 1];
             uint4 o;
-            o.x = quant1(a.x, osub, oadd, step, hi, unit) | (quant1(a.y, osub, oadd, step, hi, unit) << 16);
-            o.y = quant1(a.z, osub, oadd, step, hi, unit) | (quant1(a.w, osub, oadd, step, hi, unit) << 16);
-            o.z = quant1(b.x, osub, oadd, step, hi, unit) | (quant1(b.y, osub, oadd, step, hi, unit) << 16);
-            o.w = quant1(b.z, osub, oadd, step, hi, unit) | (quant1(b.w, osub, oadd, step, hi, unit) << 16);
+            o.x = quantq<TRUNC>(a.x, osub, oadd, step, hi, unit) | (quantq<TRUNC>(a.y, osub, oadd, step, hi, unit) << 16);
+            o.y = quantq<TRUNC>(a.z, osub, oadd, step, hi, unit) | (quantq<TRUNC>(a.w, osub, oadd, step, hi, unit) << 16);
+            o.z = quantq<TRUNC>(b.x, osub, oadd, step, hi, unit) | (quantq<TRUNC>(b.y, osub, oadd, step, hi, unit) << 16);
+            o.w = quantq<TRUNC>(b.z, osub, oadd, step, hi, unit) | (quantq<TRUNC>(b.w, osub, oadd, step, hi, unit) << 16);
             __stcs(reinterpret_cast<uint4 *>(out) + 2 * i + k, o);
         }
     }
     for (long long i = (nv << 4) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = (uint16_t)quant1(in[i], osub, oadd, step, hi, unit);
+        out[i] = (uint16_t)quantq<TRUNC>(in[i], osub, oadd, step, hi, unit);
 }
 
 // --------------------------------------------------- chunk byte shuffle ----
@@ -522,14 +523,16 @@ __global__ void __launch_bounds__(512) k_hist(const uint16_t *__restrict__ in, l
 }
 
 // -------------------------------------------- float32 analysis (match map) --
-// per-block partials: {max |frac dev|, min rint, max rint, min z, max z, unused}
+// per-block partials: {max |frac dev|, min rint, max rint, min z, max z, 1 if any value is NaN or infinite}
 constexpr int AN_BLOCKS = 592;
 __global__ void __launch_bounds__(256) k_analyze(const float *__restrict__ in, long long n, double c,
                                                  double *__restrict__ partial) {
-    double dev = 0.0, lo = 1e300, hi = -1e300, zlo = 1e300, zhi = -1e300;
+    double dev = 0.0, lo = 1e300, hi = -1e300, zlo = 1e300, zhi = -1e300, nonfinite = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double z = (double)in[i];
+        const float zf32 = in[i];
+        if (!isfinite(zf32)) nonfinite = 1.0;  // fmin / fmax drop NaNs: count them explicitly
+        const double z = (double)zf32;
         const double v = z + c, rv = rint(v);
         dev = fmax(dev, fabs(v - rv));
         lo = fmin(lo, rv);
@@ -537,9 +540,10 @@ __global__ void __launch_bounds__(256) k_analyze(const float *__restrict__ in, l
         zlo = fmin(zlo, z);
         zhi = fmax(zhi, z);
     }
-    __shared__ double sh[5][8];
+    __shared__ double sh[6][8];
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
+        nonfinite = fmax(nonfinite, __shfl_xor_sync(B4D_FULL, nonfinite, m));
         dev = fmax(dev, __shfl_xor_sync(B4D_FULL, dev, m));
         lo = fmin(lo, __shfl_xor_sync(B4D_FULL, lo, m));
         hi = fmax(hi, __shfl_xor_sync(B4D_FULL, hi, m));
@@ -553,6 +557,7 @@ __global__ void __launch_bounds__(256) k_analyze(const float *__restrict__ in, l
         sh[2][warp] = hi;
         sh[3][warp] = zlo;
         sh[4][warp] = zhi;
+        sh[5][warp] = nonfinite;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -562,9 +567,9 @@ __global__ void __launch_bounds__(256) k_analyze(const float *__restrict__ in, l
             sh[2][0] = fmax(sh[2][0], sh[2][w]);
             sh[3][0] = fmin(sh[3][0], sh[3][w]);
             sh[4][0] = fmax(sh[4][0], sh[4][w]);
+            sh[5][0] = fmax(sh[5][0], sh[5][w]);
         }
-        for (int q = 0; q < 5; ++q) partial[blockIdx.x * 6 + q] = sh[q][0];
-        partial[blockIdx.x * 6 + 5] = 0.0;
+        for (int q = 0; q < 6; ++q) partial[blockIdx.x * 6 + q] = sh[q][0];
     }
 }
 
@@ -612,6 +617,13 @@ void b4d_launch_u16_sub_offset(const uint16_t *in, const float *off, float *out,
                                unsigned *minmax, cudaStream_t s) {
     k_u16_sub_offset<<<grid_for((vol_stride & 7) ? n : (n >> 3), 256, 8), 256, 0, s>>>(in, off, out, vol_stride, n, minmax);
 }
+__global__ void __launch_bounds__(256) k_add_scalar(float *__restrict__ x, long long n, float c) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = __fadd_rn(x[i], c);
+}
+void b4d_launch_add_scalar(float *x, long long n, float c, cudaStream_t s) {
+    k_add_scalar<<<grid_for(n, 256, 8), 256, 0, s>>>(x, n, c);
+}
 void b4d_launch_clip(float *x, long long n, float hi, cudaStream_t s) {
     k_clip<<<grid_for(n >> 2, 256, 8), 256, 0, s>>>(x, n, hi);
 }
@@ -634,6 +646,20 @@ void b4d_launch_normalise_wm(const long long *numq, const uint32_t *gmap, const 
     o.out = out;
     launch_norm(numq, gmap, fallback, o, D, H, W, nvol, z0, z1, inv_qscale, kf, s);
 }
+// K6 + K7 fused: the quantized uint16 volume is written directly (float32 result never stored)
+void b4d_launch_normalise_q16(const long long *numq, const uint32_t *gmap, const float *fallback, uint16_t *q16, int D,
+                              int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4],
+                              float offset_sub, float offset_add, float step, int trunc, cudaStream_t s) {
+    NormOut o{};
+    o.q16 = q16;
+    o.q_sub = offset_sub;
+    o.q_add = offset_add;
+    o.q_step = step;
+    o.q_hi = 65535.0f / step;  // float32 division, as k_quantize's __fdiv_rn(65535.0f, step)
+    o.q_unit = step == 1.0f;
+    o.q_trunc = trunc;
+    launch_norm(numq, gmap, fallback, o, D, H, W, nvol, z0, z1, inv_qscale, kf, s);
+}
 void b4d_launch_normalise_match(const long long *numq, const uint32_t *gmap, const float *fallback, float *out,
                                 uint16_t *match, float mscale, int ishift, int D, int H, int W, int nvol,
                                 float inv_qscale, const float kf[4], cudaStream_t s) {
@@ -646,7 +672,11 @@ void b4d_launch_normalise_match(const long long *numq, const uint32_t *gmap, con
 }
 void b4d_launch_quantize(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
                          float step, cudaStream_t s) {
-    k_quantize<<<grid_for(n >> 4, 256, 8), 256, 0, s>>>(in, out, n, offset_sub, offset_add, step);
+    k_quantize<false><<<grid_for(n >> 4, 256, 8), 256, 0, s>>>(in, out, n, offset_sub, offset_add, step);
+}
+void b4d_launch_quantize_trunc(const float *in, uint16_t *out, long long n, float offset_sub, float offset_add,
+                               float step, cudaStream_t s) {
+    k_quantize<true><<<grid_for(n >> 4, 256, 8), 256, 0, s>>>(in, out, n, offset_sub, offset_add, step);
 }
 void b4d_launch_chunk_shuffle(const uint16_t *in, int D, int H, int W, int cz, int cy, int cx, uint8_t *out,
                               uint32_t *hist, cudaStream_t s) {

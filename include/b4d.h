@@ -159,6 +159,9 @@ int b4d_slab_stage1_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3
 int b4d_slab_basic_planes(b4d_handle *h, int64_t plane0, int64_t nplanes, float *buf, int to_handle,
                           int buf_on_device);
 int b4d_slab_stage2(b4d_handle *h, int64_t own_begin, int64_t own_end, float *out, int out_on_device);
+/* the same with the fused quantizer (see b4d_denoise_q16_u16) */
+int b4d_slab_stage2_q16(b4d_handle *h, int64_t own_begin, int64_t own_end, float offset_sub,
+                        float offset_add, float step, int truncate, uint16_t *out, int out_on_device);
 
 /* Instrumented stage-1 matcher (bit-exactness test, BASELINE config 3).
  * R = number of reference blocks, K = profile.k_ht.  Host pointers.
@@ -175,6 +178,24 @@ int64_t b4d_num_refs(const int64_t shape[3]);
 int b4d_quantize_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub,
                      float offset_add, float step, uint16_t *out, int in_on_device,
                      int out_on_device);
+/* The truncating variant the evaluator uses: np.maximum(x, 0).astype(int) (evaluate.py:202) followed by the
+ * uint16 cast of compute_cratio (utils/img_util.py:420-423):
+ *   q = uint16(int64(trunc(max((x - offset_sub + offset_add) / step, 0))))   toward zero, no upper clip,
+ *   wrapping modulo 2^16 as the NumPy cast does; NaN gives 0. */
+int b4d_quantize_trunc_u16(b4d_handle *h, const float *in, int64_t n, float offset_sub,
+                           float offset_add, float step, uint16_t *out, int in_on_device,
+                           int out_on_device);
+
+/* Denoise -> offset -> quantize in one call (K6 + K7 fused: the float32 result is never stored, 2 bytes per
+ * voxel leave the device instead of 4).  Equal, bit for bit, to b4d_quantize_u16 / b4d_quantize_trunc_u16
+ * (truncate != 0) applied to the output of the matching denoise call.  Needs profile.stages = 2. */
+int b4d_denoise_slab_q16_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
+                             int64_t z_total, int64_t own_begin, int64_t own_end, float sigma,
+                             float offset_sub, float offset_add, float step, int truncate, uint16_t *out,
+                             int in_on_device, int out_on_device);
+int b4d_denoise_q16_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3], float sigma,
+                        float offset_sub, float offset_add, float step, int truncate, uint16_t *out,
+                        int in_on_device, int out_on_device);
 
 /* Intensity foreground mask of `n` equal-shape uint16 patches — make_foreground_mask
  * (machine_learning/metrics.py:32-61), the mask both datasets fall back to when a patch has no

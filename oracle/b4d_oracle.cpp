@@ -57,6 +57,8 @@ struct b4d_handle_impl {
     int arith;  // 0 = mirror (float32, CUDA op order), 1 = f64 plain restatement
     int threads;
     mutable std::vector<int64_t> last_numq, last_wmap;  // mirror: accumulators of the last filter stage
+    mutable std::vector<uint16_t> last_widx2;           // stage-2 match lists of the last two-stage call
+    mutable std::vector<uint8_t> last_cnt2;
 };
 
 // ---------------------------------------------------------------- profile ---
@@ -688,7 +690,9 @@ struct MatchMap {
     int integral;
 };
 int centre_shift(double lo, double hi) { return (int)(std::floor((65535.0 - (hi - lo)) * 0.5) - lo); }
-MatchMap derive_match_map(const float *z, int64_t n, float sigma) {
+// *centre: see csrc/b4d_api.cu derive_match_map (large-DC float data are denoised on z - c0)
+constexpr double CENTRE_LIMIT = 131072.0;
+MatchMap derive_match_map(const float *z, int64_t n, float sigma, float *centre = nullptr) {
     double c = std::rint((double)z[0]) - (double)z[0];
     double dev = 0, lo = 1e300, hi = -1e300, zlo = 1e300, zhi = -1e300;
 #pragma omp parallel for reduction(max : dev, hi, zhi) reduction(min : lo, zlo)
@@ -706,16 +710,21 @@ MatchMap derive_match_map(const float *z, int64_t n, float sigma) {
         mm.scale = 1.0f;
         mm.cf = (float)c;
         mm.ishift = centre_shift(lo, hi);
-        return mm;
+    } else {
+        double range = std::max(zhi - zlo, 1e-30);
+        int e_range = (int)std::floor(std::log2(65535.0 / range));
+        int e_sigma = (int)std::floor(std::log2(64.0 / (double)sigma));
+        int e = std::min(e_range, e_sigma);
+        mm.integral = 0;
+        mm.scale = (float)std::ldexp(1.0, e);
+        mm.cf = 0.0f;
+        mm.ishift = centre_shift(std::floor(zlo * (double)mm.scale), std::ceil(zhi * (double)mm.scale));
     }
-    double range = std::max(zhi - zlo, 1e-30);
-    int e_range = (int)std::floor(std::log2(65535.0 / range));
-    int e_sigma = (int)std::floor(std::log2(64.0 / (double)sigma));
-    int e = std::min(e_range, e_sigma);
-    mm.integral = 0;
-    mm.scale = (float)std::ldexp(1.0, e);
-    mm.cf = 0.0f;
-    mm.ishift = centre_shift(std::floor(zlo * (double)mm.scale), std::ceil(zhi * (double)mm.scale));
+    if (centre) {
+        const double peak = std::max(std::fabs(zlo), std::fabs(zhi)) * (double)mm.scale;
+        *centre = 0.0f;
+        if (peak > CENTRE_LIMIT) *centre = mm.integral ? (float)std::rint(0.5 * (lo + hi)) : (float)(0.5 * (zlo + zhi));
+    }
     return mm;
 }
 inline uint16_t to_match_u16(float v, float cf, float scale, int ishift) {
@@ -749,7 +758,17 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
         }
         mm.ishift = centre_shift(lo, hi);
     } else {
-        mm = derive_match_map(in_f32, V, sigma);
+        for (int64_t i = 0; i < V; ++i)
+            if (!std::isfinite(in_f32[i])) return fail(B4D_ERR_INVALID, "input contains non-finite values (NaN or infinity)");
+        float centre = 0.0f;
+        mm = derive_match_map(in_f32, V, sigma, &centre);
+        if (centre != 0.0f) {  // large DC level: denoise z - c0, add c0 back (csrc/b4d_api.cu denoise_batch)
+            std::vector<float> shifted(V);
+            for (int64_t i = 0; i < V; ++i) shifted[i] = in_f32[i] + (-centre);
+            if (int e = denoise_one(h, nullptr, shifted.data(), g1, g2, sigma, out)) return e;
+            for (int64_t i = 0; i < V; ++i) out[i] = out[i] + centre;
+            return 0;
+        }
         for (int64_t i = 0; i < V; ++i) {
             zf[i] = in_f32[i];
             u[i] = to_match_u16(in_f32[i], mm.cf, mm.scale, mm.ishift);
@@ -767,6 +786,8 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
         }
         for (int64_t i = 0; i < V; ++i) u[i] = to_match_u16((float)basic[i], 0.0f, mm.scale, mm.ishift);
         match_all(u.data(), g2, p.search_wie, p.k_wie, tau_int(p.tau_wie, sigma, mm.scale), m);
+        h->last_widx2 = m.widx;
+        h->last_cnt2 = m.cnt;
         std::fill(num.begin(), num.end(), 0.0);
         std::fill(den.begin(), den.end(), 0.0);
         filter_f64<true>(zf.data(), basic.data(), g2, m, p.search_wie, (double)sigma, p, num, den);
@@ -789,6 +810,8 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     }
     for (int64_t i = 0; i < V; ++i) u[i] = to_match_u16(basic[i], 0.0f, mm.scale, mm.ishift);
     match_all(u.data(), g2, p.search_wie, p.k_wie, tau_int(p.tau_wie, sigma, mm.scale), m);
+    h->last_widx2 = m.widx;
+    h->last_cnt2 = m.cnt;
     std::fill(numq.begin(), numq.end(), 0);
     std::fill(denq.begin(), denq.end(), 0);
     filter_mirror<true>(zf.data(), basic.data(), g2, m, p.search_wie, t, mm.scale, numq, denq);
@@ -962,6 +985,40 @@ int b4d_quantize_u16(b4d_handle *, const float *in, int64_t n, float offset_sub,
     return 0;
 }
 
+// truncating variant: np.maximum(x, 0).astype(int) (evaluate.py:202) + the uint16 cast of compute_cratio
+// (utils/img_util.py:420-423): toward zero, no upper clip, int64 -> uint16 wraps modulo 2^16
+int b4d_quantize_trunc_u16(b4d_handle *, const float *in, int64_t n, float offset_sub, float offset_add, float step,
+                           uint16_t *out, int, int) {
+    if (!in || !out || n < 0) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!(step >= 1.0f)) return fail(B4D_ERR_INVALID, "step must be >= 1");
+    for (int64_t i = 0; i < n; ++i) {
+        float v = (in[i] - offset_sub) + offset_add;
+        if (step != 1.0f) v = v / step;
+        v = std::isnan(v) ? 0.0f : fmaxf(v, 0.0f);
+        out[i] = (uint16_t)((int64_t)v & 0xFFFF);
+    }
+    return 0;
+}
+// denoise -> quantize in one call: the restatement simply chains the two restated steps
+int b4d_denoise_slab_q16_u16(b4d_handle *hh, const uint16_t *in, const int64_t shape[3], int64_t z_begin,
+                             int64_t z_total, int64_t own_begin, int64_t own_end, float sigma, float offset_sub,
+                             float offset_add, float step, int truncate, uint16_t *out, int, int) {
+    if (!shape || !out || own_end <= own_begin) return fail(B4D_ERR_INVALID, "bad argument");
+    const int64_t n = (own_end - own_begin) * shape[1] * shape[2];
+    std::vector<float> y((size_t)n);
+    if (int e = b4d_denoise_slab_u16(hh, in, shape, z_begin, z_total, own_begin, own_end, sigma, y.data(), 0, 0)) return e;
+    return truncate ? b4d_quantize_trunc_u16(hh, y.data(), n, offset_sub, offset_add, step, out, 0, 0)
+                    : b4d_quantize_u16(hh, y.data(), n, offset_sub, offset_add, step, out, 0, 0);
+}
+int b4d_denoise_q16_u16(b4d_handle *hh, const uint16_t *in, const int64_t shape[3], float sigma, float offset_sub,
+                        float offset_add, float step, int truncate, uint16_t *out, int, int) {
+    if (!shape) return fail(B4D_ERR_INVALID, "NULL argument");
+    return b4d_denoise_slab_q16_u16(hh, in, shape, 0, shape[0], 0, shape[0], sigma, offset_sub, offset_add, step,
+                                    truncate, out, 0, 0);
+}
+int b4d_slab_stage2_q16(b4d_handle *, int64_t, int64_t, float, float, float, int, uint16_t *, int) {
+    return fail(B4D_ERR_UNSUPPORTED, "oracle: use b4d_denoise_slab_q16_u16");
+}
 int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *, int64_t *, int) {
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }
@@ -1074,6 +1131,16 @@ int b4d_last_timings(b4d_handle *, float *, int64_t *) {
 }
 int b4d_measure_pipe_peaks(b4d_handle *, double *) {
     return fail(B4D_ERR_UNSUPPORTED, "no device in the oracle");
+}
+// oracle-only: the stage-2 match lists (window index per match [R][K], group size [R]) of the last two-stage
+// single-volume call, for the test that traces every large float32-vs-float64 difference to a flipped match
+int b4d_oracle_stage2_matches(b4d_handle *hh, uint16_t *widx, uint8_t *cnt, int64_t refs) {
+    auto *h = reinterpret_cast<b4d_handle_impl *>(hh);
+    if (!h || !widx || !cnt || (int64_t)h->last_cnt2.size() != refs)
+        return fail(B4D_ERR_INVALID, "no stage-2 match lists of that size");
+    std::memcpy(widx, h->last_widx2.data(), h->last_widx2.size() * sizeof(uint16_t));
+    std::memcpy(cnt, h->last_cnt2.data(), h->last_cnt2.size());
+    return 0;
 }
 int b4d_debug_accumulators(b4d_handle *hh, int64_t *numq, int64_t *wmap, int64_t n) {
     auto *h = reinterpret_cast<b4d_handle_impl *>(hh);

@@ -241,6 +241,17 @@ class Oracle:
         )
         return out
 
+    def stage2_matches(self, shape):
+        """(widx[R, K], cnt[R]) of the last two-stage call on one volume of `shape`: window index
+        (dz*Ns + dy)*Ns + dx of every match, group size per reference block."""
+        R = int(load().b4d_num_refs(self._shape3(shape)))
+        K = self.profile.k_wie
+        widx = np.empty((R, K), dtype=np.uint16)
+        cnt = np.empty((R,), dtype=np.uint8)
+        _check(load().b4d_oracle_stage2_matches(self._h, widx.ctypes.data_as(ctypes.c_void_p),
+                                                cnt.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(R)))
+        return widx, cnt
+
     def accumulators(self, n):
         """(numq, wmap) int64 arrays of the last mirror filter stage (see b4d_debug_accumulators)."""
         numq = np.empty(n, dtype=np.int64)

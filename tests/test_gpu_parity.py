@@ -5,9 +5,11 @@ Bars (BASELINE.json north_star / DESIGN.md §5):
   * denoised output: BIT-EXACT vs the oracle's float32 mirror (same discrete
     decisions, same rounding; aggregation is always order-independent fixed point,
     the `deterministic` profile flag is kept for compatibility);
-  * denoised output vs the plain float64 oracle: rel-L2 <= 1e-3 (north_star);
-    block matching is discontinuous, so a float64 pipeline may flip a handful of
-    near-tied matches: max-abs is bounded at 0.5 for >= 99.99 % of voxels and reported;
+  * denoised output vs the plain float64 oracle: rel-L2 <= 1e-3 and max-abs <= 0.5 (north_star).
+    Block matching is discontinuous, so a float64 pipeline may flip a handful of near-tied
+    stage-2 matches; the tests extract the stage-2 match lists of both pipelines and PROVE that
+    every voxel above 0.5 lies under a flipped group, and that the difference stays below 0.01
+    everywhere else (tests/parity_util.py);
   * quantize, statistics: bit-exact.
 """
 import numpy as np
@@ -78,6 +80,18 @@ def test_stage1_match_lists_config3_slice(dn, oracle_lib):
     assert np.array_equal(gc, oc) and np.array_equal(gi, oi) and np.array_equal(gs, os_)
 
 
+def test_stage1_match_lists_config3_full_size(dn, oracle_lib):
+    """BASELINE config 3 at its stated size: the 256^3 tile, R = 614 125 reference blocks, K = 16 —
+    idx[R, K], ssd[R, K], count[R] bit-exact against the oracle's brute-force matcher (OpenMP: seconds)."""
+    from b4d import synth
+
+    vol = synth.vol(256, 256, 256, seed=3)
+    gi, gs, gc = dn.match_stage1(vol, 24.0)
+    oi, os_, oc = oracle_lib.Oracle("f64").match_stage1(vol, 24.0)
+    assert gi.shape == (85 ** 3, 16)
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi) and np.array_equal(gs, os_)
+
+
 @pytest.mark.parametrize("ns,k", [(7, 8), (15, 16), (5, 4), (13, 32)])
 def test_stage1_other_windows(ns, k, b4d_mod, oracle_lib):
     from b4d import synth
@@ -123,22 +137,28 @@ def test_default_profile_config1_patch(dn, oracle_lib):
 
     vol = synth.vol(64, 64, 64, seed=1)  # BASELINE config 1 input
     raw = vol.astype(np.float32) - np.float32(37.0)
+    import parity_util
+
     for z in (vol, raw):
         y = dn.denoise(z, 24.0)
-        m = oracle_lib.Oracle("mirror").denoise(z, 24.0)
-        f = oracle_lib.Oracle("f64").denoise(z, 24.0)
+        om, of = oracle_lib.Oracle("mirror"), oracle_lib.Oracle("f64")
+        m = om.denoise(z, 24.0)
+        f = of.denoise(z, 24.0)
         assert np.array_equal(y, m)
-        assert np.abs(y - f).max() <= 16 * MAX_ABS and rel_l2(y, f) <= REL_L2
-        frac_bad = float((np.abs(y - f) > MAX_ABS).mean())
-        print("fast vs f64: max-abs %.4f, frac > 0.5: %.2e" % (np.abs(y - f).max(), frac_bad))
-        assert frac_bad <= 1e-4
+        assert rel_l2(y, f) <= REL_L2
+        # max-abs <= 0.5 except under a flipped stage-2 match (the device output equals the mirror bit for
+        # bit, so the mirror's match lists are the device's), <= 0.01 away from any flip
+        rep = parity_util.check_against_f64(y, f, om.stage2_matches(z.shape), of.stage2_matches(z.shape),
+                                            max_abs=MAX_ABS, quiet_abs=0.01)
+        print("device vs f64:", rep)
     # evaluator surface (evaluate.py:201-202): non-contiguous uint16 view, sigma 10
     view = vol[5:-5, 5:-5, 5:-5]
     import b4d
 
-    y = np.maximum(b4d.bm4d(view, 10), 0).astype(int)
-    m = np.maximum(oracle_lib.Oracle("mirror").denoise(np.ascontiguousarray(view), 10.0), 0).astype(int)
-    assert y.shape == (54, 54, 54) and (np.abs(y - m) <= 1).all() and (y != m).mean() < 1e-3
+    yv = b4d.bm4d(view, 10)
+    mv = oracle_lib.Oracle("mirror").denoise(np.ascontiguousarray(view), 10.0)
+    assert yv.shape == (54, 54, 54) and np.array_equal(yv, mv)
+    assert np.array_equal(np.maximum(yv, 0).astype(int), np.maximum(mv, 0).astype(int))
 
 
 def test_batch_equals_per_patch_and_precompute_targets(b4d_mod, oracle_lib):
@@ -228,6 +248,47 @@ def test_quantize_bit_exact(dn, oracle_lib):
     assert dn.quantize(np.zeros(0, np.float32)).size == 0
     with pytest.raises(ValueError):
         dn.quantize(x, step=0.5)
+    # the evaluator's truncating variant (evaluate.py:202 + the uint16 cast of img_util.py:420-423), written
+    # with the reference's own NumPy expressions; values above 65535 wrap like the NumPy cast
+    xt = np.concatenate([x, np.float32([0.0, -0.0, 0.999, 1.0, 65535.9, 65536.0, 70000.5, -3.2])])
+    assert np.array_equal(dn.quantize(xt, truncate=True), oracle_lib.quantize_truncating(xt))
+    assert np.array_equal(dn.quantize(xt, truncate=True),
+                          np.ascontiguousarray(np.maximum(xt, 0).astype(int), dtype=np.uint16))
+    assert np.array_equal(dn.quantize(xt, 3.5, 37.0, 2.5, truncate=True),
+                          oracle_lib.quantize_truncating((xt - np.float32(3.5) + np.float32(37.0)) / np.float32(2.5)))
+
+
+def test_fused_denoise_quantize_equals_the_two_calls(dn, b4d_mod, oracle_lib):
+    """K6 + K7 fused (b4d_denoise_q16_u16 and the slab forms): the uint16 volume must equal K7 applied to the
+    float32 output of the unfused call, bit for bit — rounding and truncating modes, offsets, noise-scaled
+    step; device tensors and host arrays (pipelined copy-out); and the oracle's restatement."""
+    import torch
+
+    from b4d import synth
+
+    vol = synth.vol(40, 44, 48, seed=11)
+    y = dn.denoise(vol, 24.0)
+    for osub, oadd, step, trunc in ((0.0, 0.0, 1.0, False), (36.5, 0.0, 1.0, False), (36.5, 3.0, 12.6, False),
+                                    (0.0, 0.0, 1.0, True), (30.0, 0.0, 2.5, True)):
+        want = dn.quantize(y, osub, oadd, step, truncate=trunc)
+        got = dn.denoise_quantized(vol, 24.0, osub, oadd, step, truncate=trunc)
+        assert got.dtype == np.uint16 and np.array_equal(got, want)
+        gt = dn.denoise_quantized(torch.from_numpy(vol).cuda(), 24.0, osub, oadd, step, truncate=trunc)
+        assert gt.dtype == torch.uint16 and np.array_equal(gt.cpu().numpy(), want)
+    o = oracle_lib.Oracle("mirror")
+    assert np.array_equal(dn.denoise_quantized(vol, 24.0, 36.5, 0.0, 2.0),
+                          oracle_lib.quantize_noise_scaled(o.denoise(vol, 24.0), 36.5, 0.0, 2.0))
+    # slab form: owned planes of a haloed slab, and the pipelined host path on a volume large enough for it
+    big = synth.vol(160, 96, 96, seed=12)
+    dn.set_pipeline_min_voxels(1 << 20)
+    try:
+        yb = dn.denoise(big, 24.0)
+        qb = dn.denoise_quantized(big, 24.0, 36.5, 0.0, 1.0)
+        assert np.array_equal(qb, dn.quantize(yb, 36.5, 0.0, 1.0))
+        qs = dn.denoise_slab(big[20:130], 20, 160, 46, 104, 24.0, quantize=(36.5, 0.0, 1.0))
+        assert np.array_equal(qs, qb[46:104])
+    finally:
+        dn.set_pipeline_min_voxels(1 << 26)
 
 
 def test_tile_stats_exact(dn, oracle_lib):
@@ -258,6 +319,37 @@ def test_errors(dn, b4d_mod):
         dn.denoise(np.zeros((8, 8, 8), np.uint16), 500.0)  # tau*sigma^2*64 exceeds the 32-bit key
     with pytest.raises(ValueError):
         b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(max_stack_size_ht=12))
+    # non-finite float input is refused (NaN as well as infinity: fmin / fmax reductions alone drop NaNs)
+    for bad in (np.nan, np.inf, -np.inf):
+        z = np.full((8, 9, 10), 100.0, np.float32)
+        z[3, 4, 5] = bad
+        with pytest.raises(ValueError):
+            dn.denoise(z, 24.0)
+
+
+def test_float_input_with_a_large_dc_level(dn, oracle_lib):
+    """float32 data far from zero (a DC level much larger than the range) would push the fixed-point numerator
+    terms past their clamp; such inputs are denoised on z - c0 and c0 is added back.  Bit-exact against the
+    mirror (which states the same rule), within the float32 spacing of the DC level against the float64 oracle,
+    and equal to the DC-free result up to that spacing (medians; a near-tied match may flip)."""
+    from b4d import synth
+
+    v = synth.vol(24, 26, 28, seed=2).astype(np.float32)
+    base = dn.denoise(v, 24.0)
+    for dc in (1.0e6, 3.0e7, -2.5e5):
+        z = (v + np.float32(dc)).astype(np.float32)
+        y = dn.denoise(z, 24.0)
+        assert np.array_equal(y, oracle_lib.Oracle("mirror").denoise(z, 24.0))
+        f = oracle_lib.Oracle("f64").denoise(z, 24.0)
+        ulp = float(np.spacing(np.float32(abs(dc) + 65536.0)))
+        assert np.abs(y.astype(np.float64) - f).max() <= max(ulp, 0.5)
+        # against the DC-free result: the same image up to float32 spacing, except under a flipped near-tied match
+        delta = np.abs((y.astype(np.float64) - dc) - base)
+        assert np.median(delta) <= 2 * ulp + 1e-3 and delta.max() <= 4.0
+    x = np.random.default_rng(0).normal(1000.0, 0.05, (20, 21, 22)).astype(np.float32)  # non-integral, sigma << DC
+    y = dn.denoise(x, 0.05)
+    assert np.array_equal(y, oracle_lib.Oracle("mirror").denoise(x, 0.05))
+    assert np.std(y - 1000.0) < 0.5 * np.std(x - 1000.0)
 
 
 def test_full_size_properties_128(dn, b4d_mod):
@@ -541,4 +633,32 @@ def test_full_size_1024_translation_property(dn):
     err_out = (y[384:512, 384:512, 384:512] - clean).pow(2).mean().sqrt()
     assert float(err_out) < 0.5 * float(err_in)
     del y, vol, small
+    torch.cuda.empty_cache()
+
+
+def test_bench_volume_1024_crops_equal_the_oracle(dn, oracle_lib):
+    """The ACTUAL benchmark input (bench.make_slab_device, seed 4, 1024^3) denoised whole on the device,
+    compared with the oracle on haloed crops cut from it.  A crop whose origin is a multiple of the grid
+    step (3) and whose side s has (s - 4) % 3 == 0 carries exactly the global reference grid; its result is
+    exact at least 2 * (Ns - 1 + L - 1) = 26 voxels away from every cut face, so the
+    interior must equal the whole-volume result BIT FOR BIT — in the middle of the volume, at the origin
+    corner and at the far corner (where the crop face is the volume face and needs no halo)."""
+    import torch
+
+    import bench
+
+    S, side, halo = 1024, 97, 27
+    vol = bench.make_slab_device(S, 0, S, torch.device("cuda", 0))
+    y = dn.denoise(vol, bench.SIGMA)
+    assert y.shape == (S, S, S)
+    o = oracle_lib.Oracle("mirror")
+    for org in ((501, 300, 699), (0, 0, 0), (S - side, S - side, S - side), (0, 927, 402)):
+        assert all(c % 3 == 0 for c in org) and (side - 4) % 3 == 0
+        sl = tuple(slice(c, c + side) for c in org)
+        m = o.denoise(vol[sl].cpu().numpy(), bench.SIGMA)
+        inner = tuple(slice(0 if c == 0 else halo, side if c + side == S else side - halo) for c in org)
+        got = y[sl][inner].cpu().numpy()
+        assert got.size >= 43 ** 3
+        assert np.array_equal(got, m[inner]), "crop at %r: max-abs %g" % (org, np.abs(got - m[inner]).max())
+    del y, vol
     torch.cuda.empty_cache()

@@ -68,6 +68,22 @@ def test_mirror_matches_plain_f64(oracle_lib, vol24):
         assert np.abs(a - b).max() < 0.5
 
 
+def test_large_differences_between_the_two_oracle_paths_sit_under_flipped_matches(oracle_lib):
+    """The stated bar is max-abs 0.5 against the float64 oracle.  The float32 mirror crosses it at a few
+    voxels; every one of them lies under a stage-2 group whose match list flipped between the two pipelines
+    (near-tied candidates, matching image rounded from basic estimates that differ by 1e-4), and away from
+    such groups the two paths agree to 0.01 — checked voxel by voxel from the match lists of both."""
+    import parity_util
+
+    for seed, shape in ((1, (40, 40, 40)), (3, (33, 36, 41))):
+        v = synth.vol(*shape, seed=seed)
+        om, of = oracle_lib.Oracle("mirror"), oracle_lib.Oracle("f64")
+        m, f = om.denoise(v, 24.0), of.denoise(v, 24.0)
+        rep = parity_util.check_against_f64(m, f, om.stage2_matches(v.shape), of.stage2_matches(v.shape),
+                                            max_abs=0.5, quiet_abs=0.01)
+        assert rep["voxels_under_flips"] < 0.05 * v.size, rep
+
+
 def test_all_ones_window_and_other_profiles(oracle_lib, vol24):
     y = oracle_lib.Oracle("f64", kaiser_beta=0.0, search_ht=7, search_wie=9, k_ht=8, k_wie=16).denoise(vol24, 24.0)
     assert np.isfinite(y).all() and rel_l2(y, vol24.astype(np.float32)) < 0.9
