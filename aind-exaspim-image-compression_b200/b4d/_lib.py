@@ -46,6 +46,8 @@ EXPORTS = (
     "b4d_denoise_q16_u16",
     "b4d_denoise_slab_q16_u16",
     "b4d_slab_stage2_q16",
+    "b4d_slab_basic_ptr",
+    "b4d_slab_stage2_begin",
 )
 
 
@@ -107,6 +109,7 @@ def load():
     lib.b4d_num_refs.restype = ctypes.c_int64
     lib.b4d_destroy.restype = None
     lib.b4d_stream.restype = ctypes.c_void_p
+    lib.b4d_slab_basic_ptr.restype = ctypes.c_void_p
     lib.b4d_default_profile.restype = None
     if lib.b4d_version() != ABI_VERSION:
         raise B4DLibraryError("libb4d.so ABI %d != binding ABI %d" % (lib.b4d_version(), ABI_VERSION))

@@ -344,6 +344,26 @@ class Denoiser:
             _lib.check(self.lib.b4d_slab_basic_planes(self._h, ctypes.c_int64(plane0), ctypes.c_int64(n),
                                                       ctypes.c_void_p(ptr), 1, int(on_dev)))
 
+    def slab_basic_tensor(self, device):
+        """Zero-copy torch view (D, H, W) float32 of the open slab's basic estimate on `device`: a neighbour
+        exchange reads the owned planes and writes the halo planes in place (b4d_slab_basic_ptr)."""
+        import torch
+
+        ptr = self.lib.b4d_slab_basic_ptr(self._h)
+        if not ptr:
+            _lib.check(-1)
+        shape = tuple(int(v) for v in self._slab_shape)
+
+        class _View:  # the CUDA array interface torch.as_tensor understands
+            __cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                        "strides": None}
+
+        return torch.as_tensor(_View(), device=device)
+
+    def slab_stage2_begin(self, own_begin, own_end):
+        """Launch, without waiting, the part of the stage-2 front end that reads owned planes only."""
+        _lib.check(self.lib.b4d_slab_stage2_begin(self._h, ctypes.c_int64(own_begin), ctypes.c_int64(own_end)))
+
     def slab_stage2(self, own_begin, own_end, out=None, device=None, quantize=None):
         """Stage 2 on the completed basic estimate -> float32 owned planes (NumPy, or torch on
         `device`; `out` may be a preallocated NumPy array, e.g. pinned).  quantize = (offset_sub, offset_add,

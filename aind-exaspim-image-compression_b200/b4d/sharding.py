@@ -76,6 +76,17 @@ def denoise_slab_exchange(denoiser, slab, z_begin, z_total, own_begin, own_end, 
     if (rank > 0 and own_end - own_begin < lo_h) or (rank < world - 1 and own_end - own_begin < hi_h):
         raise ValueError("every rank must own at least as many planes as the halo")
     o0, o1 = own_begin - z_begin, own_end - z_begin  # owned planes, slab-local
+    if device is not None and world > 1:
+        # device path: the exchange reads and writes the handle's basic-estimate buffer in place (no staging
+        # copies) and overlaps the part of the stage-2 front end that needs owned planes only
+        basic = denoiser.slab_basic_tensor(device)
+        denoiser.slab_stage2_begin(own_begin, own_end)
+        exchange_planes(basic[o0 : o0 + lo_h] if rank > 0 else None, basic[o1 - hi_h : o1] if rank < world - 1 else None,
+                        basic[0:lo_h] if rank > 0 else None, basic[o1 : o1 + hi_h] if rank < world - 1 else None,
+                        rank, world, group)
+        torch.cuda.current_stream(device).synchronize()  # the received planes are in place
+        return denoiser.slab_stage2(own_begin, own_end, out=out, device=device if out is None else None,
+                                    quantize=quantize)
 
     def planes(p0, n):
         t = denoiser.slab_basic(p0, n, device=device)

@@ -80,6 +80,11 @@ struct b4d_handle {
     HostMover mover;  // pageable host arrays <-> device (pinned ring + copy threads)
     // state between b4d_slab_stage1_u16 and b4d_slab_stage2
     bool slab_open = false;
+    // two-call slab form: what b4d_slab_stage2_begin already launched (planes [pre_o0, pre_o1) of the matching image,
+    // cell planes [pre_cz0, pre_cz1), tile layers [pre_tz0, pre_tz1) classified and matched)
+    bool pre_done = false;
+    cudaEvent_t pre_ev0 = nullptr, pre_ev1 = nullptr;  // device time of part 1, added to the stage-2 matching slot
+    int pre_o0 = 0, pre_o1 = 0, pre_cz0 = 0, pre_cz1 = 0, pre_tz0 = 0, pre_tz1 = 0;
     int64_t slab_shape[3] = {0, 0, 0};
     int64_t slab_z_begin = 0, slab_z_total = 0;
     float slab_sigma = 0.f;
@@ -385,7 +390,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     B4D_TRY(h->gmap.ensure((size_t)TV * sizeof(uint32_t)));
     const B4dTables tab = make_tables(p, sigma);
     b4d_upload_tables(tab, s);
-    if (phase != 2) CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
+    if (phase < 2) CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
 
     auto zero_acc = [&]() -> int {
         CU_TRY(cudaMemsetAsync(h->numq.p, 0, (size_t)TV * sizeof(long long), s));
@@ -401,7 +406,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     bool fused_match = false;
     MatchParams mp;
     FilterParams fp;
-    if (phase != 2) {
+    if (phase < 2) {
     // ---- stage 1: hard thresholding
     B4D_TRY(zero_acc());
     const bool streamed = src && src->host && can_stream_upload(h, pl) && R1 > 0;
@@ -486,7 +491,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     CU_TRY(cudaGetLastError());
     }
     if (p.stages == 1 || phase == 1) return 0;
-    if (phase == 2) {  // the stage-1 call filled everything but the stage-2 specific fields
+    if (phase >= 2) {  // the stage-1 call filled everything but the stage-2 specific fields
         mp.u = d_u;
         mp.s21 = h->s2.as<uint2>();
         mp.cells = h->cells.as<uint32_t>();
@@ -505,15 +510,67 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     }
 
     // ---- stage 2: Wiener, matching on the basic estimate
-    if (!fused_match) b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
-    B4D_TRY(zero_acc());
-    b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
-    clk.mark(B4D_T_PREP, 3);
     mp.g = g2;
     mp.tau = tau2;
     mp.K = p.k_wie;
-    if (R2 > 0) b4d_launch_match(mp, p.search_wie, s);
-    clk.mark(B4D_T_MATCH2, 4);
+    const long long Pv = (long long)pl.H * pl.W;
+    const long long tiles_per_layer = (long long)g2.ty * g2.tx;
+    const int cd2 = (pl.D + 3) / 4;
+    if (phase == 3) {
+        // Two-call slab form, part 1 (b4d_slab_stage2_begin): everything of the stage-2 front end that does not
+        // read a plane outside [pre_o0, pre_o1) — the planes a neighbour exchange is about to overwrite lie
+        // outside.  Launched and left running: the exchange overlaps it.
+        const int o0 = h->pre_o0, o1 = h->pre_o1, E2 = p.search_wie + 12, r2 = p.search_wie / 2;
+        h->pre_cz0 = (o0 + 3) / 4;
+        h->pre_cz1 = (o1 == pl.D) ? cd2 : o1 / 4;
+        int t0 = 0, t1 = g2.tz;
+        auto layer_inside = [&](int tz) {
+            const int bz = pl.rz2[4 * tz] - r2;
+            const int zlo = std::max(bz, 0), zhi = std::min(bz + E2 - 1, pl.D - 1);
+            return zlo / 4 >= h->pre_cz0 && zhi / 4 < h->pre_cz1 && zlo >= o0 && zhi < o1;
+        };
+        while (t0 < g2.tz && !layer_inside(t0)) ++t0;
+        t1 = t0;
+        while (t1 < g2.tz && layer_inside(t1)) ++t1;
+        h->pre_tz0 = t0;
+        h->pre_tz1 = t1;
+        if (o1 > o0)
+            b4d_launch_to_match(d_basic + (long long)o0 * Pv, d_u + (long long)o0 * Pv, (long long)(o1 - o0) * Pv, 0.0f,
+                                mm.scale, mm.ishift, s);
+        B4D_TRY(zero_acc());
+        b4d_launch_block_energy_range(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, 1, o0, std::max(o0, o1 - 3), s);
+        if (R2 > 0)
+            b4d_launch_match_range(mp, p.search_wie, h->pre_cz0, std::max(h->pre_cz0, h->pre_cz1), t0 * tiles_per_layer,
+                                   t1 * tiles_per_layer, s);
+        h->pre_done = true;
+        CU_TRY(cudaGetLastError());
+        return 0;
+    }
+    if (phase == 2 && h->pre_done) {
+        // part 2: the rest of the front end (planes, origins, cells and tile layers outside the ranges of part 1)
+        const int o0 = h->pre_o0, o1 = h->pre_o1;
+        if (o0 > 0) b4d_launch_to_match(d_basic, d_u, (long long)o0 * Pv, 0.0f, mm.scale, mm.ishift, s);
+        if (o1 < pl.D)
+            b4d_launch_to_match(d_basic + (long long)o1 * Pv, d_u + (long long)o1 * Pv, (long long)(pl.D - o1) * Pv, 0.0f,
+                                mm.scale, mm.ishift, s);
+        b4d_launch_block_energy_range(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, 1, 0, std::min(o0, pl.D - 3), s);
+        b4d_launch_block_energy_range(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, 1, std::max(o0, o1 - 3), pl.D - 3, s);
+        clk.mark(B4D_T_PREP, 4);
+        if (R2 > 0) {
+            b4d_launch_match_range(mp, p.search_wie, 0, h->pre_cz0, 0, h->pre_tz0 * tiles_per_layer, s);
+            b4d_launch_match_range(mp, p.search_wie, std::max(h->pre_cz0, h->pre_cz1), cd2, h->pre_tz1 * tiles_per_layer,
+                                   (long long)g2.tz * tiles_per_layer, s);
+        }
+        clk.mark(B4D_T_MATCH2, 8);
+        h->pre_done = false;
+    } else {
+        if (!fused_match) b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
+        B4D_TRY(zero_acc());
+        b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
+        clk.mark(B4D_T_PREP, 3);
+        if (R2 > 0) b4d_launch_match(mp, p.search_wie, s);
+        clk.mark(B4D_T_MATCH2, 4);
+    }
     fp.g = g2;
     fp.basic = d_basic;
     fp.K = p.k_wie;
@@ -1113,6 +1170,7 @@ int b4d_slab_stage1_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3
                          &src));
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
+    h->pre_done = false;
     h->slab_cf = mm.cf;
     h->slab_scale = mm.scale;
     h->slab_ishift = src.used ? src.ishift : mm.ishift;
@@ -1151,6 +1209,7 @@ static int slab_stage2_impl(b4d_handle *h, int64_t own_begin, int64_t own_end, v
     cudaStream_t s = h->stream;
     const long long P = h->slab_shape[1] * h->slab_shape[2];
     const Plan pl = slab_plan_of(h);
+    const bool had_pre = h->pre_done;
     MatchMap mm;
     mm.cf = h->slab_cf;
     mm.scale = h->slab_scale;
@@ -1170,6 +1229,15 @@ static int slab_stage2_impl(b4d_handle *h, int64_t own_begin, int64_t own_end, v
                         (size_t)(own_end - own_begin) * P * esz, out_on_device, s));
     CU_TRY(cudaStreamSynchronize(s));
     clk.resolve();
+    if (had_pre) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->pre_ev0, h->pre_ev1) == cudaSuccess) {
+            h->t_ms[B4D_T_MATCH2] += ms;
+            h->launches[B4D_T_MATCH2] += 5;
+        } else {
+            cudaGetLastError();
+        }
+    }
     CU_TRY(cudaMemcpy(h->match_stats, h->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     h->slab_open = false;
     return 0;
@@ -1185,6 +1253,40 @@ int b4d_slab_stage2_q16(b4d_handle *h, int64_t own_begin, int64_t own_end, float
     q.step = step;
     q.trunc = truncate;
     return slab_stage2_impl(h, own_begin, own_end, out, out_on_device, &q);
+}
+
+float *b4d_slab_basic_ptr(b4d_handle *h) {
+    if (!h || !h->slab_open) {
+        fail(B4D_ERR_INVALID, "b4d_slab_stage1_u16 has not been called");
+        return nullptr;
+    }
+    return h->basic.as<float>();
+}
+
+int b4d_slab_stage2_begin(b4d_handle *h, int64_t own_begin, int64_t own_end) {
+    if (!h) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!h->slab_open) return fail(B4D_ERR_INVALID, "b4d_slab_stage1_u16 has not been called");
+    const int64_t zb = h->slab_z_begin, D = h->slab_shape[0];
+    if (own_begin < zb || own_end > zb + D || own_begin >= own_end)
+        return fail(B4D_ERR_INVALID, "owned range outside the slab");
+    CU_TRY(cudaSetDevice(h->device));
+    const Plan pl = slab_plan_of(h);
+    MatchMap mm;
+    mm.cf = h->slab_cf;
+    mm.scale = h->slab_scale;
+    mm.ishift = h->slab_ishift;
+    StageClock clk(h);
+    clk.mark(-1, 0);
+    h->pre_o0 = (int)(own_begin - zb);
+    h->pre_o1 = (int)(own_end - zb);
+    if (!h->pre_ev0) {
+        CU_TRY(cudaEventCreate(&h->pre_ev0));
+        CU_TRY(cudaEventCreate(&h->pre_ev1));
+    }
+    CU_TRY(cudaEventRecord(h->pre_ev0, h->stream));
+    B4D_TRY(run_pipeline(h, pl, h->zf.as<float>(), h->in.as<uint16_t>(), mm, h->slab_sigma, h->out.as<float>(), clk, 3));
+    CU_TRY(cudaEventRecord(h->pre_ev1, h->stream));
+    return 0;  // no synchronisation: the launches run while the caller exchanges planes
 }
 
 int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], float sigma, int32_t *idx,

@@ -266,8 +266,7 @@ def main():
     import torch.distributed as dist
 
     import b4d
-    from b4d.sharding import (denoise_slab_exchange, exchange_halo, halo_planes, merge_histograms, slab_plan,
-                              stats_from_hist)
+    from b4d.sharding import denoise_slab_exchange, exchange_halo, halo_planes, slab_plan, stats_from_hist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -292,6 +291,7 @@ def main():
     slab_pin = torch.empty(slab_dev.shape, dtype=torch.uint16, pin_memory=True)
     slab_pin.copy_(slab_dev)
     out_pin = torch.empty((own_e - own_b, S, S), dtype=torch.float32, pin_memory=True)
+    outq_pin = torch.empty((own_e - own_b, S, S), dtype=torch.uint16, pin_memory=True)
     torch.cuda.synchronize()
     if rank == 0:
         log("data: slab %s generated in %.1fs" % (tuple(slab_dev.shape), time.perf_counter() - t0))
@@ -302,29 +302,41 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def stats_step():
-        # the path's only collective: all-gather of per-slab histograms
+    def stats_begin():
+        # the path's only collective: all-gather of per-slab histograms.  N > 1: started asynchronously, it
+        # travels while the slab is denoised; stats_end() sums the parts and evaluates the statistics.
         st, hist = dn.tile_stats(slab_dev[own_b - zb : own_e - zb], 0.1, return_hist=True)
-        if world > 1:
-            total = merge_histograms(torch.from_numpy(hist).to(dev))
-            return stats_from_hist(total.cpu().numpy(), 0.1)
-        return st
+        if world == 1:
+            return st
+        mine = torch.from_numpy(hist).to(dev)
+        parts = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=dev)
+        return (dist.all_gather_into_tensor(parts, mine, async_op=True), parts, mine)
+
+    def stats_end(tok):
+        if world == 1:
+            return tok
+        tok[0].wait()
+        return stats_from_hist(tok[1].sum(0).cpu().numpy(), 0.1)
 
     def step_resident():
-        st = stats_step()
+        tok = stats_begin()
         if exchange:  # stage 1, neighbour exchange of basic-estimate planes (NCCL p2p), stage 2
             y = denoise_slab_exchange(dn, slab_dev, zb, S, own_b, own_e, SIGMA, rank, world, device=dev)
         else:
             y = dn.denoise_slab(slab_dev, zb, S, own_b, own_e, SIGMA)
-        return st, y
+        return stats_end(tok), y
 
-    def step_e2e():
-        # host in -> host out through the public API; H2D and D2H happen inside the call
+    # end to end, host in -> host out through the public API; H2D and D2H happen inside the call.  The path named
+    # by BASELINE.json ends in the quantizer: the fused form returns the uint16 volume (denoise -> background-offset
+    # subtract -> quantize, 2 bytes per voxel back to the host); the float32 form (the bm4d() return value, 4 bytes
+    # per voxel) is timed as well and reported as e2e_float32.
+    def step_e2e(quant=None, host_in=None, host_out=None):
+        src = slab_pin.numpy() if host_in is None else host_in
+        dst = (outq_pin.numpy() if quant is not None else out_pin.numpy()) if host_out is None else host_out
         if exchange:
-            denoise_slab_exchange(dn, slab_pin.numpy(), zb, S, own_b, own_e, SIGMA, rank, world, device=dev,
-                                  out=out_pin.numpy())
+            denoise_slab_exchange(dn, src, zb, S, own_b, own_e, SIGMA, rank, world, device=dev, out=dst, quantize=quant)
         else:
-            dn.denoise_slab(slab_pin.numpy(), zb, S, own_b, own_e, SIGMA, out=out_pin.numpy())
+            dn.denoise_slab(src, zb, S, own_b, own_e, SIGMA, out=dst, quantize=quant)
 
     # ---- warm-up (also sizes the scratch buffers)
     stats = None
@@ -390,7 +402,16 @@ def main():
     cratio_est = b4d.estimate_cratio(chist.cpu().numpy()) if rank == 0 else None
     del y_last, qv, cby, chist
 
-    # ---- timed: end to end with host buffers
+    # ---- timed: end to end with host buffers (pinned): quantized uint16 result, then the float32 result
+    quant = (float(stats["offset"]), 0.0, 1.0)
+    step_e2e(quant)
+    barrier()
+    ev0.record(ext)
+    for _ in range(args.steps):
+        step_e2e(quant)
+    ev1.record(ext)
+    barrier()
+    dt_e2e = ev0.elapsed_time(ev1) * 1e-3
     step_e2e()
     barrier()
     ev0.record(ext)
@@ -398,7 +419,7 @@ def main():
         step_e2e()
     ev1.record(ext)
     barrier()
-    dt_e2e = ev0.elapsed_time(ev1) * 1e-3
+    dt_e2e_f32 = ev0.elapsed_time(ev1) * 1e-3
 
     # ---- the same with ordinary (pageable) NumPy arrays, what the reference's callers hand over: the
     # library stages them through its pinned ring (HostMover).  Wall clock between barriers (the call
@@ -406,25 +427,19 @@ def main():
     slab_np = np.array(slab_pin.numpy(), copy=True)
     out_np = np.empty(tuple(out_pin.shape), dtype=np.float32)
 
-    def step_pageable():
-        if exchange:
-            denoise_slab_exchange(dn, slab_np, zb, S, own_b, own_e, SIGMA, rank, world, device=dev, out=out_np)
-        else:
-            dn.denoise_slab(slab_np, zb, S, own_b, own_e, SIGMA, out=out_np)
-
-    step_pageable()
+    step_e2e(None, slab_np, out_np)
     barrier()
     t_pg = time.perf_counter()
     for _ in range(args.steps):
-        step_pageable()
+        step_e2e(None, slab_np, out_np)
     barrier()
     dt_pg = time.perf_counter() - t_pg
     del slab_np, out_np
 
-    times = torch.tensor([dt, dt_e2e, dt_pg], dtype=torch.float64, device=dev)
+    times = torch.tensor([dt, dt_e2e, dt_pg, dt_e2e_f32], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt, dt_e2e, dt_pg = float(times[0]), float(times[1]), float(times[2])
+    dt, dt_e2e, dt_pg, dt_e2e_f32 = (float(t) for t in times)
     h2d = torch.tensor([slab_pin.numel() * 2, out_pin.numel() * 4, launches], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
@@ -492,11 +507,15 @@ def main():
                 timing="CUDA events on the library stream around the K steps, between barrier + synchronize, max over ranks",
             ),
             "e2e": {"value": V * args.steps / dt_e2e, "unit": "voxels/s",
-                    "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1]),
-                    "host_buffers": "pinned"},
+                    "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1]) // 2,
+                    "host_buffers": "pinned",
+                    "result": "uint16 volume of the fused denoise -> offset subtract -> quantize call (the path's output)"},
+            "e2e_float32": {"value": V * args.steps / dt_e2e_f32, "unit": "voxels/s",
+                            "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1]),
+                            "host_buffers": "pinned", "result": "float32 volume (the bm4d() return value)"},
             "e2e_pageable": {"value": V * args.steps / dt_pg, "unit": "voxels/s",
                              "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(h2d[1]),
-                             "host_buffers": "pageable NumPy arrays (the reference's call surface), wall clock"},
+                             "host_buffers": "pageable NumPy arrays (the reference's call surface), float32 result, wall clock"},
             "cpus_bound_to_gpu_numa_node": numa_cpus,
             "gpu_launches": int(h2d[2]),
             "clocks": clocks,

@@ -159,6 +159,14 @@ int b4d_slab_stage1_u16(b4d_handle *h, const uint16_t *in, const int64_t shape[3
 int b4d_slab_basic_planes(b4d_handle *h, int64_t plane0, int64_t nplanes, float *buf, int to_handle,
                           int buf_on_device);
 int b4d_slab_stage2(b4d_handle *h, int64_t own_begin, int64_t own_end, float *out, int out_on_device);
+/* Optional, between 1 and 3, for callers that exchange planes device to device:
+ *   b4d_slab_basic_ptr      device pointer to the basic estimate of the open slab, [D][H][W] float32 — a neighbour
+ *                           exchange (NCCL point-to-point) may read the owned planes and write the halo planes in place;
+ *   b4d_slab_stage2_begin   launches, without waiting, the part of the stage-2 front end (matching image, block
+ *                           energies, tile classification, matching) that reads owned planes only, so that the
+ *                           exchange overlaps it; b4d_slab_stage2 then does the rest.  The result is unchanged. */
+float *b4d_slab_basic_ptr(b4d_handle *h);
+int b4d_slab_stage2_begin(b4d_handle *h, int64_t own_begin, int64_t own_end);
 /* the same with the fused quantizer (see b4d_denoise_q16_u16) */
 int b4d_slab_stage2_q16(b4d_handle *h, int64_t own_begin, int64_t own_end, float offset_sub,
                         float offset_add, float step, int truncate, uint16_t *out, int out_on_device);

@@ -1126,6 +1126,10 @@ int b4d_slab_basic_planes(b4d_handle *, int64_t, int64_t, float *, int, int) {
 int b4d_slab_stage2(b4d_handle *, int64_t, int64_t, float *, int) {
     return fail(B4D_ERR_UNSUPPORTED, "oracle: use b4d_denoise_slab_u16");
 }
+float *b4d_slab_basic_ptr(b4d_handle *) { return nullptr; }
+int b4d_slab_stage2_begin(b4d_handle *, int64_t, int64_t) {
+    return fail(B4D_ERR_UNSUPPORTED, "oracle: use b4d_denoise_slab_u16");
+}
 int b4d_last_timings(b4d_handle *, float *, int64_t *) {
     return fail(B4D_ERR_UNSUPPORTED, "no device timings in the oracle");
 }

@@ -344,8 +344,9 @@ def test_float_input_with_a_large_dc_level(dn, oracle_lib):
         ulp = float(np.spacing(np.float32(abs(dc) + 65536.0)))
         assert np.abs(y.astype(np.float64) - f).max() <= max(ulp, 0.5)
         # against the DC-free result: the same image up to float32 spacing, except under a flipped near-tied match
-        delta = np.abs((y.astype(np.float64) - dc) - base)
-        assert np.median(delta) <= 2 * ulp + 1e-3 and delta.max() <= 4.0
+        if ulp < 0.1:  # (at 3e7 the float32 spacing is 2: adding the DC level already changed the data)
+            delta = np.abs((y.astype(np.float64) - dc) - base)
+            assert np.median(delta) <= 2 * ulp + 1e-3 and delta.max() <= 4.0
     x = np.random.default_rng(0).normal(1000.0, 0.05, (20, 21, 22)).astype(np.float32)  # non-integral, sigma << DC
     y = dn.denoise(x, 0.05)
     assert np.array_equal(y, oracle_lib.Oracle("mirror").denoise(x, 0.05))
@@ -464,6 +465,56 @@ def test_exchange_variant_slabs_equal_whole(b4d_mod):
             parts.append(d.slab_stage2(ob, oe))
             d.close()
         assert np.array_equal(np.concatenate(parts, 0), whole)
+
+
+def test_overlapped_exchange_form_equals_whole(b4d_mod):
+    """The device form of the exchange variant: after stage 1 every rank launches the part of the stage-2 front end
+    that needs owned planes only (b4d_slab_stage2_begin, no wait) while the neighbours' planes are written straight
+    into its basic-estimate buffer (b4d_slab_basic_ptr, zero-copy torch views; here a device-to-device copy stands
+    in for the NCCL point-to-point).  Union of the owned planes == whole volume, bit for bit — float32 and the
+    fused uint16 quantizer."""
+    import torch
+
+    from b4d import synth
+    from b4d.sharding import exchange_halo, slab_plan
+
+    dev = torch.device("cuda", 0)
+    vol = synth.vol(120, 40, 36, seed=19)
+    whole_dn = b4d_mod.Denoiser(0)
+    whole = whole_dn.denoise(vol, 24.0)
+    whole_q = whole_dn.quantize(whole, 36.5, 0.0, 2.0)
+    h = exchange_halo(11, 11)
+    for world in (2, 3):
+        ranks = []
+        for r in range(world):
+            ob, oe, zb, ze = slab_plan(120, world, r, h)
+            d = b4d_mod.Denoiser(0)
+            d.slab_stage1(torch.from_numpy(vol[zb:ze]).to(dev), zb, 120, 24.0)
+            ranks.append((d, ob, oe, zb, ze, d.slab_basic_tensor(dev)))
+        torch.cuda.synchronize()
+        sends = [(b[ob - zb : ob - zb + h].clone(), b[oe - zb - h : oe - zb].clone()) for d, ob, oe, zb, ze, b in ranks]
+        for d, ob, oe, zb, ze, b in ranks:
+            d.slab_stage2_begin(ob, oe)  # runs while the planes below are "exchanged"
+        for r, (d, ob, oe, zb, ze, b) in enumerate(ranks):
+            if r > 0:
+                b[0 : ob - zb].copy_(sends[r - 1][1])
+            if r < world - 1:
+                b[oe - zb : oe - zb + h].copy_(sends[r + 1][0])
+        torch.cuda.synchronize()
+        parts, qparts = [], []
+        for r, (d, ob, oe, zb, ze, b) in enumerate(ranks):
+            if r % 2 == 0:
+                parts.append(d.slab_stage2(ob, oe, device=dev).cpu().numpy())
+                qparts.append(None)
+            else:
+                qparts.append(d.slab_stage2(ob, oe, device=dev, quantize=(36.5, 0.0, 2.0)).cpu().numpy())
+                parts.append(None)
+            d.close()
+        for r, (d, ob, oe, zb, ze, b) in enumerate(ranks):
+            if parts[r] is not None:
+                assert np.array_equal(parts[r], whole[ob:oe]), "world %d rank %d" % (world, r)
+            else:
+                assert np.array_equal(qparts[r], whole_q[ob:oe]), "world %d rank %d (quantized)" % (world, r)
 
 
 def test_pipelined_host_transfers_equal_device_result(b4d_mod):
