@@ -48,6 +48,7 @@ EXPORTS = (
     "b4d_slab_stage2_q16",
     "b4d_slab_basic_ptr",
     "b4d_slab_stage2_begin",
+    "b4d_stats_from_hist",
 )
 
 

@@ -1577,28 +1577,7 @@ int b4d_chunk_shuffle_u16(b4d_handle *h, const uint16_t *in, const int64_t shape
     return 0;
 }
 
-int b4d_tile_stats(b4d_handle *h, const uint16_t *in, int64_t n, double pct, b4d_stats *out, int64_t *hist_out,
-                   int in_on_device) {
-    if (!h || !in || !out || n < 1) return fail(B4D_ERR_INVALID, "NULL argument or empty tile");
-    if (!(pct >= 0.0 && pct <= 100.0)) return fail(B4D_ERR_INVALID, "percentile must be in [0, 100]");
-    CU_TRY(cudaSetDevice(h->device));
-    cudaStream_t s = h->stream;
-    const uint16_t *d_in = in;
-    if (!in_on_device || (reinterpret_cast<uintptr_t>(in) & 15)) {
-        B4D_TRY(h->in.ensure((size_t)n * sizeof(uint16_t)));
-        CU_TRY(copy_in(h, h->in.p, in, (size_t)n * sizeof(uint16_t), in_on_device, s));
-        d_in = h->in.as<uint16_t>();
-    }
-    B4D_TRY(h->hist.ensure(65536 * sizeof(unsigned long long)));
-    CU_TRY(cudaMemsetAsync(h->hist.p, 0, 65536 * sizeof(unsigned long long), s));
-    b4d_launch_hist(d_in, n, h->hist.as<unsigned long long>(), s);
-    CU_TRY(cudaGetLastError());
-    std::vector<unsigned long long> hist(65536);
-    CU_TRY(cudaMemcpyAsync(hist.data(), h->hist.p, 65536 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
-    if (hist_out)
-        for (int v = 0; v < 65536; ++v) hist_out[v] = (int64_t)hist[v];
-
+static int stats_of_hist(const std::vector<unsigned long long> &hist, int64_t n, double pct, b4d_stats *out) {
     std::memset(out, 0, sizeof(*out));
     out->n = n;
     out->n_nonzero = n - (int64_t)hist[0];
@@ -1638,6 +1617,47 @@ int b4d_tile_stats(b4d_handle *h, const uint16_t *in, int64_t n, double pct, b4d
     out->mad = mad;
     out->sigma = sig;
     return 0;
+}
+
+int b4d_tile_stats(b4d_handle *h, const uint16_t *in, int64_t n, double pct, b4d_stats *out, int64_t *hist_out,
+                   int in_on_device) {
+    if (!h || !in || !out || n < 1) return fail(B4D_ERR_INVALID, "NULL argument or empty tile");
+    if (!(pct >= 0.0 && pct <= 100.0)) return fail(B4D_ERR_INVALID, "percentile must be in [0, 100]");
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const uint16_t *d_in = in;
+    if (!in_on_device || (reinterpret_cast<uintptr_t>(in) & 15)) {
+        B4D_TRY(h->in.ensure((size_t)n * sizeof(uint16_t)));
+        CU_TRY(copy_in(h, h->in.p, in, (size_t)n * sizeof(uint16_t), in_on_device, s));
+        d_in = h->in.as<uint16_t>();
+    }
+    B4D_TRY(h->hist.ensure(65536 * sizeof(unsigned long long)));
+    CU_TRY(cudaMemsetAsync(h->hist.p, 0, 65536 * sizeof(unsigned long long), s));
+    b4d_launch_hist(d_in, n, h->hist.as<unsigned long long>(), s);
+    CU_TRY(cudaGetLastError());
+    std::vector<unsigned long long> hist(65536);
+    CU_TRY(cudaMemcpyAsync(hist.data(), h->hist.p, 65536 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (hist_out)
+        for (int v = 0; v < 65536; ++v) hist_out[v] = (int64_t)hist[v];
+
+    return stats_of_hist(hist, n, pct, out);
+}
+
+// The statistics of an exact 65 536-bin histogram (any number of merged tiles): what b4d_tile_stats evaluates
+// after its counting kernel; host arithmetic only.  Ranks that all-gather their histograms call it on the sum.
+int b4d_stats_from_hist(const int64_t *hist_in, double pct, b4d_stats *out) {
+    if (!hist_in || !out) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!(pct >= 0.0 && pct <= 100.0)) return fail(B4D_ERR_INVALID, "percentile must be in [0, 100]");
+    std::vector<unsigned long long> hist(65536);
+    long long n = 0;
+    for (int v = 0; v < 65536; ++v) {
+        if (hist_in[v] < 0) return fail(B4D_ERR_INVALID, "negative count");
+        hist[v] = (unsigned long long)hist_in[v];
+        n += hist_in[v];
+    }
+    if (n < 1) return fail(B4D_ERR_INVALID, "empty histogram");
+    return stats_of_hist(hist, n, pct, out);
 }
 
 int b4d_last_timings(b4d_handle *h, float ms[B4D_T_COUNT], int64_t launches[B4D_T_COUNT]) {

@@ -255,6 +255,7 @@ def main():
     ap.add_argument("--impl", default="b4d", choices=["b4d", "reference"])
     ap.add_argument("--size", type=int, default=1024, help="volume side (default 1024: the metric's config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stats", action="store_true", help="diagnostic: leave the statistics pass out of the step")
     ap.add_argument("--no-exchange", action="store_true",
                     help="N > 1: 26-plane halos and no data-path exchange instead of 13-plane halos + one "
                          "neighbour exchange of basic-estimate planes between the stages")
@@ -266,7 +267,7 @@ def main():
     import torch.distributed as dist
 
     import b4d
-    from b4d.sharding import denoise_slab_exchange, exchange_halo, halo_planes, slab_plan, stats_from_hist
+    from b4d.sharding import denoise_slab_exchange, exchange_halo, halo_planes, slab_plan, stats_from_hist_lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -316,15 +317,28 @@ def main():
         if world == 1:
             return tok
         tok[0].wait()
-        return stats_from_hist(tok[1].sum(0).cpu().numpy(), 0.1)
+        return stats_from_hist_lib(tok[1].sum(0).cpu().numpy(), 0.1)
+
+    host_ms = {"stats_begin": 0.0, "denoise": 0.0, "stats_end": 0.0}
 
     def step_resident():
-        tok = stats_begin()
+        t0 = time.perf_counter()
+        if args.no_stats and stats is not None:
+            tok = None
+        else:
+            tok = stats_begin()
+        t1 = time.perf_counter()
         if exchange:  # stage 1, neighbour exchange of basic-estimate planes (NCCL p2p), stage 2
             y = denoise_slab_exchange(dn, slab_dev, zb, S, own_b, own_e, SIGMA, rank, world, device=dev)
         else:
             y = dn.denoise_slab(slab_dev, zb, S, own_b, own_e, SIGMA)
-        return stats_end(tok), y
+        t2 = time.perf_counter()
+        st = stats if tok is None else stats_end(tok)
+        t3 = time.perf_counter()
+        host_ms["stats_begin"] += (t1 - t0) * 1e3
+        host_ms["denoise"] += (t2 - t1) * 1e3
+        host_ms["stats_end"] += (t3 - t2) * 1e3
+        return st, y
 
     # end to end, host in -> host out through the public API; H2D and D2H happen inside the call.  The path named
     # by BASELINE.json ends in the quantizer: the fused form returns the uint16 volume (denoise -> background-offset
@@ -368,6 +382,7 @@ def main():
     ev1.record(ext)
     barrier()
     dt = ev0.elapsed_time(ev1) * 1e-3
+    log("rank %d host ms per step (warm-up included): %s" % (rank, {k: round(v / (args.steps + max(args.warmup, 3)), 2) for k, v in host_ms.items()}))
     clocks = sampler.stop() if rank == 0 else None
     mstats = dn.last_match_stats()
 

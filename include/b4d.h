@@ -235,6 +235,9 @@ int b4d_chunk_shuffle_u16(b4d_handle *h, const uint16_t *in, const int64_t shape
  * payload ranks allgather to agree on a global offset / sigma. */
 int b4d_tile_stats(b4d_handle *h, const uint16_t *in, int64_t n, double pct, b4d_stats *out,
                    int64_t *hist, int in_on_device);
+/* The same statistics from an exact 65 536-bin histogram of counts (e.g. the sum of the per-slab histograms the
+ * ranks all-gather): host arithmetic only, no device work. */
+int b4d_stats_from_hist(const int64_t *hist, double pct, b4d_stats *out);
 
 /* Device time of the last denoise call, per kernel family, in milliseconds
  * (CUDA events on the handle's stream).  names: see B4D_T_* below. */

@@ -1022,6 +1022,9 @@ int b4d_slab_stage2_q16(b4d_handle *, int64_t, int64_t, float, float, float, int
 int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *, int64_t *, int) {
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }
+int b4d_stats_from_hist(const int64_t *, double, b4d_stats *) {
+    return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
+}
 void *b4d_stream(b4d_handle *) { return nullptr; }
 int b4d_set_pass_voxels(b4d_handle *, int64_t) { return 0; }
 int b4d_set_pipeline_min_voxels(b4d_handle *, int64_t) { return 0; }  // the CPU restatement has no passes

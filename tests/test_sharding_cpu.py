@@ -147,3 +147,17 @@ def test_neighbour_plane_exchange_three_ranks():
         assert p.exitcode == 0
     # rank r receives rank r-1's `up` (10(r-1)+2) from below and rank r+1's `down` (10(r+1)+1) from above
     assert res[0] == (0, None, 11.0) and res[1] == (1, 2.0, 21.0) and res[2] == (2, 12.0, None)
+
+
+def test_library_statistics_of_a_merged_histogram_equal_the_numpy_form():
+    """b4d_stats_from_hist (host arithmetic of libb4d, what the ranks evaluate on the summed histogram inside the
+    step) against the NumPy form, which the golden tests pin to the reference's estimate_offset / robust sigma."""
+    from b4d.sharding import stats_from_hist, stats_from_hist_lib
+
+    rng = np.random.default_rng(3)
+    for n, mu, pct in ((200001, 40.0, 0.1), (1000, 300.0, 1.0), (77777, 5.0, 50.0), (4096, 0.2, 1.0)):
+        h = np.zeros(65536, np.int64)
+        np.add.at(h, np.clip(rng.normal(mu, 24, n), 0, 65535).astype(np.int64), 1)
+        a, b = stats_from_hist(h, pct), stats_from_hist_lib(h, pct)
+        for k in ("n", "n_nonzero", "offset", "median", "mad", "sigma"):
+            assert a[k] == b[k], (k, a, b)
