@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     noise_scaled_step,
     precompute_targets,
     quantize,
+    patch_has_incoherent_segment,
     denoise_quantized,
     tile_stats,
 )
@@ -42,6 +43,7 @@ __all__ = [
     "noise_scaled_step",
     "precompute_targets",
     "quantize",
+    "patch_has_incoherent_segment",
     "denoise_quantized",
     "tile_stats",
     "slab_plan",

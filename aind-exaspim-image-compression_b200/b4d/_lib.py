@@ -49,6 +49,7 @@ EXPORTS = (
     "b4d_slab_basic_ptr",
     "b4d_slab_stage2_begin",
     "b4d_stats_from_hist",
+    "b4d_coherence_gate",
 )
 
 
@@ -116,6 +117,13 @@ def load():
         raise B4DLibraryError("libb4d.so ABI %d != binding ABI %d" % (lib.b4d_version(), ABI_VERSION))
     _lib = lib
     return lib
+
+
+class SegmentScore(ctypes.Structure):
+    """Mirror of ``struct b4d_segment_score`` (include/b4d.h)."""
+
+    _fields_ = [("label", ctypes.c_uint64), ("voxels", ctypes.c_int64), ("autocorr", ctypes.c_double),
+                ("highfreq", ctypes.c_double)]
 
 
 def check(rc):

@@ -590,6 +590,46 @@ class Denoiser:
         d = {k: getattr(st, k) for k, _ in _lib.Stats._fields_}
         return (d, hist) if return_hist else d
 
+    def coherence_scores(self, labels, raw, smooth_sigma=1.0, coherence_lag=2, min_autocorr=0.4,
+                         max_highfreq_frac=0.35, min_segment_voxels=50, max_segments=1024):
+        """The spatial-coherence gate of the sampler (metrics.py:189-260) on the device, for one patch (3-D arrays)
+        or a batch (4-D): returns (reject[n] bool, [ {label: (voxels, autocorr, highfreq)} per patch ])."""
+        lab = np.ascontiguousarray(labels, dtype=np.uint64)
+        x = np.ascontiguousarray(raw, dtype=np.float32)
+        if lab.shape != x.shape or x.ndim not in (3, 4):
+            raise ValueError("labels and raw must be 3-D (or batched 4-D) arrays of the same shape")
+        n = 1 if x.ndim == 3 else x.shape[0]
+        shape = x.shape[-3:]
+        reject = np.zeros(n, dtype=np.uint8)
+        seg = (_lib.SegmentScore * (n * max_segments))()
+        cnt = np.zeros(n, dtype=np.int64)
+        _lib.check(
+            self.lib.b4d_coherence_gate(
+                self._h, x.ctypes.data_as(ctypes.c_void_p), lab.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n),
+                _lib.shape3(shape), ctypes.c_double(min_autocorr), ctypes.c_double(max_highfreq_frac),
+                ctypes.c_int64(min_segment_voxels), ctypes.c_double(smooth_sigma), ctypes.c_int(coherence_lag),
+                reject.ctypes.data_as(ctypes.c_void_p), seg, ctypes.c_int64(max_segments),
+                cnt.ctypes.data_as(ctypes.c_void_p), 0,
+            )
+        )
+        tables = []
+        for i in range(n):
+            if cnt[i] > max_segments:
+                raise ValueError("patch %d holds %d segments, max_segments is %d" % (i, cnt[i], max_segments))
+            tables.append({int(seg[i * max_segments + j].label): (int(seg[i * max_segments + j].voxels),
+                                                                   float(seg[i * max_segments + j].autocorr),
+                                                                   float(seg[i * max_segments + j].highfreq))
+                           for j in range(int(cnt[i]))})
+        return reject.astype(bool), tables
+
+    def patch_has_incoherent_segment(self, labels, raw, min_autocorr=0.4, max_highfreq_frac=0.35,
+                                     min_segment_voxels=50, smooth_sigma=1.0, coherence_lag=2):
+        """Drop-in for metrics.patch_has_incoherent_segment (same arguments, same bool); a 4-D batch returns one bool
+        per patch."""
+        rej, _ = self.coherence_scores(labels, raw, smooth_sigma, coherence_lag, min_autocorr, max_highfreq_frac,
+                                       min_segment_voxels)
+        return bool(rej[0]) if np.ndim(raw) == 3 else rej
+
     def stream_ptr(self):
         """cudaStream_t of the handle (int): wrap it in torch.cuda.ExternalStream to
         record CUDA events around calls."""
@@ -725,6 +765,13 @@ def quantize(x, offset_sub=0.0, offset_add=0.0, step=1.0, device=None, truncate=
 def denoise_quantized(vol, sigma, offset_sub=0.0, offset_add=0.0, step=1.0, truncate=False, device=None):
     """Denoise -> background-offset subtract -> (noise-scaled) quantize of one uint16 volume, fused on the device."""
     return get_denoiser(device).denoise_quantized(vol, sigma, offset_sub, offset_add, step, truncate)
+
+
+def patch_has_incoherent_segment(labels, raw, min_autocorr=0.4, max_highfreq_frac=0.35, min_segment_voxels=50,
+                                 smooth_sigma=1.0, coherence_lag=2, device=None):
+    """metrics.patch_has_incoherent_segment (metrics.py:189-260) on the device; same arguments and result."""
+    return get_denoiser(device).patch_has_incoherent_segment(labels, raw, min_autocorr, max_highfreq_frac,
+                                                             min_segment_voxels, smooth_sigma, coherence_lag)
 
 
 def noise_scaled_step(sigma_tile, kappa):

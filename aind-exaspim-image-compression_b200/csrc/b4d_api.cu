@@ -70,6 +70,7 @@ struct b4d_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // host transfers (and the normalise of finished planes) overlapped with kernels
     b4d_profile prof;
+    DevBuf coh_x, coh_sm, coh_tmp, coh_keys, coh_sums, coh_lab, coh_w;
     DevBuf in, u16, zf, numq, gmap, basic, out, widx, cnt, ssd, refs, hist, partial, sink, stats, s2, cells, tcls;
     DevBuf alt_in, alt_zf, alt_out, alt_partial, alt_sink;  // second buffer set of b4d_targets_u16
     float t_ms[B4D_T_COUNT];
@@ -849,6 +850,7 @@ int b4d_create(int device, const b4d_profile *profile, b4d_handle **out) {
 void b4d_destroy(b4d_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    for (DevBuf *b : {&h->coh_x, &h->coh_sm, &h->coh_tmp, &h->coh_keys, &h->coh_sums, &h->coh_lab, &h->coh_w}) b->release();
     for (DevBuf *b : {&h->in, &h->u16, &h->zf, &h->numq, &h->gmap, &h->basic, &h->out, &h->widx, &h->cnt,
                       &h->ssd, &h->refs, &h->hist, &h->partial, &h->sink, &h->stats, &h->s2, &h->cells, &h->tcls,
                       &h->alt_in, &h->alt_zf, &h->alt_out, &h->alt_partial, &h->alt_sink})
@@ -1675,6 +1677,100 @@ void *b4d_stream(b4d_handle *h) { return h ? (void *)h->stream : nullptr; }
 int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]) {
     if (!h || !out) return fail(B4D_ERR_INVALID, "NULL argument");
     for (int i = 0; i < 4; ++i) out[i] = h->match_stats[i];
+    return 0;
+}
+
+int b4d_coherence_gate(b4d_handle *h, const float *raw, const uint64_t *labels, int64_t n, const int64_t shape[3],
+                       double min_autocorr, double max_highfreq_frac, int64_t min_segment_voxels, double smooth_sigma,
+                       int lag, uint8_t *reject, b4d_segment_score *seg, int64_t max_segments, int64_t *seg_count,
+                       int in_on_device) {
+    if (!h || !raw || !labels || !shape || !reject || n < 1) return fail(B4D_ERR_INVALID, "NULL argument or n < 1");
+    for (int i = 0; i < 3; ++i)
+        if (shape[i] < 1 || shape[i] > 65535) return fail(B4D_ERR_INVALID, "every dimension must be in [1, 65535]");
+    if (!(smooth_sigma > 0) || smooth_sigma > 8.0) return fail(B4D_ERR_INVALID, "smooth_sigma must be in (0, 8]");
+    if (lag < 1) return fail(B4D_ERR_INVALID, "lag must be >= 1");
+    if (seg && (!seg_count || max_segments < 1)) return fail(B4D_ERR_INVALID, "seg needs seg_count and max_segments");
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int D = (int)shape[0], H = (int)shape[1], W = (int)shape[2];
+    const long long V = (long long)D * H * W, TV = V * n;
+    constexpr int CAP = 1024, NS = 23;
+    // scipy.ndimage.gaussian_filter: radius int(truncate * sigma + 0.5), truncate = 4; weights exp(-x^2 / (2 sigma^2))
+    // normalised to sum 1, float64
+    const int radius = (int)(4.0 * smooth_sigma + 0.5);
+    std::vector<double> w((size_t)2 * radius + 1);
+    double wsum = 0.0;
+    for (int k = -radius; k <= radius; ++k) wsum += (w[(size_t)(k + radius)] = std::exp(-0.5 / (smooth_sigma * smooth_sigma) * k * k));
+    for (auto &v : w) v /= wsum;
+    B4D_TRY(h->coh_x.ensure((size_t)TV * sizeof(double)));
+    B4D_TRY(h->coh_sm.ensure((size_t)TV * sizeof(double)));
+    B4D_TRY(h->coh_tmp.ensure((size_t)TV * sizeof(double)));
+    B4D_TRY(h->coh_keys.ensure((size_t)n * CAP * sizeof(unsigned long long)));
+    B4D_TRY(h->coh_sums.ensure((size_t)n * CAP * NS * sizeof(double) + 64));
+    B4D_TRY(h->coh_w.ensure(w.size() * sizeof(double) + 64));
+    const float *d_raw = raw;
+    const unsigned long long *d_lab = reinterpret_cast<const unsigned long long *>(labels);
+    if (!in_on_device) {
+        B4D_TRY(h->in.ensure((size_t)TV * sizeof(float)));
+        B4D_TRY(h->coh_lab.ensure((size_t)TV * sizeof(unsigned long long)));
+        CU_TRY(copy_in(h, h->in.p, raw, (size_t)TV * sizeof(float), 0, s));
+        CU_TRY(copy_in(h, h->coh_lab.p, labels, (size_t)TV * sizeof(unsigned long long), 0, s));
+        d_raw = h->in.as<float>();
+        d_lab = h->coh_lab.as<unsigned long long>();
+    }
+    CU_TRY(cudaMemcpyAsync(h->coh_w.p, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    int *d_over = reinterpret_cast<int *>(h->coh_w.as<char>() + w.size() * sizeof(double));
+    b4d_launch_coherence(d_raw, d_lab, D, H, W, n, lag, radius, h->coh_w.as<double>(), h->coh_x.as<double>(),
+                         h->coh_sm.as<double>(), h->coh_tmp.as<double>(), h->coh_keys.as<unsigned long long>(), CAP,
+                         h->coh_sums.as<double>(), d_over, s);
+    CU_TRY(cudaGetLastError());
+    std::vector<unsigned long long> keys((size_t)n * CAP);
+    std::vector<double> sums((size_t)n * CAP * NS);
+    int over = 0;
+    CU_TRY(cudaMemcpyAsync(keys.data(), h->coh_keys.p, keys.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(sums.data(), h->coh_sums.p, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (over) return fail(B4D_ERR_UNSUPPORTED, "a patch holds more than 1024 distinct labels");
+    for (int64_t i = 0; i < n; ++i) {
+        reject[i] = 0;
+        int64_t cnt = 0;
+        for (int slot = 0; slot < CAP; ++slot) {
+            const unsigned long long key = keys[(size_t)i * CAP + slot];
+            if (!key) continue;
+            const double *q = &sums[((size_t)i * CAP + slot) * NS];
+            const double nv = q[0];
+            // local_autocorr (metrics.py:96-112): per axis, pairs inside the segment; skipped when fewer than two
+            // pairs or a standard deviation below 1e-6; mean over the axes left, 1.0 when none is
+            double acs = 0.0;
+            int nax = 0;
+            for (int a = 0; a < 3; ++a) {
+                const double *p = q + 5 + 6 * a;
+                const double np_ = p[0];
+                if (np_ < 2.0) continue;
+                const double mx = p[1] / np_, my = p[2] / np_;
+                const double vx = std::max(p[3] / np_ - mx * mx, 0.0), vy = std::max(p[4] / np_ - my * my, 0.0);
+                if (std::sqrt(vx) < 1e-6 || std::sqrt(vy) < 1e-6) continue;
+                acs += (p[5] / np_ - mx * my) / std::sqrt(vx * vy);
+                ++nax;
+            }
+            const double autocorr = nax ? acs / nax : 1.0;
+            // highfreq_energy_fraction (metrics.py:148-155): population variances over the segment
+            const double mv = q[1] / nv, mh = q[3] / nv;
+            const double vv = std::max(q[2] / nv - mv * mv, 0.0), vh = std::max(q[4] / nv - mh * mh, 0.0);
+            const double hf = vv < 1e-12 ? 0.0 : vh / vv;
+            if ((int64_t)nv >= min_segment_voxels && autocorr < min_autocorr && hf > max_highfreq_frac) reject[i] = 1;
+            if (seg && cnt < max_segments) {
+                b4d_segment_score &o = seg[i * max_segments + cnt];
+                o.label = key;
+                o.voxels = (int64_t)nv;
+                o.autocorr = autocorr;
+                o.highfreq = hf;
+            }
+            ++cnt;
+        }
+        if (seg_count) seg_count[i] = cnt;
+    }
     return 0;
 }
 

@@ -115,6 +115,10 @@ void b4d_launch_fg_mask(const uint16_t *in, const float *off, const float *thr, 
 // K9: C-order chunk gather + 2-byte shuffle (+ per-chunk byte histograms [nchunks][2][256])
 void b4d_launch_chunk_shuffle(const uint16_t *in, int D, int H, int W, int cz, int cy, int cx, uint8_t *out,
                               uint32_t *hist, cudaStream_t s);
+// coherence gate (b4d_coherence.cu): 23 sums per (patch, label slot), see there
+void b4d_launch_coherence(const float *raw, const unsigned long long *labels, int D, int H, int W, long long npatch,
+                          int lag, int radius, const double *w, double *x, double *sm, double *tmp,
+                          unsigned long long *keys, int cap, double *sums, int *overflow, cudaStream_t s);
 // analysis of a float32 volume for the matching map: partial[6*blocks] doubles
 int b4d_analyze_blocks();
 void b4d_launch_analyze(const float *in, long long n, double c, double *partial, cudaStream_t s);

@@ -268,6 +268,23 @@ int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]);
  *   out[3] = FFMA lane-ops/s.                                                */
 int b4d_measure_pipe_peaks(b4d_handle *h, double out[4]);
 
+/* The spatial-coherence gate that precedes BM4D in the sampler (machine_learning/metrics.py:189-260
+ * patch_has_incoherent_segment, with local_autocorr :64-112 and highfreq_energy_fraction :115-155; call site
+ * data_handling.py:398-407), for `n` equal-shape patches: raw float32 counts, labels uint64 (0 = background).
+ *   reject[i] = 1 when some segment of patch i with at least min_segment_voxels voxels has a lag-`lag`
+ *   autocorrelation below min_autocorr AND a high-frequency energy fraction above max_highfreq_frac.
+ * Optional per-segment scores (NULL to skip): seg[i * max_segments + j], j < seg_count[i], in no particular order. */
+typedef struct b4d_segment_score {
+    uint64_t label;
+    int64_t voxels;
+    double autocorr;   /* 1.0 when it cannot be measured, as the reference returns */
+    double highfreq;   /* 0.0 when the segment's variance is degenerate            */
+} b4d_segment_score;
+int b4d_coherence_gate(b4d_handle *h, const float *raw, const uint64_t *labels, int64_t n, const int64_t shape[3],
+                       double min_autocorr, double max_highfreq_frac, int64_t min_segment_voxels,
+                       double smooth_sigma, int lag, uint8_t *reject, b4d_segment_score *seg,
+                       int64_t max_segments, int64_t *seg_count, int in_on_device);
+
 /* Diagnostics: the fixed-point aggregation state the LAST filter stage of the last single-volume call left
  * behind, copied to host arrays of n = D*H*W entries: numq = sum of the rounded numerator terms per voxel,
  * wmap = sum of the 20-bit group weights per block origin.  The tests compare both with the oracle mirror's,

@@ -1022,6 +1022,10 @@ int b4d_slab_stage2_q16(b4d_handle *, int64_t, int64_t, float, float, float, int
 int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *, int64_t *, int) {
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }
+int b4d_coherence_gate(b4d_handle *, const float *, const uint64_t *, int64_t, const int64_t *, double, double, int64_t,
+                       double, int, uint8_t *, b4d_segment_score *, int64_t, int64_t *, int) {
+    return fail(B4D_ERR_UNSUPPORTED, "the coherence gate is restated in oracle/np_oracle.py (NumPy / SciPy)");
+}
 int b4d_stats_from_hist(const int64_t *, double, b4d_stats *) {
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
 }

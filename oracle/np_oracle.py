@@ -90,6 +90,44 @@ def make_foreground_mask_reference(raw, k=6.0, dilate=1):
     return mask
 
 
+def coherence_scores_reference(labels, raw, smooth_sigma=1.0, lag=2):
+    """Per-segment (voxels, lag autocorrelation, high-frequency energy fraction) the way the sampler's gate
+    computes them: local_autocorr (metrics.py:96-112), highfreq_energy_fraction (:148-155) with the Gaussian
+    smooth of the whole patch (:247-248), all float64.  Returns {label: (voxels, autocorr, highfreq)}."""
+    from scipy import ndimage
+
+    labels = np.asarray(labels)
+    raw = np.asarray(raw, dtype=np.float64)
+    smooth = ndimage.gaussian_filter(raw, sigma=smooth_sigma)
+    out = {}
+    for lid in np.unique(labels[labels > 0]):
+        seg = labels == lid
+        vals = []
+        for ax in range(raw.ndim):
+            lo = [slice(None)] * raw.ndim
+            hi = [slice(None)] * raw.ndim
+            lo[ax], hi[ax] = slice(0, -lag), slice(lag, None)
+            sel = seg[tuple(lo)] & seg[tuple(hi)]
+            if sel.sum() < 2:
+                continue
+            x, y = raw[tuple(lo)][sel], raw[tuple(hi)][sel]
+            if x.std() < 1e-6 or y.std() < 1e-6:
+                continue
+            vals.append(float(np.corrcoef(x, y)[0, 1]))
+        ac = float(np.mean(vals)) if vals else 1.0
+        v = raw[seg]
+        hf = 0.0 if v.var() < 1e-12 else float((raw - smooth)[seg].var() / v.var())
+        out[int(lid)] = (int(seg.sum()), ac, hf)
+    return out
+
+
+def patch_has_incoherent_segment_reference(labels, raw, min_autocorr=0.4, max_highfreq_frac=0.35,
+                                           min_segment_voxels=50, smooth_sigma=1.0, coherence_lag=2):
+    """The gate's decision (metrics.py:241-260) from the scores above."""
+    sc = coherence_scores_reference(labels, raw, smooth_sigma, coherence_lag)
+    return any(n >= min_segment_voxels and ac < min_autocorr and hf > max_highfreq_frac for n, ac, hf in sc.values())
+
+
 def chunk_shuffle_reference(img, patch_shape=(64, 64, 64)):
     """The chunk loop of compute_cratio (utils/img_util.py:427-438) with Blosc's byte shuffle for
     2-byte items applied to each piece instead of the codec call: returns (bytes of all pieces back

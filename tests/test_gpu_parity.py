@@ -713,3 +713,28 @@ def test_bench_volume_1024_crops_equal_the_oracle(dn, oracle_lib):
         assert np.array_equal(got, m[inner]), "crop at %r: max-abs %g" % (org, np.abs(got - m[inner]).max())
     del y, vol
     torch.cuda.empty_cache()
+
+
+def test_coherence_gate_matches_the_reference(dn, b4d_mod, oracle_lib):
+    """The sampler's spatial-coherence gate on the device (b4d_coherence_gate) against outputs of the LIVE reference
+    (tests/golden/reference_coherence.npz): verdicts equal; per-segment voxel counts equal, lag autocorrelation and
+    high-frequency energy fraction within 1e-9 (float64 sums in another order); a batch equals the single calls."""
+    from test_oracle_golden import _coherence_cases
+
+    cases = list(_coherence_cases())
+    for lab, raw, kw, ids, scores, verdict in cases:
+        rej, tabs = dn.coherence_scores(lab, raw, kw["smooth_sigma"], kw["coherence_lag"], kw["min_autocorr"],
+                                        kw["max_highfreq_frac"], kw["min_segment_voxels"])
+        assert bool(rej[0]) == verdict
+        assert sorted(tabs[0]) == [int(v) for v in ids]
+        for lid, want in zip(ids, scores):
+            got = tabs[0][int(lid)]
+            assert got[0] == int(want[0])
+            assert abs(got[1] - want[1]) <= 1e-9 and abs(got[2] - want[2]) <= 1e-9, (lid, got, want)
+        assert b4d_mod.patch_has_incoherent_segment(lab, raw, **kw) == verdict
+    same = [c for c in cases if c[0].shape == (48, 48, 48) and c[2] == cases[0][2]]
+    rej = dn.patch_has_incoherent_segment(np.stack([c[0] for c in same]), np.stack([c[1] for c in same]))
+    assert rej.tolist() == [c[5] for c in same]
+    # offsets do not matter (every statistic is shift invariant): raw counts minus a pedestal give the same verdict
+    lab, raw, kw, ids, scores, verdict = cases[2]
+    assert dn.patch_has_incoherent_segment(lab, raw + np.float32(1000.25), **kw) == verdict

@@ -94,3 +94,31 @@ def test_foreground_mask_restatements_match_the_reference(oracle_lib):
 def test_truncating_variant(oracle_lib):
     x = np.array([-3.2, 0.0, 0.9, 1.5, 2.5, 65535.9], dtype=np.float32)
     assert oracle_lib.quantize_truncating(x).tolist() == [0, 0, 0, 1, 2, 65535]
+
+
+def _coherence_cases():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_coherence.npz"))
+    for i in range(int(g["n"])):
+        p = g["params%d" % i]
+        kw = dict(min_autocorr=float(p[0]), max_highfreq_frac=float(p[1]), min_segment_voxels=int(p[2]),
+                  smooth_sigma=float(p[3]), coherence_lag=int(p[4]))
+        yield g["labels%d" % i], g["raw%d" % i], kw, g["ids%d" % i], g["scores%d" % i], bool(g["verdict%d" % i])
+
+
+def test_coherence_gate_restatement_matches_the_reference(oracle_lib):
+    """np_oracle's restatement of the sampler's coherence gate against outputs of the LIVE reference
+    (tests/golden/make_golden_coherence.py: patch_has_incoherent_segment, local_autocorr,
+    highfreq_energy_fraction of metrics.py): verdicts equal, per-segment scores equal to 1e-12."""
+    n = 0
+    for lab, raw, kw, ids, scores, verdict in _coherence_cases():
+        sc = oracle_lib.coherence_scores_reference(lab, raw, kw["smooth_sigma"], kw["coherence_lag"])
+        assert sorted(sc) == [int(v) for v in ids]
+        for lid, want in zip(ids, scores):
+            got = sc[int(lid)]
+            assert got[0] == int(want[0])
+            assert abs(got[1] - want[1]) <= 1e-12 and abs(got[2] - want[2]) <= 1e-12
+        assert oracle_lib.patch_has_incoherent_segment_reference(lab, raw, **kw) == verdict
+        n += 1
+    assert n >= 8
