@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     noise_scaled_step,
     precompute_targets,
     quantize,
+    noise_model_from_psd,
     patch_has_incoherent_segment,
     denoise_quantized,
     tile_stats,
@@ -43,6 +44,7 @@ __all__ = [
     "noise_scaled_step",
     "precompute_targets",
     "quantize",
+    "noise_model_from_psd",
     "patch_has_incoherent_segment",
     "denoise_quantized",
     "tile_stats",

@@ -50,6 +50,7 @@ EXPORTS = (
     "b4d_slab_stage2_begin",
     "b4d_stats_from_hist",
     "b4d_coherence_gate",
+    "b4d_set_noise_model",
 )
 
 

@@ -13,7 +13,7 @@ What it replaces (paths under /root/reference/src/aind_exaspim_image_compression
 
 Same names, argument meaning and error behaviour as the ``bm4d`` package's entry
 point (``ValueError`` for shape/dtype, ``RuntimeError`` for CUDA,
-``NotImplementedError`` for a coloured PSD).  NumPy in -> NumPy out; torch in ->
+``NotImplementedError`` for options outside the path).  NumPy in -> NumPy out; torch in ->
 torch out on the same device.  Everything computes on the GPU through the C ABI;
 there is no CPU fallback.
 """
@@ -130,6 +130,19 @@ class Denoiser:
         _lib.check(self.lib.b4d_debug_accumulators(self._h, numq.ctypes.data_as(ctypes.c_void_p),
                                                    wmap.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n)))
         return numq, wmap
+
+    def set_noise_model(self, nu_ht=None, nu_wie=None):
+        """Coloured noise: relative coefficient variances of the two block transforms (b4d_set_noise_model,
+        see noise_model_from_psd); None, None switches back to white noise."""
+        if nu_ht is None and nu_wie is None:
+            _lib.check(self.lib.b4d_set_noise_model(self._h, None, None))
+            return
+        a = np.ascontiguousarray(nu_ht, dtype=np.float32).reshape(-1)
+        b = np.ascontiguousarray(nu_wie, dtype=np.float32).reshape(-1)
+        if a.size != 64 or b.size != 64:
+            raise ValueError("nu_ht and nu_wie must hold 64 values each")
+        _lib.check(self.lib.b4d_set_noise_model(self._h, a.ctypes.data_as(ctypes.c_void_p),
+                                                b.ctypes.data_as(ctypes.c_void_p)))
 
     def set_profile(self, profile=None, stages=2):
         """Switch algorithm constants (no-op when nothing changes)."""
@@ -679,7 +692,42 @@ def _sigma_scalar(sigma_psd):
     if np.all(s == s.reshape(-1)[0]):
         # a constant PSD of an N-voxel transform equals sigma^2 * N (white noise)
         return float(np.sqrt(s.reshape(-1)[0] / s.size))
-    raise NotImplementedError("coloured-noise PSD input is not implemented; pass a scalar sigma")
+    raise NotImplementedError("a coloured-noise PSD is accepted by bm4d() only; this entry point takes a scalar sigma")
+
+
+_HAAR4 = np.array([[0.5, 0.5, 0.5, 0.5], [0.5, 0.5, -0.5, -0.5], [np.sqrt(0.5), -np.sqrt(0.5), 0.0, 0.0],
+                   [0.0, 0.0, np.sqrt(0.5), -np.sqrt(0.5)]])
+_DCT4 = np.array([[(0.5 if k == 0 else np.sqrt(0.5)) * np.cos(np.pi * (2 * n + 1) * k / 8.0) for n in range(4)]
+                  for k in range(4)])
+
+
+def noise_model_from_psd(psd):
+    """Reduce a noise PSD to what the kernels need (include/b4d.h, b4d_set_noise_model): (sigma, nu_ht[64],
+    nu_wie[64]) — the root of the mean noise variance and, for the stage-1 (Haar = bior1.5 at length 4) and stage-2
+    (DCT-II) block transforms, the relative variance of each of the 64 coefficients of a 4^3 block of that noise.
+
+    ``psd`` is the array form of bm4d's ``sigma_psd``: E|FFT(noise)|^2 on the grid of the volume (or any grid of at
+    least 4 points per axis), unnormalised DFT, so that white noise of standard deviation s has psd == s^2 * psd.size.
+    The autocovariance r = ifftn(psd) / psd.size gives the covariance C[u, v] = r[u - v] of the 64 voxels of a
+    block; coefficient c of the orthonormal transform T has the variance (T C T^t)[c, c]."""
+    P = np.asarray(psd, dtype=np.float64)
+    if P.ndim != 3 or min(P.shape) < 4:
+        raise ValueError("a noise PSD must be a 3-D array with at least 4 points per axis")
+    if not np.all(np.isfinite(P)) or P.min() < 0 or P.max() <= 0:
+        raise ValueError("a noise PSD must be finite, non-negative and not identically zero")
+    r = np.real(np.fft.ifftn(P)) / P.size
+    idx = np.arange(4)
+    d = idx[:, None] - idx[None, :]  # u - v per axis
+    C = r[np.ix_(*[np.arange(-3, 4) % n for n in P.shape])]  # offsets -3 .. 3 per axis, as a 7^3 cube
+    cov = C[(d + 3)[:, None, None, :, None, None], (d + 3)[None, :, None, None, :, None],
+            (d + 3)[None, None, :, None, None, :]].reshape(64, 64)
+    sigma2 = float(r[0, 0, 0])
+    out = []
+    for t1 in (_HAAR4, _DCT4):
+        T = np.kron(t1, np.kron(t1, t1))  # index (z*4 + y)*4 + x on both sides
+        var = np.einsum("cu,uv,cv->c", T, cov, T)
+        out.append(np.maximum(var / sigma2, 1e-12).astype(np.float32))
+    return float(np.sqrt(sigma2)), out[0], out[1]
 
 
 def _prepare(z):
@@ -703,7 +751,8 @@ def bm4d(z, sigma_psd, profile="np", stage_arg=BM4DStages.ALL_STAGES, blockmatch
 
     z          NumPy or torch, 3-D, uint16 or float32 (other real dtypes are
                converted), any strides.
-    sigma_psd  noise standard deviation in the units of ``z`` (scalar).
+    sigma_psd  noise standard deviation in the units of ``z`` (scalar), or the noise PSD as a 3-D array
+               (E|FFT(noise)|^2, unnormalised DFT: white noise of std s is s^2 * size) for coloured noise.
     Returns a new array of the same shape: float32 (input dtype for float64).
     Unclipped — callers clip (data_handling.py:333, evaluate.py:202).
     """
@@ -717,11 +766,21 @@ def bm4d(z, sigma_psd, profile="np", stage_arg=BM4DStages.ALL_STAGES, blockmatch
         raise NotImplementedError("passing a basic estimate as stage_arg is not implemented")
     if np.ndim(z) != 3 if not _is_torch(z) else z.ndim != 3:
         raise ValueError("bm4d expects a 3-D array, got %d-D" % (z.ndim if _is_torch(z) else np.ndim(z)))
-    sigma = _sigma_scalar(sigma_psd)
     h = get_denoiser(device)
     h.set_profile(profile, stages)
     zz, cast = _prepare(z)
-    out = h.denoise(zz, sigma)
+    s = np.asarray(sigma_psd, dtype=np.float64)
+    if s.ndim == 3 and s.size > 1 and not np.all(s == s.reshape(-1)[0]):
+        # coloured noise: per-coefficient variances of both block transforms (a constant PSD is white noise and
+        # takes the scalar path, bit for bit)
+        sigma, nu_ht, nu_wie = noise_model_from_psd(s)
+        h.set_noise_model(nu_ht, nu_wie)
+        try:
+            out = h.denoise(zz, sigma)
+        finally:
+            h.set_noise_model(None, None)
+    else:
+        out = h.denoise(zz, _sigma_scalar(sigma_psd))
     return out.astype(cast) if cast is not None else out
 
 

@@ -80,6 +80,9 @@ struct b4d_handle {
     long long pipeline_min_voxels = 1ll << 26;  // host transfers are pipelined from this volume size up
     HostMover mover;  // pageable host arrays <-> device (pinned ring + copy threads)
     // state between b4d_slab_stage1_u16 and b4d_slab_stage2
+    // coloured noise (b4d_set_noise_model): relative coefficient variances of both transforms, or white
+    bool psd = false;
+    float nu_ht[64], nu_wie[64];
     bool slab_open = false;
     // two-call slab form: what b4d_slab_stage2_begin already launched (planes [pre_o0, pre_o1) of the matching image,
     // cell planes [pre_cz0, pre_cz1), tile layers [pre_tz0, pre_tz1) classified and matched)
@@ -167,9 +170,25 @@ double bessel_i0(double x) {
     }
     return s;
 }
-B4dTables make_tables(const b4d_profile &p, float sigma) {
+B4dTables make_tables(const b4d_profile &p, float sigma, const float *nu_ht = nullptr, const float *nu_wie = nullptr) {
     B4dTables t;
     std::memset(&t, 0, sizeof(t));
+    // coloured-noise tables (white: nu = 1): identical code in oracle/b4d_oracle.cpp make_tables
+    for (int c = 0; c < 64; ++c) {
+        t.nu_ht[c] = nu_ht ? nu_ht[c] : 1.0f;
+        t.nu_wie[c] = nu_wie ? nu_wie[c] : 1.0f;
+        {
+            volatile float s2f = sigma * sigma;       // float32 product, as sigma2 below
+            volatile float s2c = s2f * t.nu_wie[c];   // nu = 1 reproduces the white path bit for bit
+            t.s2c[c] = s2c;
+        }
+        const int n = ((c & 3) >= 2) + (((c >> 2) & 3) >= 2) + ((c >> 4) >= 2);
+        for (int l = 0; l < 6; ++l) {
+            const int m = 6 - n + l;
+            const double sc = std::ldexp(1.0, m / 2) * ((m & 1) ? M_SQRT2 : 1.0);
+            t.thc[c * 6 + l] = (float)((double)p.lambda_ht * (double)sigma * sc * std::sqrt((double)t.nu_ht[c]));
+        }
+    }
     float kf[4];
     for (int n = 0; n < 4; ++n) {
         double w = 1.0;
@@ -389,7 +408,9 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     // profile.deterministic is kept in the ABI and is always honoured.
     B4D_TRY(h->numq.ensure((size_t)TV * sizeof(long long)));
     B4D_TRY(h->gmap.ensure((size_t)TV * sizeof(uint32_t)));
-    const B4dTables tab = make_tables(p, sigma);
+    const B4dTables tab = make_tables(p, sigma, h->psd ? h->nu_ht : nullptr, h->psd ? h->nu_wie : nullptr);
+    if (h->psd && (p.search_ht > 11 || p.search_wie > 11))
+        return fail(B4D_ERR_UNSUPPORTED, "a coloured-noise model needs search windows of at most 11");
     b4d_upload_tables(tab, s);
     if (phase < 2) CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
 
@@ -474,6 +495,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     fp.K = p.k_ht;
     fp.Ns = p.search_ht;
     fp.nseg = 1;
+    fp.psd = h->psd ? 1 : 0;
     fp.qscale = mm.scale;  // data * scale spans at most the 16-bit matching range: terms stay below 2^39
     fp.numq = h->numq.as<long long>();
     fp.gmap = h->gmap.as<uint32_t>();
@@ -505,6 +527,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
         fp.widx = mp.widx;
         fp.cnt = mp.cnt;
         fp.nseg = 1;
+        fp.psd = h->psd ? 1 : 0;
         fp.qscale = mm.scale;
         fp.numq = h->numq.as<long long>();
         fp.gmap = h->gmap.as<uint32_t>();
@@ -1677,6 +1700,22 @@ void *b4d_stream(b4d_handle *h) { return h ? (void *)h->stream : nullptr; }
 int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]) {
     if (!h || !out) return fail(B4D_ERR_INVALID, "NULL argument");
     for (int i = 0; i < 4; ++i) out[i] = h->match_stats[i];
+    return 0;
+}
+
+int b4d_set_noise_model(b4d_handle *h, const float *nu_ht, const float *nu_wie) {
+    if (!h) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!nu_ht && !nu_wie) {
+        h->psd = false;
+        return 0;
+    }
+    if (!nu_ht || !nu_wie) return fail(B4D_ERR_INVALID, "both tables or none");
+    for (int c = 0; c < 64; ++c)
+        if (!(nu_ht[c] > 0.0f) || !(nu_wie[c] > 0.0f) || !std::isfinite(nu_ht[c]) || !std::isfinite(nu_wie[c]))
+            return fail(B4D_ERR_INVALID, "relative variances must be positive and finite");
+    std::memcpy(h->nu_ht, nu_ht, sizeof(h->nu_ht));
+    std::memcpy(h->nu_wie, nu_wie, sizeof(h->nu_wie));
+    h->psd = true;
     return 0;
 }
 

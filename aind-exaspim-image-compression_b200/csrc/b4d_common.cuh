@@ -34,6 +34,12 @@ struct B4dTables {
     float wb[24];        // [n][l] = S_n^2 2^(-l): raw * W -> input of the unnormalised inverse butterflies
     float tq;            // 1 + sqrt 2 = c1 / c3
     float sigma2;
+    // coloured noise (b4d_set_noise_model): relative variance nu_c = var_c / sigma^2 of every coefficient of the 3-D
+    // transform of a 4^3 block of noise, in the kernels' coefficient order (z*4 + y)*4 + x-position
+    float nu_ht[B4D_LV];   // Haar domain (stage 1)
+    float nu_wie[B4D_LV];  // DCT domain (stage 2)
+    float s2c[B4D_LV];     // sigma^2 nu_wie[c]
+    float thc[B4D_LV * 6]; // [c][l] = lambda sigma sqrt(nu_ht[c]) 2^(m/2), m = 6 - n(c) + l
 };
 
 struct MatchParams {
@@ -66,6 +72,7 @@ struct FilterParams {
     float qscale;                // power of two: numerator terms are rint(wq * qscale * x), |.| < 2^39
     long long *numq;             // fixed-point numerator (order independent): sum of rint(wq * qscale * x)
     uint32_t *gmap;              // weight map: per block origin, the sum of the 20-bit group weights qg
+    int psd;                     // coloured-noise tables are in effect (per-coefficient thresholds / attenuation)
 #ifdef B4D_DEBUG_DUMP
     long long dbg_ref;           // developer builds: the Wiener-stage reference whose intermediates are printed
 #endif

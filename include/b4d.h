@@ -268,6 +268,16 @@ int b4d_last_match_stats(b4d_handle *h, uint64_t out[4]);
  *   out[3] = FFMA lane-ops/s.                                                */
 int b4d_measure_pipe_peaks(b4d_handle *h, double out[4]);
 
+/* Coloured (spatially correlated) noise — the array form of bm4d's `sigma_psd` argument.  The caller reduces the
+ * noise PSD to the relative variance nu_c = var_c / sigma^2 of each of the 64 coefficients of the 3-D block
+ * transform of pure noise, for the stage-1 transform (Haar = bior1.5 at length 4) and the stage-2 transform
+ * (DCT-II), coefficient order (z*4 + y)*4 + x with the positions of oracle/b4d_oracle.cpp; `sigma` of the following
+ * denoise calls is the root of the mean noise variance.  Then: hard threshold lambda sigma sqrt(nu_c), weight
+ * 1 / sum of nu_c over the retained coefficients; Wiener W = y^2 / (y^2 + sigma^2 nu_c), weight 1 / sum W^2 nu_c;
+ * matching threshold tau sigma^2 64.  nu = 1 everywhere is the white model (bit-identical to NULL, NULL, which
+ * switches the model off).  Search windows above 11 are not supported with a coloured model. */
+int b4d_set_noise_model(b4d_handle *h, const float nu_ht[64], const float nu_wie[64]);
+
 /* The spatial-coherence gate that precedes BM4D in the sampler (machine_learning/metrics.py:189-260
  * patch_has_incoherent_segment, with local_autocorr :64-112 and highfreq_energy_fraction :115-155; call site
  * data_handling.py:398-407), for `n` equal-shape patches: raw float32 counts, labels uint64 (0 = background).

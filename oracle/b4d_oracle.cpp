@@ -56,6 +56,8 @@ struct b4d_handle_impl {
     b4d_profile prof;
     int arith;  // 0 = mirror (float32, CUDA op order), 1 = f64 plain restatement
     int threads;
+    bool psd = false;  // coloured-noise model (b4d_set_noise_model)
+    float nu_ht[64], nu_wie[64];
     mutable std::vector<int64_t> last_numq, last_wmap;  // mirror: accumulators of the last filter stage
     mutable std::vector<uint16_t> last_widx2;           // stage-2 match lists of the last two-stage call
     mutable std::vector<uint8_t> last_cnt2;
@@ -303,7 +305,7 @@ void group_xf(const std::vector<double> &G, int K, bool transpose, std::vector<d
 template <bool WIENER>
 void filter_f64(const float *zf, const double *basic, const Geom &g, const Matches &m, int Ns,
                 double sigma, const b4d_profile &p, std::vector<double> &num,
-                std::vector<double> &den) {
+                std::vector<double> &den, const float *nu = nullptr) {
     const Mats mats = make_mats();
     const int r = Ns / 2;
     double kw[4], win[LV];
@@ -347,23 +349,26 @@ void filter_f64(const float *zf, const double *basic, const Geom &g, const Match
         }
         group_xf(hm[lg], kp, false, noisy);
         double weight;
+        // coloured noise: coefficient v of every block has the variance sigma^2 nu[v] (nu = 1: white)
         if (!WIENER) {
-            int64_t kept = 0;
-            for (auto &c : noisy) {
-                if (std::fabs(c) < thr)
-                    c = 0.0;
+            double kept = 0;
+            for (size_t i = 0; i < noisy.size(); ++i) {
+                const double nv = nu ? (double)nu[i % LV] : 1.0;
+                if (std::fabs(noisy[i]) < thr * std::sqrt(nv))
+                    noisy[i] = 0.0;
                 else
-                    ++kept;
+                    kept += nv;
             }
-            weight = 1.0 / (double)std::max<int64_t>(kept, 1);  // sigma^-2 cancels in num/den
+            weight = 1.0 / std::max(kept, 1.0);  // sigma^-2 cancels in num/den
         } else {
             group_xf(hm[lg], kp, false, est);
             double sw2 = 0;
             for (size_t i = 0; i < noisy.size(); ++i) {
+                const double nv = nu ? (double)nu[i % LV] : 1.0;
                 double y2 = est[i] * est[i];
-                double w = y2 / (y2 + sigma * sigma);
+                double w = y2 / (y2 + sigma * sigma * nv);
                 noisy[i] *= w;
-                sw2 += w * w;
+                sw2 += w * w * nv;
             }
             weight = 1.0 / std::max(sw2, 1.0);
         }
@@ -398,9 +403,28 @@ struct MirrorTables {
     float wb[24];        // [n][l] = float(S_n^2 2^(-l))
     float tq;            // float(1 + sqrt 2) = c1 / c3
     float sigma2;        // float(sigma)*float(sigma)
+    // coloured noise: relative coefficient variances and the tables derived from them (csrc/b4d_api.cu make_tables)
+    bool psd;
+    float nu_ht[LV], nu_wie[LV], s2c[LV], thc[LV * 6];
 };
-MirrorTables make_tables(const b4d_profile &p, float sigma) {
+MirrorTables make_tables(const b4d_profile &p, float sigma, const float *nu_ht = nullptr, const float *nu_wie = nullptr) {
     MirrorTables t{};
+    t.psd = nu_ht != nullptr;
+    for (int c = 0; c < 64; ++c) {
+        t.nu_ht[c] = nu_ht ? nu_ht[c] : 1.0f;
+        t.nu_wie[c] = nu_wie ? nu_wie[c] : 1.0f;
+        {
+            volatile float s2f = sigma * sigma;       // float32 product, as sigma2 below
+            volatile float s2c = s2f * t.nu_wie[c];   // nu = 1 reproduces the white path bit for bit
+            t.s2c[c] = s2c;
+        }
+        const int n = ((c & 3) >= 2) + (((c >> 2) & 3) >= 2) + ((c >> 4) >= 2);
+        for (int l = 0; l < 6; ++l) {
+            const int m = 6 - n + l;
+            const double sc = std::ldexp(1.0, m / 2) * ((m & 1) ? M_SQRT2 : 1.0);
+            t.thc[c * 6 + l] = (float)((double)p.lambda_ht * (double)sigma * sc * std::sqrt((double)t.nu_ht[c]));
+        }
+    }
     double kw[4];
     kaiser4(p.kaiser_beta, kw);
     float kf[4];
@@ -539,21 +563,41 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
             ghaar_fwd(noisy, kp);
             for (int k = 0; k < kp; ++k) xf3_fwd<false>(noisy + k * LV, t);
             int kept = 0;
+            float part[32];
+            for (int k = 0; k < 32; ++k) part[k] = 0.0f;
             for (int k = 0; k < kp; ++k) {
                 const int l = group_level(k, lg);
-                for (int v = 0; v < LV; ++v) {
-                    const int n = spatial_class(v);
-                    float c = noisy[k * LV + v];
-                    if (fabsf(c) < t.tht[6 - n + l]) {
-                        c = 0.0f;
-                    } else {
-                        ++kept;
-                        c = ldexpf(c, -(6 - n + l));  // exact: squared normalisation 2^(-6+n-l)
-                    }
-                    noisy[k * LV + v] = c;
-                }
+                // coloured noise: the weight sums nu_c of the retained coefficients in the kernel's order — lane k
+                // chains (z, y, x pair (0|1) then (2|3)), low halves (x 0, 2) and high halves (x 1, 3) apart
+                float kf_lo = 0.0f, kf_hi = 0.0f;
+                for (int zy = 0; zy < 16; ++zy)
+                    for (int o = 0; o < 2; ++o)
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int v = zy * 4 + 2 * o + hf;
+                            const int n = spatial_class(v);
+                            float c = noisy[k * LV + v];
+                            const float th = t.psd ? t.thc[v * 6 + l] : t.tht[6 - n + l];
+                            if (fabsf(c) < th) {
+                                c = 0.0f;
+                            } else {
+                                ++kept;
+                                (hf ? kf_hi : kf_lo) += t.nu_ht[v];
+                                c = ldexpf(c, -(6 - n + l));  // exact: squared normalisation 2^(-6+n-l)
+                            }
+                            noisy[k * LV + v] = c;
+                        }
+                part[k] = kf_lo + kf_hi;
             }
-            weight = 1.0f / (float)std::max(kept, 1);
+            if (t.psd) {
+                for (int mm = 16; mm >= 1; mm >>= 1) {
+                    float nx[32];
+                    for (int k = 0; k < 32; ++k) nx[k] = part[k] + part[k ^ mm];
+                    std::memcpy(part, nx, sizeof(nx));
+                }
+                weight = 1.0f / fmaxf(part[0], 1.0f);
+            } else {
+                weight = 1.0f / (float)std::max(kept, 1);
+            }
             for (int k = 0; k < kp; ++k) xf3_inv<false>(noisy + k * LV, t);
             ghaar_inv(noisy, kp);
         } else {
@@ -590,10 +634,17 @@ void filter_mirror(const float *zf, const float *basic, const Geom &g, const Mat
                             const int n = dct_class(v);
                             const float yn = est[k * LV + v] * t.wa[n * 6 + l];
                             const float y2 = yn * yn;
-                            const float nd = (-t.sigma2) - y2;
+                            const float nd = (t.psd ? -t.s2c[v] : -t.sigma2) - y2;
                             const float w = y2 / (-nd);
-                            if (h == 0) acc_lo = fmaf(w, w, acc_lo);
-                            else acc_hi = fmaf(w, w, acc_hi);
+                            if (t.psd) {  // sum of W^2 nu_c as fma(W nu_c, W, acc): nu = 1 is the white chain
+                                const float wn = w * t.nu_wie[v];
+                                if (h == 0) acc_lo = fmaf(wn, w, acc_lo);
+                                else acc_hi = fmaf(wn, w, acc_hi);
+                            } else if (h == 0) {
+                                acc_lo = fmaf(w, w, acc_lo);
+                            } else {
+                                acc_hi = fmaf(w, w, acc_hi);
+                            }
                             noisy[k * LV + v] = (noisy[k * LV + v] * w) * t.wb[n * 6 + l];
                         }
                 part[k] = acc_lo + acc_hi;
@@ -778,7 +829,7 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
     match_all(u.data(), g1, p.search_ht, p.k_ht, tau_int(p.tau_ht, sigma, mm.scale), m);
     if (h->arith == 1) {
         std::vector<double> num(V, 0.0), den(V, 0.0), basic(V);
-        filter_f64<false>(zf.data(), nullptr, g1, m, p.search_ht, (double)sigma, p, num, den);
+        filter_f64<false>(zf.data(), nullptr, g1, m, p.search_ht, (double)sigma, p, num, den, h->psd ? h->nu_ht : nullptr);
         for (int64_t i = 0; i < V; ++i) basic[i] = den[i] > 0 ? num[i] / den[i] : (double)zf[i];
         if (p.stages == 1) {
             for (int64_t i = 0; i < V; ++i) out[i] = (float)basic[i];
@@ -790,11 +841,12 @@ int denoise_one(const b4d_handle_impl *h, const uint16_t *in_u16, const float *i
         h->last_cnt2 = m.cnt;
         std::fill(num.begin(), num.end(), 0.0);
         std::fill(den.begin(), den.end(), 0.0);
-        filter_f64<true>(zf.data(), basic.data(), g2, m, p.search_wie, (double)sigma, p, num, den);
+        filter_f64<true>(zf.data(), basic.data(), g2, m, p.search_wie, (double)sigma, p, num, den,
+                         h->psd ? h->nu_wie : nullptr);
         for (int64_t i = 0; i < V; ++i) out[i] = (float)(den[i] > 0 ? num[i] / den[i] : basic[i]);
         return 0;
     }
-    const MirrorTables t = make_tables(p, sigma);
+    const MirrorTables t = make_tables(p, sigma, h->psd ? h->nu_ht : nullptr, h->psd ? h->nu_wie : nullptr);
     std::vector<int64_t> numq(V, 0), denq(V, 0);
     std::vector<float> basic(V);
     const double inv_q = 1.0 / (double)mm.scale;
@@ -1021,6 +1073,19 @@ int b4d_slab_stage2_q16(b4d_handle *, int64_t, int64_t, float, float, float, int
 }
 int b4d_tile_stats(b4d_handle *, const uint16_t *, int64_t, double, b4d_stats *, int64_t *, int) {
     return fail(B4D_ERR_UNSUPPORTED, "tile statistics are restated in oracle/np_oracle.py (NumPy)");
+}
+int b4d_set_noise_model(b4d_handle *hh, const float *nu_ht, const float *nu_wie) {
+    auto *h = reinterpret_cast<b4d_handle_impl *>(hh);
+    if (!h) return fail(B4D_ERR_INVALID, "NULL argument");
+    if (!nu_ht && !nu_wie) {
+        h->psd = false;
+        return 0;
+    }
+    if (!nu_ht || !nu_wie) return fail(B4D_ERR_INVALID, "both tables or none");
+    std::memcpy(h->nu_ht, nu_ht, sizeof(h->nu_ht));
+    std::memcpy(h->nu_wie, nu_wie, sizeof(h->nu_wie));
+    h->psd = true;
+    return 0;
 }
 int b4d_coherence_gate(b4d_handle *, const float *, const uint64_t *, int64_t, const int64_t *, double, double, int64_t,
                        double, int, uint8_t *, b4d_segment_score *, int64_t, int64_t *, int) {

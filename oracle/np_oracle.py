@@ -279,6 +279,15 @@ class Oracle:
         )
         return out
 
+    def set_noise_model(self, nu_ht=None, nu_wie=None):
+        """Coloured noise: relative coefficient variances (include/b4d.h b4d_set_noise_model); None: white."""
+        if nu_ht is None:
+            _check(load().b4d_set_noise_model(self._h, None, None))
+            return
+        a = np.ascontiguousarray(nu_ht, dtype=np.float32)
+        b = np.ascontiguousarray(nu_wie, dtype=np.float32)
+        _check(load().b4d_set_noise_model(self._h, a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p)))
+
     def stage2_matches(self, shape):
         """(widx[R, K], cnt[R]) of the last two-stage call on one volume of `shape`: window index
         (dz*Ns + dy)*Ns + dx of every match, group size per reference block."""

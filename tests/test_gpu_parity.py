@@ -738,3 +738,44 @@ def test_coherence_gate_matches_the_reference(dn, b4d_mod, oracle_lib):
     # offsets do not matter (every statistic is shift invariant): raw counts minus a pedestal give the same verdict
     lab, raw, kw, ids, scores, verdict = cases[2]
     assert dn.patch_has_incoherent_segment(lab, raw + np.float32(1000.25), **kw) == verdict
+
+
+def test_coloured_noise_psd_input(dn, b4d_mod, oracle_lib):
+    """bm4d(z, sigma_psd) with an array PSD (the other half of the call surface): bit-exact against the mirror with
+    the same per-coefficient variance tables, close to the float64 path, better than the white model on correlated
+    noise; nu = 1 tables and a constant PSD reproduce the scalar path bit for bit; uint16 and float32 inputs, both
+    group-size instantiations."""
+    from test_oracle_bm4d import _coloured_case
+
+    shape = (24, 28, 32)
+    psd, clean, z = _coloured_case(shape)
+    s, a, b = b4d_mod.noise_model_from_psd(psd)
+    y = b4d_mod.bm4d(z, psd)
+    om, of = oracle_lib.Oracle("mirror"), oracle_lib.Oracle("f64")
+    om.set_noise_model(a, b)
+    of.set_noise_model(a, b)
+    assert np.array_equal(y, om.denoise(z, s))
+    f = of.denoise(z, s)
+    assert rel_l2(y, f) <= REL_L2 and np.abs(y - f).max() <= MAX_ABS
+    white = b4d_mod.bm4d(z, s)
+    rmse = lambda v: float(np.sqrt(np.mean((v - clean) ** 2)))  # noqa: E731
+    assert rmse(y) < 0.85 * rmse(white)
+    # the model is switched off again after the call; a constant PSD is the scalar path
+    assert np.array_equal(b4d_mod.bm4d(z, s), white)
+    assert np.array_equal(b4d_mod.bm4d(z, np.full(shape, s * s * np.prod(shape))), white)
+    # nu = 1 tables == white, bit for bit; uint16 input; 16-block Wiener groups
+    zu = np.clip(np.rint(z + 200.0), 0, 65535).astype(np.uint16)
+    for kw, okw in (({}, {}), ({"max_stack_size_wiener": 16, "max_stack_size_ht": 8}, {"k_wie": 16, "k_ht": 8})):
+        d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(**kw))
+        w0 = d.denoise(zu, s)
+        d.set_noise_model(np.ones(64, np.float32), np.ones(64, np.float32))
+        assert np.array_equal(d.denoise(zu, s), w0)
+        d.set_noise_model(a, b)
+        o = oracle_lib.Oracle("mirror", **okw)
+        o.set_noise_model(a, b)
+        assert np.array_equal(d.denoise(zu, s), o.denoise(zu, s))
+        d.close()
+    with pytest.raises(NotImplementedError):
+        d = b4d_mod.Denoiser(0, b4d_mod.BM4DProfile(search_window_ht=(7, 7, 7)))
+        d.set_noise_model(a, b)
+        d.denoise(zu, s)

@@ -140,3 +140,43 @@ def test_argument_errors(oracle_lib):
         o.denoise(np.zeros((8, 8, 8), np.uint16), 0.0)
     with pytest.raises(RuntimeError):
         oracle_lib.Oracle("f64", search_ht=4)
+
+
+def _coloured_case(shape=(24, 28, 32), seed=1):
+    """Noise = white noise convolved with a small kernel; its PSD in bm4d's convention; a clean phantom."""
+    rng = np.random.default_rng(seed)
+    k = np.zeros(shape)
+    k[0, 0, 0], k[0, 0, 1], k[0, 1, 0], k[1, 0, 0] = 1.0, 0.6, 0.3, 0.2
+    K = np.fft.fftn(k)
+    psd = np.abs(K) ** 2 * np.prod(shape) * 20.0 ** 2
+    noise = np.real(np.fft.ifftn(np.fft.fftn(rng.normal(0.0, 20.0, shape)) * K))
+    clean = synth.clean_vol(*shape, 3).astype(np.float64)
+    return psd, clean, (clean + noise).astype(np.float32)
+
+
+def test_coloured_noise_model(oracle_lib):
+    """The array form of sigma_psd: the PSD is reduced to per-coefficient relative variances of
+    both block transforms (b4d.noise_model_from_psd); nu = 1 reproduces the white path bit for bit, a white PSD gives
+    nu = 1, the float32 mirror follows the float64 path, and on correlated noise the coloured model beats the
+    white model of the same total variance."""
+    import b4d
+
+    shape = (24, 28, 32)
+    s, a, b = b4d.noise_model_from_psd(np.full(shape, 24.0 ** 2 * np.prod(shape)))
+    assert abs(s - 24.0) < 1e-9 and np.all(a == 1.0) and np.all(b == 1.0)
+    psd, clean, z = _coloured_case(shape)
+    s, a, b = b4d.noise_model_from_psd(psd)
+    assert abs(a.mean() - 1.0) < 1e-5 and abs(b.mean() - 1.0) < 1e-5 and a.min() > 0 and a.max() > 2.0
+    om, of, ow = oracle_lib.Oracle("mirror"), oracle_lib.Oracle("f64"), oracle_lib.Oracle("f64")
+    om.set_noise_model(a, b)
+    of.set_noise_model(a, b)
+    m, f, fw = om.denoise(z, s), of.denoise(z, s), ow.denoise(z, s)
+    assert rel_l2(m, f) < 1e-5 and np.abs(m - f).max() < 0.5
+    rmse = lambda y: float(np.sqrt(np.mean((y - clean) ** 2)))  # noqa: E731
+    assert rmse(f) < 0.85 * rmse(fw) < rmse(z)
+    o1 = oracle_lib.Oracle("mirror")
+    o1.set_noise_model(np.ones(64, np.float32), np.ones(64, np.float32))
+    u = synth.vol(*shape, seed=3)
+    assert np.array_equal(o1.denoise(u, 24.41311), oracle_lib.Oracle("mirror").denoise(u, 24.41311))
+    o1.set_noise_model(None, None)
+    assert np.array_equal(o1.denoise(u, 24.0), oracle_lib.Oracle("mirror").denoise(u, 24.0))
