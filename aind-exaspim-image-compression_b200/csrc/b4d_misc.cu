@@ -159,14 +159,12 @@ __global__ void __launch_bounds__(256) k_clip(float *__restrict__ x, long long n
 // oracle den_from_weight_map, so the result is identical bit for bit.  Origins outside the volume hold 0, and
 // fma(k, 0, acc) == acc, so the tile halo needs no special cases.  out = num / den / qscale, else the fallback.
 //
-// One CTA owns an 8 x 32 (y, x) tile and marches along z over NZ planes: per plane the uint32 map tile (+3 halo in
-// y and x) goes through shared memory for the x and y passes, the z pass runs on a rolling window of four
-// xy-convolved values in registers.  Algorithmic traffic: int64 numerator 8 B + map 4 B + result 4 B per voxel (the
+// Algorithmic traffic: int64 numerator 8 B + map 4 B + result 4 B per voxel (the
 // fallback is read only where the denominator is zero, which a complete block grid never produces).
 // Optional fused outputs: the uint16 matching image of the next stage (K3: saves the separate conversion pass) and
 // the quantized uint16 volume (K6 + K7 fused: float32 result never written).
-constexpr int WM_TY = 8, WM_TX = 32, WM_NZ = 32;
-constexpr int WM_EY = WM_TY + 3, WM_EX = WM_TX + 3;
+constexpr int WM_TY = 8, WM_TX = 29, WM_NZ = 32, WM_WARPS = 8;
+constexpr int WM_EY = WM_TY + 3;
 struct NormOut {
     float *out;          // float32 result (may be null when q16 is set)
     uint16_t *match;     // optional: clamp(rint(y * mscale) + ishift, 0, 65535)
@@ -178,17 +176,21 @@ struct NormOut {
 };
 __device__ __forceinline__ uint32_t quant1(float x, float osub, float oadd, float step, float hi, bool unit);
 __device__ __forceinline__ uint32_t quant1_trunc(float x, float osub, float oadd, float step, float hi, bool unit);
-__global__ void __launch_bounds__(256) k_normalise_wm(const long long *__restrict__ numq,
-                                                      const uint32_t *__restrict__ gmap,
-                                                      const float *__restrict__ fb, NormOut o, int D, int H, int W,
-                                                      int nvol, int z0, int z1, float inv_qscale, float kf0, float kf1,
-                                                      float kf2, float kf3) {
-    __shared__ double sa[2][WM_EY][WM_EX + 1];
-    __shared__ double sb[2][WM_EY][WM_TX];
+// One WARP owns an 8 x 29 (y, x) tile and marches along z over WM_NZ planes (+3 planes of run-in); no shared memory,
+// no barrier.  Lane i holds column X0 - 3 + i of the uint32 map for the 11 rows Y0 - 3 .. Y0 + 7 (lanes 0-2 are the
+// x halo); the x pass takes the three left neighbours by warp shuffles of the uint32 values, the y pass runs on the
+// 11 x-convolved rows in registers, the z pass on a rolling window of three earlier xy-convolved values per row.
+__global__ void __launch_bounds__(WM_WARPS * 32) k_normalise_wm(const long long *__restrict__ numq,
+                                                                const uint32_t *__restrict__ gmap,
+                                                                const float *__restrict__ fb, NormOut o, int D, int H,
+                                                                int W, int nvol, int z0, int z1, float inv_qscale,
+                                                                float kf0, float kf1, float kf2, float kf3) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double k[4] = {(double)kf0, (double)kf1, (double)kf2, (double)kf3};
     const double inv = (double)inv_qscale;
     const int ntx = (W + WM_TX - 1) / WM_TX, nty = (H + WM_TY - 1) / WM_TY, ntz = (z1 - z0 + WM_NZ - 1) / WM_NZ;
-    long long t = blockIdx.x;
+    long long t = (long long)blockIdx.x * WM_WARPS + warp;
+    if (t >= (long long)nvol * ntz * nty * ntx) return;
     const int ix = (int)(t % ntx);
     t /= ntx;
     const int iy = (int)(t % nty);
@@ -198,47 +200,50 @@ __global__ void __launch_bounds__(256) k_normalise_wm(const long long *__restric
     const long long P = (long long)H * W, V = P * D;
     const int X0 = ix * WM_TX, Y0 = iy * WM_TY, Za = z0 + iz * WM_NZ, Zb = min(Za + WM_NZ, z1);
     const uint32_t *g = gmap + vol * V;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int gy = Y0 + ty, gx = X0 + tx;
-    const bool mine = gy < H && gx < W;
-    double w1 = 0.0, w2 = 0.0, w3 = 0.0;  // xy-convolved map of the three previous planes
+    const int gx = X0 - 3 + lane;  // this lane's column
+    const bool col_in = (unsigned)gx < (unsigned)W;
+    const bool out_lane = lane >= 3 && col_in;
+    double h1[WM_TY], h2[WM_TY], h3[WM_TY];  // xy-convolved map of the three previous planes
+#pragma unroll
+    for (int r = 0; r < WM_TY; ++r) h1[r] = h2[r] = h3[r] = 0.0;
     for (int z = Za - 3; z < Zb; ++z) {
-        const int buf = z & 1;
-        // map tile of plane z (zeros outside the volume)
-        for (int i = threadIdx.x; i < WM_EY * WM_EX; i += 256) {
-            const int lx = i % WM_EX, ly = i / WM_EX;
-            const int yy = Y0 - 3 + ly, xx = X0 - 3 + lx;
-            const bool in = z >= 0 && (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W;
-            sa[buf][ly][lx] = in ? (double)__ldg(g + (long long)z * P + (long long)yy * W + xx) : 0.0;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < WM_EY * WM_TX; i += 256) {  // x pass
-            const int lx = i % WM_TX, ly = i / WM_TX;
-            double acc = 0.0;
+        uint32_t gv[WM_EY];
 #pragma unroll
-            for (int d = 0; d < 4; ++d) acc = fma(k[d], sa[buf][ly][lx + 3 - d], acc);
-            sb[buf][ly][lx] = acc;
+        for (int r = 0; r < WM_EY; ++r) {
+            const int yy = Y0 - 3 + r;
+            gv[r] = (z >= 0 && col_in && (unsigned)yy < (unsigned)H) ? __ldg(g + (long long)z * P + (long long)yy * W + gx) : 0u;
         }
-        __syncthreads();
-        double w0 = 0.0;  // y pass
+        double xr[WM_EY];  // x pass: sum over d of k[d] G[x - d]
 #pragma unroll
-        for (int d = 0; d < 4; ++d) w0 = fma(k[d], sb[buf][ty + 3 - d][tx], w0);
-        if (z >= Za && mine) {
-            double den = fma(k[0], w0, 0.0);
-            den = fma(k[1], w1, den);
-            den = fma(k[2], w2, den);
-            den = fma(k[3], w3, den);
-            const long long a = vol * V + (long long)z * P + (long long)gy * W + gx;
-            const float y = den > 0.0 ? (float)(((double)__ldcs(numq + a) / den) * inv) : fb[a];
-            if (o.out) o.out[a] = y;
-            if (o.match) o.match[a] = (uint16_t)to_match(y, 0.0f, o.mscale, o.ishift);
-            if (o.q16)
-                o.q16[a] = (uint16_t)(o.q_trunc ? quant1_trunc(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0)
-                                                : quant1(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0));
+        for (int r = 0; r < WM_EY; ++r) {
+            double acc = fma(k[0], (double)gv[r], 0.0);
+#pragma unroll
+            for (int d = 1; d < 4; ++d) acc = fma(k[d], (double)__shfl_up_sync(B4D_FULL, gv[r], d), acc);
+            xr[r] = acc;
         }
-        w3 = w2;
-        w2 = w1;
-        w1 = w0;
+#pragma unroll
+        for (int r = 0; r < WM_TY; ++r) {
+            double w0 = 0.0;  // y pass
+#pragma unroll
+            for (int d = 0; d < 4; ++d) w0 = fma(k[d], xr[r + 3 - d], w0);
+            const int gy = Y0 + r;
+            if (z >= Za && out_lane && gy < H) {
+                double den = fma(k[0], w0, 0.0);
+                den = fma(k[1], h1[r], den);
+                den = fma(k[2], h2[r], den);
+                den = fma(k[3], h3[r], den);
+                const long long a = vol * V + (long long)z * P + (long long)gy * W + gx;
+                const float y = den > 0.0 ? (float)(((double)__ldcs(numq + a) / den) * inv) : fb[a];
+                if (o.out) o.out[a] = y;
+                if (o.match) o.match[a] = (uint16_t)to_match(y, 0.0f, o.mscale, o.ishift);
+                if (o.q16)
+                    o.q16[a] = (uint16_t)(o.q_trunc ? quant1_trunc(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0)
+                                                    : quant1(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0));
+            }
+            h3[r] = h2[r];
+            h2[r] = h1[r];
+            h1[r] = w0;
+        }
     }
 }
 
@@ -636,8 +641,8 @@ static void launch_norm(const long long *numq, const uint32_t *gmap, const float
     if (z1 <= z0) return;
     const long long tiles = (long long)nvol * ((z1 - z0 + WM_NZ - 1) / WM_NZ) * ((H + WM_TY - 1) / WM_TY) *
                             ((W + WM_TX - 1) / WM_TX);
-    k_normalise_wm<<<(unsigned)tiles, 256, 0, s>>>(numq, gmap, fallback, o, D, H, W, nvol, z0, z1, inv_qscale, kf[0],
-                                                  kf[1], kf[2], kf[3]);
+    k_normalise_wm<<<(unsigned)((tiles + WM_WARPS - 1) / WM_WARPS), WM_WARPS * 32, 0, s>>>(
+        numq, gmap, fallback, o, D, H, W, nvol, z0, z1, inv_qscale, kf[0], kf[1], kf[2], kf[3]);
 }
 void b4d_launch_normalise_wm(const long long *numq, const uint32_t *gmap, const float *fallback, float *out, int D,
                              int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4],
