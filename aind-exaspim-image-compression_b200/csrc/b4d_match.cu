@@ -129,18 +129,19 @@ struct Geo {
 // For every block origin (z,y,x) with z <= D-4, y <= H-4, x <= W-4 (others are left
 // untouched): S2 = sum over the 4x4x4 block of u^2 (exact, < 2^38) and S1 = sum of u
 // (< 2^22), packed as uint2 {S2 mod 2^32, S1 | (S2 >> 32) << 24}.
-// Separable box sums: a CTA owns an 8 x 32 (y, x) tile of origins and marches along z; each
-// input plane tile (11 x 35) goes through shared memory once (4-tap sums along x, then along
-// y), the sum over 4 planes slides in registers.  HBM-bound: 2 B read + 8 B written per voxel.
-constexpr int K0_TY = 8, K0_TX = 32, K0_ZC = 64;
-__global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict__ u, uint2 *__restrict__ s21, int D,
-                                                      int H, int W, int nvol, int zo0, int zo1) {
-    __shared__ uint16_t s_in[K0_TY + 3][K0_TX + 4];
-    __shared__ unsigned long long s_x2[K0_TY + 3][K0_TX];
-    __shared__ uint32_t s_x1[K0_TY + 3][K0_TX];
+// Separable box sums without shared memory or barriers: a WARP owns K0_TY x 29 (y, x) origins and marches along
+// z.  Lane i holds column x0 + i of the K0_TY + 3 rows of a plane (the next plane's loads are issued before the
+// current one is summed); the 4-tap sum along x takes the three right-hand neighbours by shuffle (lanes 29-31
+// only feed them), the sums along y and z are register arithmetic (pair sums, three older plane sums per row).
+// HBM-bound: 2 B read + 8 B written per voxel.
+constexpr int K0_TY = 8, K0_TX = 29, K0_ZC = 64, K0_WARPS = 8;
+__global__ void __launch_bounds__(K0_WARPS * 32) k_block_energy(const uint16_t *__restrict__ u, uint2 *__restrict__ s21,
+                                                               int D, int H, int W, int nvol, int zo0, int zo1) {
+    const int lane = threadIdx.x & 31;
     const int ntx = (W - 3 + K0_TX - 1) / K0_TX, nty = (H - 3 + K0_TY - 1) / K0_TY;
     const int nzc = (zo1 - zo0 + K0_ZC - 1) / K0_ZC;  // origins z in [zo0, zo1) only
-    long long t = blockIdx.x;
+    long long t = (long long)blockIdx.x * K0_WARPS + (threadIdx.x >> 5);
+    if (t >= (long long)ntx * nty * nzc * nvol) return;  // warp-uniform
     const int txi = (int)(t % ntx);
     t /= ntx;
     const int tyi = (int)(t % nty);
@@ -150,38 +151,72 @@ __global__ void __launch_bounds__(256) k_block_energy(const uint16_t *__restrict
     const int x0 = txi * K0_TX, y0 = tyi * K0_TY, z0 = zo0 + zci * K0_ZC, z1 = min(z0 + K0_ZC, zo1);
     const uint16_t *__restrict__ uv = u + (long long)vol * D * H * W;
     uint2 *__restrict__ ov = s21 + (long long)vol * D * H * W;
-    const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
-    const bool wr = (y0 + ty <= H - 4) && (x0 + tx <= W - 4);
-    unsigned long long q1 = 0ull, q2 = 0ull, q3 = 0ull;  // plane sums of z-1, z-2, z-3
-    uint32_t l1 = 0u, l2 = 0u, l3 = 0u;
-    for (int z = z0; z < z1 + 3; ++z) {
-        for (int i = tid; i < (K0_TY + 3) * (K0_TX + 3); i += 256) {
-            const int yy = i / (K0_TX + 3), xx = i - yy * (K0_TX + 3);
-            const int gy = y0 + yy, gx = x0 + xx;
-            s_in[yy][xx] = (gy < H && gx < W) ? __ldg(uv + ((long long)z * H + gy) * W + gx) : (uint16_t)0;
+    const int gx = x0 + lane;
+    const bool cin = gx < W;
+    const bool wx = lane < K0_TX && gx <= W - 4;
+    const long long plane = (long long)H * W;
+    const uint16_t *col = uv + (cin ? gx : 0);
+
+    uint32_t nxt[K0_TY + 3];
+    auto load_plane = [&](int z) {
+        const uint16_t *pz = col + (long long)z * plane;
+#pragma unroll
+        for (int r = 0; r < K0_TY + 3; ++r) {
+            const int gy = y0 + r;
+            nxt[r] = (cin && gy < H) ? (uint32_t)__ldg(pz + (long long)gy * W) : 0u;
         }
-        __syncthreads();
-        for (int i = tid; i < (K0_TY + 3) * K0_TX; i += 256) {
-            const int yy = i >> 5, xx = i & 31;
-            const uint32_t a = s_in[yy][xx], b = s_in[yy][xx + 1], c = s_in[yy][xx + 2], d = s_in[yy][xx + 3];
-            s_x2[yy][xx] = (unsigned long long)(a * a) + (b * b) + (unsigned long long)(c * c) + (d * d);
-            s_x1[yy][xx] = a + b + c + d;
+    };
+    unsigned long long q1[K0_TY], q2[K0_TY], q3[K0_TY];  // plane sums of z-1, z-2, z-3 per output row
+    uint32_t l1[K0_TY], l2[K0_TY], l3[K0_TY];
+#pragma unroll
+    for (int r = 0; r < K0_TY; ++r) {
+        q1[r] = q2[r] = q3[r] = 0ull;
+        l1[r] = l2[r] = l3[r] = 0u;
+    }
+    load_plane(z0);
+    for (int z = z0; z < z1 + 3; ++z) {  // z1 + 2 <= D - 1
+        uint32_t cur[K0_TY + 3];
+#pragma unroll
+        for (int r = 0; r < K0_TY + 3; ++r) cur[r] = nxt[r];
+        if (z + 1 < z1 + 3) load_plane(z + 1);
+        // sums along x: this lane's value and its three right-hand neighbours
+        unsigned long long x2[K0_TY + 3];
+        uint32_t x1[K0_TY + 3];
+#pragma unroll
+        for (int r = 0; r < K0_TY + 3; ++r) {
+            const uint32_t a = cur[r];
+            const uint32_t b = __shfl_down_sync(B4D_FULL, a, 1), c = __shfl_down_sync(B4D_FULL, a, 2),
+                           d = __shfl_down_sync(B4D_FULL, a, 3);
+            x1[r] = a + b + c + d;
+            x2[r] = (unsigned long long)(a * a) + (b * b) + (unsigned long long)(c * c) + (d * d);
         }
-        __syncthreads();
-        const unsigned long long q0 = s_x2[ty][tx] + s_x2[ty + 1][tx] + s_x2[ty + 2][tx] + s_x2[ty + 3][tx];
-        const uint32_t l0 = s_x1[ty][tx] + s_x1[ty + 1][tx] + s_x1[ty + 2][tx] + s_x1[ty + 3][tx];
-        if (z >= z0 + 3 && wr) {
-            const unsigned long long s = q0 + q1 + q2 + q3;
-            const uint32_t m = l0 + l1 + l2 + l3;
-            // .x = S2 mod 2^32; .y = S1 | (S2 >> 32) << 24
-            ov[((long long)(z - 3) * H + y0 + ty) * W + x0 + tx] = make_uint2((uint32_t)s, m | ((uint32_t)(s >> 32) << 24));
+        // sums along y through pair sums, then the sliding sum along z
+        unsigned long long p2[K0_TY + 2];
+        uint32_t p1[K0_TY + 2];
+#pragma unroll
+        for (int r = 0; r < K0_TY + 2; ++r) {
+            p2[r] = x2[r] + x2[r + 1];
+            p1[r] = x1[r] + x1[r + 1];
         }
-        q3 = q2;
-        q2 = q1;
-        q1 = q0;
-        l3 = l2;
-        l2 = l1;
-        l1 = l0;
+        const bool out_z = z >= z0 + 3;
+        uint2 *orow = ov + (long long)(z - 3) * plane + gx;
+#pragma unroll
+        for (int r = 0; r < K0_TY; ++r) {
+            const unsigned long long q0 = p2[r] + p2[r + 2];
+            const uint32_t l0 = p1[r] + p1[r + 2];
+            if (out_z && wx && y0 + r <= H - 4) {
+                const unsigned long long sq = (q0 + q1[r]) + (q2[r] + q3[r]);
+                const uint32_t m = (l0 + l1[r]) + (l2[r] + l3[r]);
+                // .x = S2 mod 2^32; .y = S1 | (S2 >> 32) << 24
+                orow[(long long)(y0 + r) * W] = make_uint2((uint32_t)sq, m | ((uint32_t)(sq >> 32) << 24));
+            }
+            q3[r] = q2[r];
+            q2[r] = q1[r];
+            q1[r] = q0;
+            l3[r] = l2[r];
+            l2[r] = l1[r];
+            l1[r] = l0;
+        }
     }
 }
 
@@ -918,9 +953,10 @@ void launch_ns(const MatchParams &p, int cz0, int cz1, long long tile0, long lon
 void b4d_launch_block_energy_range(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, int zo0, int zo1,
                                    cudaStream_t s) {
     if (zo1 <= zo0) return;
-    const long long blocks = (long long)((W - 3 + K0_TX - 1) / K0_TX) * ((H - 3 + K0_TY - 1) / K0_TY) *
-                             ((zo1 - zo0 + K0_ZC - 1) / K0_ZC) * nvol;
-    k_block_energy<<<(unsigned)blocks, 256, 0, s>>>(u, s21, D, H, W, nvol, zo0, zo1);
+    const long long warps = (long long)((W - 3 + K0_TX - 1) / K0_TX) * ((H - 3 + K0_TY - 1) / K0_TY) *
+                            ((zo1 - zo0 + K0_ZC - 1) / K0_ZC) * nvol;
+    const long long blocks = (warps + K0_WARPS - 1) / K0_WARPS;
+    k_block_energy<<<(unsigned)blocks, K0_WARPS * 32, 0, s>>>(u, s21, D, H, W, nvol, zo0, zo1);
 }
 void b4d_launch_block_energy(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, cudaStream_t s) {
     b4d_launch_block_energy_range(u, s21, D, H, W, nvol, 0, D - 3, s);
