@@ -51,6 +51,7 @@
 // falls back to K rounds of "smallest key greater than the previous one".
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 
@@ -124,6 +125,39 @@ struct Geo {
     }
     static constexpr unsigned long long ORDER = order_pack();
 };
+
+// ---- TMA / mbarrier primitives (sm_90+): one elected thread issues the box load, everybody waits on the barrier
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // visible to the async proxy (the TMA unit)
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t mbar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 
 // ------------------------------------------------------------------ K0 ------
 // For every block origin (z,y,x) with z <= D-4, y <= H-4, x <= W-4 (others are left
@@ -217,6 +251,106 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k_block_energy(const uint16_t *
             l2[r] = l1[r];
             l1[r] = l0;
         }
+    }
+}
+
+// The same sums with the input planes brought in by TMA (the production path when W % 8 == 0): a CTA of 4 warps owns
+// K0_TY x 112 origins and marches along z; one 4-D box load per plane (120 x 11 uint16, zero fill outside the
+// volume) lands in a ring of K0T_NST shared-memory stages, so that 8 planes (21 KB) per CTA are in flight without a
+// register or an LSU slot being spent on them.  Full / empty mbarriers per stage; thread 0 refills the stage of
+// plane i - 1 after its own work on plane i (the other warps have normally released it by then).  Each warp reads
+// its 28 + 3 columns from the stage (one 2-byte LDS per row) and works on packed 64-bit words
+// v^2 | v << 40: every partial sum of S2 stays below 2^38 and of S1 below 2^22, so one 64-bit addition serves both.
+// Rows are summed first (registers), then columns by two shuffles (v + right neighbour, pair + pair two lanes on);
+// the three older plane sums per row are kept by phase (z mod 3), nothing is moved.
+constexpr int K0T_WARPS = 4, K0T_WX = 28, K0T_TX = K0T_WARPS * K0T_WX, K0T_BOXW = 120, K0T_ROWS = K0_TY + 3, K0T_NST = 8;
+constexpr uint32_t K0T_BOX_BYTES = K0T_BOXW * K0T_ROWS * 2;
+constexpr int K0T_STAGE = ((int)K0T_BOX_BYTES + 127) / 128 * 128;
+static_assert(K0T_TX % 8 == 0 && K0T_BOXW % 8 == 0 && K0T_BOXW >= K0T_TX + 3 && K0T_BOXW >= (K0T_WARPS - 1) * K0T_WX + 32,
+              "TMA box of K0");
+__global__ void __launch_bounds__(K0T_WARPS * 32) k_block_energy_tma(const __grid_constant__ CUtensorMap tmap,
+                                                                    uint2 *__restrict__ s21, int D, int H, int W, int nvol,
+                                                                    int zo0, int zo1) {
+    __shared__ __align__(128) unsigned char s_buf[K0T_NST * K0T_STAGE];
+    __shared__ __align__(8) unsigned long long s_full[K0T_NST], s_empty[K0T_NST];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntx = (W - 3 + K0T_TX - 1) / K0T_TX, nty = (H - 3 + K0_TY - 1) / K0_TY;
+    const int nzc = (zo1 - zo0 + K0_ZC - 1) / K0_ZC;
+    long long t = blockIdx.x;
+    const int txi = (int)(t % ntx);
+    t /= ntx;
+    const int tyi = (int)(t % nty);
+    t /= nty;
+    const int zci = (int)(t % nzc);
+    const int vol = (int)(t / nzc);
+    const int x0 = txi * K0T_TX, y0 = tyi * K0_TY, z0 = zo0 + zci * K0_ZC, z1 = min(z0 + K0_ZC, zo1);
+    const int nplanes = z1 + 3 - z0;  // input planes z0 .. z1 + 2 (<= D - 1)
+    const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(s_buf);
+    const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(s_full), empty0 = (uint32_t)__cvta_generic_to_shared(s_empty);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < K0T_NST; ++i) {
+            mbar_init(full0 + 8u * i, 1);
+            mbar_init(empty0 + 8u * i, K0T_WARPS);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < min(K0T_NST, nplanes); ++i) {
+            mbar_expect_tx(full0 + 8u * i, K0T_BOX_BYTES);
+            tma_load_4d(buf0 + (uint32_t)(i * K0T_STAGE), &tmap, full0 + 8u * i, x0, y0, z0 + i, vol);
+        }
+    }
+    const int gx = x0 + warp * K0T_WX + lane;
+    const bool wx = lane < K0T_WX && gx <= W - 4;
+    const long long plane = (long long)H * W;
+    uint2 *ocol = s21 + (long long)vol * D * plane + gx;
+    unsigned long long h[3][K0_TY];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int r = 0; r < K0_TY; ++r) h[k][r] = 0ull;
+
+    auto step = [&](auto PH, int i) {
+        constexpr int ph = decltype(PH)::value;
+        const int slot = i % K0T_NST;
+        mbar_wait(full0 + 8u * slot, (uint32_t)((i / K0T_NST) & 1));
+        const uint16_t *sp = reinterpret_cast<const uint16_t *>(s_buf + slot * K0T_STAGE) + warp * K0T_WX + lane;
+        uint32_t a[K0T_ROWS];
+#pragma unroll
+        for (int r = 0; r < K0T_ROWS; ++r) a[r] = sp[r * K0T_BOXW];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+        if (threadIdx.x == 0 && i >= 1 && i - 1 + K0T_NST < nplanes) {  // refill the stage of the previous plane
+            const int ps = (i - 1) % K0T_NST;
+            mbar_wait(empty0 + 8u * ps, (uint32_t)(((i - 1) / K0T_NST) & 1));
+            mbar_expect_tx(full0 + 8u * ps, K0T_BOX_BYTES);
+            tma_load_4d(buf0 + (uint32_t)(ps * K0T_STAGE), &tmap, full0 + 8u * ps, x0, y0, z0 + i - 1 + K0T_NST, vol);
+        }
+        unsigned long long w[K0T_ROWS], pr[K0T_ROWS - 1];
+#pragma unroll
+        for (int r = 0; r < K0T_ROWS; ++r) w[r] = (unsigned long long)(a[r] * a[r]) | ((unsigned long long)a[r] << 40);
+#pragma unroll
+        for (int r = 0; r < K0T_ROWS - 1; ++r) pr[r] = w[r] + w[r + 1];
+        const bool out_z = i >= 3;
+        uint2 *orow = ocol + (long long)(z0 + i - 3) * plane;
+#pragma unroll
+        for (int r = 0; r < K0_TY; ++r) {
+            const unsigned long long c = pr[r] + pr[r + 2];                           // 4 rows of this column
+            const unsigned long long c2 = c + __shfl_down_sync(B4D_FULL, c, 1);      // columns x, x + 1
+            const unsigned long long q0 = c2 + __shfl_down_sync(B4D_FULL, c2, 2);    // columns x .. x + 3
+            if (out_z && wx && y0 + r <= H - 4) {
+                const unsigned long long sq = (q0 + h[0][r]) + (h[1][r] + h[2][r]);
+                const uint32_t hi = (uint32_t)(sq >> 32);  // bits 0-5: S2 >> 32, bits 8-29: S1
+                // .x = S2 mod 2^32; .y = S1 | (S2 >> 32) << 24 = hi rotated right by 8
+                orow[(long long)(y0 + r) * W] = make_uint2((uint32_t)sq, __funnelshift_r(hi, hi, 8));
+            }
+            h[ph][r] = q0;  // replaces the sum of plane i - 3
+        }
+    };
+    for (int i = 0; i < nplanes; i += 3) {
+        step(std::integral_constant<int, 0>{}, i);
+        if (i + 1 < nplanes) step(std::integral_constant<int, 1>{}, i + 1);
+        if (i + 2 < nplanes) step(std::integral_constant<int, 2>{}, i + 2);
     }
 }
 
@@ -406,36 +540,6 @@ __device__ __forceinline__ void r8corr_row_rolled(const uint32_t *__restrict__ b
             acc[j] = __dp2a_hi(p1, r, acc[j]);
         }
     }
-}
-
-// ---- TMA / mbarrier primitives (sm_90+): one elected thread issues the box load, everybody waits on the barrier
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // visible to the async proxy (the TMA unit)
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(mbar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t mbar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
 }
 
 template <int NS, bool K32, bool BYTE>
@@ -953,8 +1057,23 @@ void launch_ns(const MatchParams &p, int cz0, int cz1, long long tile0, long lon
 void b4d_launch_block_energy_range(const uint16_t *u, uint2 *s21, int D, int H, int W, int nvol, int zo0, int zo1,
                                    cudaStream_t s) {
     if (zo1 <= zo0) return;
-    const long long warps = (long long)((W - 3 + K0_TX - 1) / K0_TX) * ((H - 3 + K0_TY - 1) / K0_TY) *
-                            ((zo1 - zo0 + K0_ZC - 1) / K0_ZC) * nvol;
+    const long long nzc = (zo1 - zo0 + K0_ZC - 1) / K0_ZC;
+    EncodeTiledFn fn = ((W & 7) == 0 && !getenv("B4D_NO_TMA")) ? encode_fn() : nullptr;
+    if (fn) {
+        CUtensorMap map;
+        const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)nvol};
+        const cuuint64_t strides[3] = {(cuuint64_t)W * 2, (cuuint64_t)W * H * 2, (cuuint64_t)W * H * D * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)K0T_BOXW, (cuuint32_t)K0T_ROWS, 1u, 1u};
+        const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+        if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint16_t *>(u), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            const long long blocks = (long long)((W - 3 + K0T_TX - 1) / K0T_TX) * ((H - 3 + K0_TY - 1) / K0_TY) * nzc * nvol;
+            k_block_energy_tma<<<(unsigned)blocks, K0T_WARPS * 32, 0, s>>>(map, s21, D, H, W, nvol, zo0, zo1);
+            return;
+        }
+    }
+    const long long warps = (long long)((W - 3 + K0_TX - 1) / K0_TX) * ((H - 3 + K0_TY - 1) / K0_TY) * nzc * nvol;
     const long long blocks = (warps + K0_WARPS - 1) / K0_WARPS;
     k_block_energy<<<(unsigned)blocks, K0_WARPS * 32, 0, s>>>(u, s21, D, H, W, nvol, zo0, zo1);
 }
