@@ -53,9 +53,8 @@
 #include <cstring>
 #include <type_traits>
 
-#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
-
 #include "b4d_common.cuh"
+#include "b4d_tma.cuh"
 
 namespace {
 
@@ -125,39 +124,6 @@ struct Geo {
     }
     static constexpr unsigned long long ORDER = order_pack();
 };
-
-// ---- TMA / mbarrier primitives (sm_90+): one elected thread issues the box load, everybody waits on the barrier
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // visible to the async proxy (the TMA unit)
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(mbar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t mbar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
 
 // ------------------------------------------------------------------ K0 ------
 // For every block origin (z,y,x) with z <= D-4, y <= H-4, x <= W-4 (others are left
@@ -986,24 +952,6 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
 // Tensor map of the uint16 matching image as a 4-D tensor (x, y, z, volume); box = the staged neighbourhood of one
 // tile.  Needs row and plane pitches that are multiples of 16 bytes (W % 8 == 0); otherwise the kernels keep the
 // cp.async / plain-load staging.  The encoder comes from the driver through the runtime (no -lcuda).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-        else
-            cudaGetLastError();
-    }
-    return fn;
-}
 template <int NS>
 bool make_window_map(const MatchParams &p, CUtensorMap *map) {
     using G = Geo<NS>;

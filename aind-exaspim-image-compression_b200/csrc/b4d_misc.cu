@@ -5,6 +5,7 @@
 // All elementwise kernels are grid-stride over 16-byte vectors with the grid
 // sized to a multiple of the SM count; the tail is handled scalar.
 #include "b4d_common.cuh"
+#include "b4d_tma.cuh"
 
 namespace {
 
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) k_clip(float *__restrict__ x, long long n
 // fallback is read only where the denominator is zero, which a complete block grid never produces).
 // Optional fused outputs: the uint16 matching image of the next stage (K3: saves the separate conversion pass) and
 // the quantized uint16 volume (K6 + K7 fused: float32 result never written).
-constexpr int WM_TY = 8, WM_TX = 29, WM_NZ = 32, WM_WARPS = 8;
+constexpr int WM_TY = 8, WM_TX = 29, WM_NZ = 32, WM_WARPS = 4;
 constexpr int WM_EY = WM_TY + 3;
 struct NormOut {
     float *out;          // float32 result (may be null when q16 is set)
@@ -206,13 +207,28 @@ __global__ void __launch_bounds__(WM_WARPS * 32) k_normalise_wm(const long long 
     double h1[WM_TY], h2[WM_TY], h3[WM_TY];  // xy-convolved map of the three previous planes
 #pragma unroll
     for (int r = 0; r < WM_TY; ++r) h1[r] = h2[r] = h3[r] = 0.0;
-    for (int z = Za - 3; z < Zb; ++z) {
-        uint32_t gv[WM_EY];
+    // Memory latency is the limit of this kernel (ncu: long-scoreboard stalls, DRAM at 17 %), so every load is
+    // issued well ahead of its use: the map values of plane z + 1 and the numerators of plane z before plane z is
+    // convolved.
+    uint32_t gn[WM_EY];
+    auto load_map = [&](int z) {
 #pragma unroll
         for (int r = 0; r < WM_EY; ++r) {
             const int yy = Y0 - 3 + r;
-            gv[r] = (z >= 0 && col_in && (unsigned)yy < (unsigned)H) ? __ldg(g + (long long)z * P + (long long)yy * W + gx) : 0u;
+            gn[r] = (z >= 0 && col_in && (unsigned)yy < (unsigned)H) ? __ldg(g + (long long)z * P + (long long)yy * W + gx) : 0u;
         }
+    };
+    load_map(Za - 3);
+    for (int z = Za - 3; z < Zb; ++z) {
+        uint32_t gv[WM_EY];
+#pragma unroll
+        for (int r = 0; r < WM_EY; ++r) gv[r] = gn[r];
+        if (z + 1 < Zb) load_map(z + 1);
+        const bool out_z = z >= Za && out_lane;
+        const long long a0 = vol * V + (long long)z * P + (long long)Y0 * W + gx;
+        long long nq[WM_TY];
+#pragma unroll
+        for (int r = 0; r < WM_TY; ++r) nq[r] = (out_z && Y0 + r < H) ? __ldcs(numq + a0 + (long long)r * W) : 0ll;
         double xr[WM_EY];  // x pass: sum over d of k[d] G[x - d]
 #pragma unroll
         for (int r = 0; r < WM_EY; ++r) {
@@ -226,14 +242,121 @@ __global__ void __launch_bounds__(WM_WARPS * 32) k_normalise_wm(const long long 
             double w0 = 0.0;  // y pass
 #pragma unroll
             for (int d = 0; d < 4; ++d) w0 = fma(k[d], xr[r + 3 - d], w0);
-            const int gy = Y0 + r;
-            if (z >= Za && out_lane && gy < H) {
+            if (out_z && Y0 + r < H) {
                 double den = fma(k[0], w0, 0.0);
                 den = fma(k[1], h1[r], den);
                 den = fma(k[2], h2[r], den);
                 den = fma(k[3], h3[r], den);
-                const long long a = vol * V + (long long)z * P + (long long)gy * W + gx;
-                const float y = den > 0.0 ? (float)(((double)__ldcs(numq + a) / den) * inv) : fb[a];
+                const long long a = a0 + (long long)r * W;
+                const float y = den > 0.0 ? (float)(((double)nq[r] / den) * inv) : fb[a];
+                if (o.out) o.out[a] = y;
+                if (o.match) o.match[a] = (uint16_t)to_match(y, 0.0f, o.mscale, o.ishift);
+                if (o.q16)
+                    o.q16[a] = (uint16_t)(o.q_trunc ? quant1_trunc(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0)
+                                                    : quant1(y, o.q_sub, o.q_add, o.q_step, o.q_hi, o.q_unit != 0));
+            }
+            h3[r] = h2[r];
+            h2[r] = h1[r];
+            h1[r] = w0;
+        }
+    }
+}
+
+// The same arithmetic with the inputs brought in by TMA (the production path when W % 4 == 0).  A CTA of 4 warps owns
+// 8 x 112 (y, x) voxels and marches along z; per plane two box loads (the map: 120 x 11 uint32 from (x0 - 4, Y0 - 3),
+// zero fill outside the volume = "no block there"; the numerators: 112 x 8 int64) land in a ring of WMT_NST stages,
+// full / empty mbarriers per stage, thread 0 refills the stage of the previous plane.  ~50 KB of loads per CTA are in
+// flight without costing registers; the warps only read shared memory.  Lane i of warp w holds map column
+// x0 + 28 w - 3 + i (lanes 3-30 produce outputs).
+constexpr int WMT_WARPS = 4, WMT_WX = 28, WMT_TX = WMT_WARPS * WMT_WX, WMT_GW = 120, WMT_NST = 4;
+constexpr uint32_t WMT_G_BYTES = WMT_GW * WM_EY * 4, WMT_N_BYTES = WMT_TX * WM_TY * 8;
+constexpr int WMT_G_STAGE = ((int)WMT_G_BYTES + 127) / 128 * 128;
+constexpr int WMT_STAGE = WMT_G_STAGE + (int)WMT_N_BYTES;
+static_assert(WMT_TX % 4 == 0 && WMT_GW % 4 == 0 && WMT_GW >= WMT_TX + 4 && WMT_N_BYTES % 128 == 0, "TMA boxes of the normalise kernel");
+__global__ void __launch_bounds__(WMT_WARPS * 32, 4) k_normalise_wm_tma(const __grid_constant__ CUtensorMap gmap_t,
+                                                                       const __grid_constant__ CUtensorMap numq_t,
+                                                                       const float *__restrict__ fb, NormOut o, int D, int H,
+                                                                       int W, int nvol, int z0, int z1, float inv_qscale,
+                                                                       float kf0, float kf1, float kf2, float kf3) {
+    extern __shared__ __align__(128) unsigned char s_buf[];
+    __shared__ __align__(8) unsigned long long s_full[WMT_NST], s_empty[WMT_NST];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double k[4] = {(double)kf0, (double)kf1, (double)kf2, (double)kf3};
+    const double inv = (double)inv_qscale;
+    const int ntx = (W + WMT_TX - 1) / WMT_TX, nty = (H + WM_TY - 1) / WM_TY, ntz = (z1 - z0 + WM_NZ - 1) / WM_NZ;
+    long long t = blockIdx.x;
+    const int ix = (int)(t % ntx);
+    t /= ntx;
+    const int iy = (int)(t % nty);
+    t /= nty;
+    const int iz = (int)(t % ntz);
+    const int vol = (int)(t / ntz);
+    const long long P = (long long)H * W, V = P * D;
+    const int x0 = ix * WMT_TX, Y0 = iy * WM_TY, Za = z0 + iz * WM_NZ, Zb = min(Za + WM_NZ, z1);
+    const int nplanes = Zb - (Za - 3);
+    const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(s_buf);
+    const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(s_full), empty0 = (uint32_t)__cvta_generic_to_shared(s_empty);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WMT_NST; ++i) {
+            mbar_init(full0 + 8u * i, 1);
+            mbar_init(empty0 + 8u * i, WMT_WARPS);
+        }
+    }
+    __syncthreads();
+    auto issue = [&](int i) {  // plane Za - 3 + i into stage i % WMT_NST (thread 0)
+        const int st = i % WMT_NST, z = Za - 3 + i;
+        const uint32_t dst = buf0 + (uint32_t)(st * WMT_STAGE), bar = full0 + 8u * st;
+        mbar_expect_tx(bar, WMT_G_BYTES + (i >= 3 ? WMT_N_BYTES : 0u));
+        tma_load_4d(dst, &gmap_t, bar, x0 - 4, Y0 - 3, z, vol);
+        if (i >= 3) tma_load_4d(dst + WMT_G_STAGE, &numq_t, bar, x0, Y0, z, vol);  // run-in planes need no numerators
+    };
+    if (threadIdx.x == 0)
+        for (int i = 0; i < min(WMT_NST, nplanes); ++i) issue(i);
+    const int gx = x0 + warp * WMT_WX - 3 + lane;  // this lane's column
+    const bool out_lane = lane >= 3 && lane < 3 + WMT_WX && gx < W;
+    double h1[WM_TY], h2[WM_TY], h3[WM_TY];  // xy-convolved map of the three previous planes
+#pragma unroll
+    for (int r = 0; r < WM_TY; ++r) h1[r] = h2[r] = h3[r] = 0.0;
+    for (int i = 0; i < nplanes; ++i) {
+        const int st = i % WMT_NST, z = Za - 3 + i;
+        mbar_wait(full0 + 8u * st, (uint32_t)((i / WMT_NST) & 1));
+        const unsigned char *sb = s_buf + st * WMT_STAGE;
+        const uint32_t *sg = reinterpret_cast<const uint32_t *>(sb) + warp * WMT_WX + 1 + lane;  // column gx - (x0 - 4)
+        const long long *sn = reinterpret_cast<const long long *>(sb + WMT_G_STAGE) + warp * WMT_WX + (lane - 3);
+        uint32_t gv[WM_EY];
+#pragma unroll
+        for (int r = 0; r < WM_EY; ++r) gv[r] = sg[r * WMT_GW];
+        const bool out_z = i >= 3 && out_lane;
+        long long nq[WM_TY];
+#pragma unroll
+        for (int r = 0; r < WM_TY; ++r) nq[r] = out_z ? sn[r * WMT_TX] : 0ll;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * st);
+        if (threadIdx.x == 0 && i >= 1 && i - 1 + WMT_NST < nplanes) {  // refill the stage of the previous plane
+            mbar_wait(empty0 + 8u * ((i - 1) % WMT_NST), (uint32_t)(((i - 1) / WMT_NST) & 1));
+            issue(i - 1 + WMT_NST);
+        }
+        double xr[WM_EY];  // x pass: sum over d of k[d] G[x - d]
+#pragma unroll
+        for (int r = 0; r < WM_EY; ++r) {
+            double acc = fma(k[0], (double)gv[r], 0.0);
+#pragma unroll
+            for (int d = 1; d < 4; ++d) acc = fma(k[d], (double)__shfl_up_sync(B4D_FULL, gv[r], d), acc);
+            xr[r] = acc;
+        }
+        const long long a0 = (long long)vol * V + (long long)z * P + (long long)Y0 * W + gx;
+#pragma unroll
+        for (int r = 0; r < WM_TY; ++r) {
+            double w0 = 0.0;  // y pass
+#pragma unroll
+            for (int d = 0; d < 4; ++d) w0 = fma(k[d], xr[r + 3 - d], w0);
+            if (out_z && Y0 + r < H) {
+                double den = fma(k[0], w0, 0.0);
+                den = fma(k[1], h1[r], den);
+                den = fma(k[2], h2[r], den);
+                den = fma(k[3], h3[r], den);
+                const long long a = a0 + (long long)r * W;
+                const float y = den > 0.0 ? (float)(((double)nq[r] / den) * inv) : fb[a];
                 if (o.out) o.out[a] = y;
                 if (o.match) o.match[a] = (uint16_t)to_match(y, 0.0f, o.mscale, o.ishift);
                 if (o.q16)
@@ -639,8 +762,22 @@ void b4d_launch_to_match(const float *in, uint16_t *out, long long n, float cf, 
 static void launch_norm(const long long *numq, const uint32_t *gmap, const float *fallback, const NormOut &o, int D,
                         int H, int W, int nvol, int z0, int z1, float inv_qscale, const float kf[4], cudaStream_t s) {
     if (z1 <= z0) return;
-    const long long tiles = (long long)nvol * ((z1 - z0 + WM_NZ - 1) / WM_NZ) * ((H + WM_TY - 1) / WM_TY) *
-                            ((W + WM_TX - 1) / WM_TX);
+    const long long ntz = (z1 - z0 + WM_NZ - 1) / WM_NZ, nty = (H + WM_TY - 1) / WM_TY;
+    CUtensorMap mg, mn;
+    if ((W & 3) == 0 && !getenv("B4D_NO_TMA") &&
+        make_map_4d(&mg, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, gmap, W, H, D, nvol, WMT_GW, WM_EY, 1) &&
+        make_map_4d(&mn, CU_TENSOR_MAP_DATA_TYPE_INT64, 8, numq, W, H, D, nvol, WMT_TX, WM_TY, 1)) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_normalise_wm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, WMT_NST * WMT_STAGE);
+            attr = true;
+        }
+        const long long blocks = (long long)nvol * ntz * nty * ((W + WMT_TX - 1) / WMT_TX);
+        k_normalise_wm_tma<<<(unsigned)blocks, WMT_WARPS * 32, WMT_NST * WMT_STAGE, s>>>(
+            mg, mn, fallback, o, D, H, W, nvol, z0, z1, inv_qscale, kf[0], kf[1], kf[2], kf[3]);
+        return;
+    }
+    const long long tiles = (long long)nvol * ntz * nty * ((W + WM_TX - 1) / WM_TX);
     k_normalise_wm<<<(unsigned)((tiles + WM_WARPS - 1) / WM_WARPS), WM_WARPS * 32, 0, s>>>(
         numq, gmap, fallback, o, D, H, W, nvol, z0, z1, inv_qscale, kf[0], kf[1], kf[2], kf[3]);
 }
