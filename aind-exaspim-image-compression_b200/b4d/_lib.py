@@ -12,7 +12,7 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("B4D_LIB") or os.path.join(_PKG, "libb4d.so")
 
 ABI_VERSION = 1
-T_NAMES = ("prep", "match1", "filter1", "norm1", "match2", "filter2", "norm2", "spare")
+T_NAMES = ("prep", "match1", "filter1", "norm1", "match2", "filter2", "norm2", "k0")
 T_COUNT = 8
 
 EXPORTS = (

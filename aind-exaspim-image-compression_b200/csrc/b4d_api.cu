@@ -432,8 +432,9 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     // ---- stage 1: hard thresholding
     B4D_TRY(zero_acc());
     const bool streamed = src && src->host && can_stream_upload(h, pl) && R1 > 0;
+    clk.mark(B4D_T_PREP, 1);
     if (!streamed) b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
-    clk.mark(B4D_T_PREP, 2);
+    clk.mark(B4D_T_K0, 1);
     mp.g = g1;
     mp.u = d_u;
     mp.s21 = h->s2.as<uint2>();
@@ -590,8 +591,9 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     } else {
         if (!fused_match) b4d_launch_to_match(d_basic, d_u, TV, 0.0f, mm.scale, mm.ishift, s);
         B4D_TRY(zero_acc());
+        clk.mark(B4D_T_PREP, 2);
         b4d_launch_block_energy(d_u, h->s2.as<uint2>(), pl.D, pl.H, pl.W, pl.nvol, s);
-        clk.mark(B4D_T_PREP, 3);
+        clk.mark(B4D_T_K0, 1);
         if (R2 > 0) b4d_launch_match(mp, p.search_wie, s);
         clk.mark(B4D_T_MATCH2, 4);
     }

@@ -476,17 +476,23 @@ def main():
             pass
         t_norm = (fam.get("norm1", 0.0) + fam.get("norm2", 0.0)) / (2.0 * args.steps) * 1e-3
         slab_vox = float(ze - zb) * S * S
+        t_k0 = fam.get("k0", 0.0) / (2.0 * args.steps) * 1e-3
         kernels = {
             "match": {"bound": "int32", "achieved": achieved / 1e12, "peak": peaks["sub_mad"] / 1e12, "unit": "TOP/s",
                       "frac": achieved / peaks["sub_mad"] if peaks["sub_mad"] else None,
                       "ms_per_launch": t_match * 1e3},
             # K3 / K6 count 8 B read + 4 B write per voxel (the kernel itself moves more: int64
-            # numerator, uint32 weight map, float32 fallback, float32 out = 20 B/voxel)
+            # numerator, uint32 weight map, float32 out = 16 B/voxel; the fallback is read only where den = 0)
             "normalise": {"bound": "hbm", "achieved": 12.0 * slab_vox / t_norm / 1e9 if t_norm > 0 else None,
                           "peak": hbm_peak, "unit": "GB/s",
                           "frac": 12.0 * slab_vox / t_norm / 1e9 / hbm_peak if t_norm > 0 else None,
-                          "moved_bytes_per_voxel": 20.0,
+                          "moved_bytes_per_voxel": 16.0,
                           "ms_per_launch": t_norm * 1e3},
+            # K0: uint16 read + {S2, S1} table write = 10 B/voxel, two launches per step (TMA-fed)
+            "block_energy": {"bound": "hbm", "achieved": 10.0 * slab_vox / t_k0 / 1e9 if t_k0 > 0 else None,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": 10.0 * slab_vox / t_k0 / 1e9 / hbm_peak if t_k0 > 0 else None,
+                             "ms_per_launch": t_k0 * 1e3},
             # K7: float32 read + uint16 write = 6 B/voxel
             "quantize": {"bound": "hbm", "achieved": 6.0 * q_vox / (q_ms * 1e-3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": 6.0 * q_vox / (q_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": q_ms},

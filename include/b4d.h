@@ -248,6 +248,7 @@ int b4d_stats_from_hist(const int64_t *hist, double pct, b4d_stats *out);
 #define B4D_T_MATCH2 4
 #define B4D_T_FILTER2 5
 #define B4D_T_NORM2 6
+#define B4D_T_K0 7 /* block energies (K0) where they run as a launch of their own; inside PREP otherwise */
 #define B4D_T_COUNT 8
 int b4d_last_timings(b4d_handle *h, float ms[B4D_T_COUNT], int64_t launches[B4D_T_COUNT]);
 
