@@ -85,13 +85,28 @@ def write_patch_cache(cache_dir, patches_u16, offsets, sigma_bm4d, fg=None, tran
         "denoiser": "b4d (B200-native BM4D, libb4d.so)",
     }
     cfg.update(extra_config or {})
+    # what a resumed run must agree on besides (N, shape, sigma): the clip, the offsets and the input itself
+    # (a hash of every patch's first and last plane and of the whole of up to 64 evenly spaced patches)
+    import hashlib
+
+    hsh = hashlib.sha1()
+    hsh.update(np.float64(max_count).tobytes())
+    hsh.update(np.ascontiguousarray(off).tobytes())
+    hsh.update(b"fg" if fg is not None else b"nofg")
+    for i in range(n):
+        hsh.update(np.ascontiguousarray(patches_u16[i, 0]).tobytes())
+        hsh.update(np.ascontiguousarray(patches_u16[i, -1]).tobytes())
+    for i in np.unique(np.linspace(0, n - 1, min(n, 64)).astype(np.int64)):
+        hsh.update(np.ascontiguousarray(patches_u16[i]).tobytes())
+    cfg["b4d_resume_fingerprint"] = hsh.hexdigest()
     paths = {k: os.path.join(cache_dir, k + ".npy") for k in ("raw", "teacher", "fg", "done")}
     fresh = not (resume and all(os.path.exists(p) for p in paths.values()))
     if not fresh:
         try:
             old = json.load(open(os.path.join(cache_dir, "config.json")))
-            fresh = (old.get("n_patches"), old.get("patch_shape"), old.get("sigma_bm4d")) != (
-                n, list(shape[1:]), float(sigma_bm4d))
+            fresh = (old.get("n_patches"), old.get("patch_shape"), old.get("sigma_bm4d"),
+                     old.get("b4d_resume_fingerprint")) != (n, list(shape[1:]), float(sigma_bm4d),
+                                                            cfg["b4d_resume_fingerprint"])
         except Exception:
             fresh = True
     mode = "w+" if fresh else "r+"

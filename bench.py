@@ -187,8 +187,10 @@ def oracle_threads():
     return np_oracle.set_threads(len(os.sched_getaffinity(0)))
 
 
-def cpu_port_throughput(sample_shape, repeats=1):
-    """voxels/s of the CPU oracle (float32 path, OpenMP over all host cores)."""
+def cpu_port_throughput(sample_shape, repeats=1, dn=None):
+    """voxels/s of the CPU oracle (float32 path, OpenMP over all host cores).  With a Denoiser the oracle also acts
+    as the checker: the GPU result on the same sample is compared with the oracle's, and a 64^3 crop with the
+    float64 oracle (max-abs, and how many stage-2 groups differ between the float32 and the float64 pipeline)."""
     from oracle import np_oracle
 
     vol = make_sample_host(sample_shape)
@@ -196,10 +198,33 @@ def cpu_port_throughput(sample_shape, repeats=1):
     best = None
     for _ in range(repeats):
         t = time.perf_counter()
-        o.denoise(vol, SIGMA)
+        ref = o.denoise(vol, SIGMA)
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
-    return vol.size / best, best
+    parity = None
+    if dn is not None:
+        from oracle import parity_util
+
+        y = np.asarray(dn.denoise(vol, SIGMA))
+        diff = np.abs(y.astype(np.float64) - ref.astype(np.float64))
+        parity = {"vs_float32_mirror": {"voxels": int(vol.size), "bit_equal": bool((y.view(np.uint32) == ref.view(np.uint32)).all()),
+                                        "voxels_differing": int((y.view(np.uint32) != ref.view(np.uint32)).sum()),
+                                        "max_abs": float(diff.max())}}
+        crop = np.ascontiguousarray(vol[:64, :64, :64])
+        of = np_oracle.Oracle("f64")
+        f = of.denoise(crop, SIGMA)
+        o.denoise(crop, SIGMA)
+        yc = np.asarray(dn.denoise(crop, SIGMA))
+        try:
+            rep = parity_util.check_against_f64(yc, f, o.stage2_matches(crop.shape), of.stage2_matches(crop.shape), 0.5, 0.05, NS)
+            rep["within_bar"] = True
+        except AssertionError as e:  # report, never hide
+            rep = dict(e.args[0]) if e.args and isinstance(e.args[0], dict) else {"error": str(e)}
+            rep["within_bar"] = False
+        rl2 = float(np.linalg.norm(yc.astype(np.float64) - f) / np.linalg.norm(f))
+        parity["vs_float64_oracle"] = dict(rep, voxels=int(crop.size), rel_l2=rl2,
+                                           bar="max-abs <= 0.5 except under flipped stage-2 matches; rel-L2 <= 1e-3")
+    return vol.size / best, best, parity
 
 
 def run_reference(args):
@@ -556,10 +581,11 @@ def main():
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (the other ranks would idle in a barrier)
             shape = (192, 256, 256)
             threads = oracle_threads()
-            v, secs = cpu_port_throughput(shape)
+            v, secs, parity = cpu_port_throughput(shape, dn=dn)
             line["cpu_baseline"] = {
                 "value": v, "unit": "voxels/s", "cores": threads, "kind": "port",
                 "sample": "%dx%dx%d sub-volume of the same seeded volume, one pass (%.1f s); CPU restatement, not the closed bm4d binary" % (shape + (secs,)),
+                "parity_of_the_gpu_path_on_the_sample": parity,
             }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,4 +1,5 @@
-"""Helpers shared by the parity tests: tracing float32-vs-float64 differences to flipped stage-2 matches."""
+"""Test infrastructure (never imported by the product).  Helpers shared by the parity tests and by the cpu_baseline
+leg of bench.py: tracing float32-vs-float64 differences to flipped stage-2 matches."""
 import numpy as np
 
 from oracle import np_oracle

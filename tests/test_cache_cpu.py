@@ -78,6 +78,14 @@ def test_cache_resume_skips_finished_patches(tmp_path, oracle_lib):
     assert np.array_equal(fgm.astype(bool), fgf(patches, np.full(4, 37.0, np.float32)))
     # a different configuration starts over
     assert cache.write_patch_cache(d, patches, 37.0, 10.0, targets_fn=base, fg_fn=fgf, batch=4) == 4
+    # ... and so do different offsets, a different clip or different patches with the same N, shape and sigma
+    # (the resume fingerprint in config.json); the same input again computes nothing
+    assert cache.write_patch_cache(d, patches, 37.0, 10.0, targets_fn=base, fg_fn=fgf, batch=4) == 0
+    assert cache.write_patch_cache(d, patches, 36.0, 10.0, targets_fn=base, fg_fn=fgf, batch=4) == 4
+    assert cache.write_patch_cache(d, patches, 36.0, 10.0, targets_fn=base, fg_fn=fgf, batch=4, max_count=1000.0) == 4
+    other = patches.copy()
+    other[2, 3, 3, 3] ^= 1
+    assert cache.write_patch_cache(d, other, 36.0, 10.0, targets_fn=base, fg_fn=fgf, batch=4, max_count=1000.0) == 4
 
 
 def test_cache_rejects_bad_input(tmp_path):

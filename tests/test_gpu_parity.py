@@ -9,7 +9,7 @@ Bars (BASELINE.json north_star / DESIGN.md §5):
     Block matching is discontinuous, so a float64 pipeline may flip a handful of near-tied
     stage-2 matches; the tests extract the stage-2 match lists of both pipelines and PROVE that
     every voxel above 0.5 lies under a flipped group, and that the difference stays below 0.01
-    everywhere else (tests/parity_util.py);
+    everywhere else (oracle/parity_util.py);
   * quantize, statistics: bit-exact.
 """
 import numpy as np
@@ -137,7 +137,7 @@ def test_default_profile_config1_patch(dn, oracle_lib):
 
     vol = synth.vol(64, 64, 64, seed=1)  # BASELINE config 1 input
     raw = vol.astype(np.float32) - np.float32(37.0)
-    import parity_util
+    from oracle import parity_util
 
     for z in (vol, raw):
         y = dn.denoise(z, 24.0)

@@ -73,7 +73,7 @@ def test_large_differences_between_the_two_oracle_paths_sit_under_flipped_matche
     voxels; every one of them lies under a stage-2 group whose match list flipped between the two pipelines
     (near-tied candidates, matching image rounded from basic estimates that differ by 1e-4), and away from
     such groups the two paths agree to 0.01 — checked voxel by voxel from the match lists of both."""
-    import parity_util
+    from oracle import parity_util
 
     for seed, shape in ((1, (40, 40, 40)), (3, (33, 36, 41))):
         v = synth.vol(*shape, seed=seed)
