@@ -396,7 +396,7 @@ int run_pipeline(b4d_handle *h, const Plan &pl, const float *d_zf, uint16_t *d_u
     B4D_TRY(h->basic.ensure((size_t)TV * sizeof(float)));
     B4D_TRY(h->s2.ensure((size_t)TV * sizeof(uint2)));
     {
-        const size_t ncell = (size_t)pl.nvol * ((pl.D + 3) / 4) * ((pl.H + 3) / 4) * ((pl.W + 3) / 4);
+        const size_t ncell = (size_t)pl.nvol * pl.D * g1.ty * g1.tx;  // per-plane window ranges of every tile
         const size_t ntile = (size_t)pl.nvol * std::max(g1.tz, g2.tz) * g1.ty * g1.tx;
         B4D_TRY(h->cells.ensure(ncell * sizeof(uint32_t)));
         B4D_TRY(h->tcls.ensure(ntile * sizeof(uint32_t)));
@@ -1352,7 +1352,7 @@ int b4d_match_stage1(b4d_handle *h, const uint16_t *in, const int64_t shape[3], 
     B4D_TRY(h->stats.ensure(4 * sizeof(unsigned long long)));
     CU_TRY(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
     B4D_TRY(h->s2.ensure((size_t)V * sizeof(uint2)));
-    B4D_TRY(h->cells.ensure((size_t)((pl.D + 3) / 4) * ((pl.H + 3) / 4) * ((pl.W + 3) / 4) * sizeof(uint32_t)));
+    B4D_TRY(h->cells.ensure((size_t)pl.D * g.ty * g.tx * sizeof(uint32_t)));
     B4D_TRY(h->tcls.ensure((size_t)g.tz * g.ty * g.tx * sizeof(uint32_t)));
     b4d_launch_block_energy(h->u16.as<uint16_t>(), h->s2.as<uint2>(), pl.D, pl.H, pl.W, 1, s);
     MatchParams mp;

@@ -46,7 +46,7 @@ struct MatchParams {
     B4dGeom g;
     const uint16_t *u;   // matching image [nvol][D][H][W]
     const uint2 *s21;    // per block origin (K0): .x = energy sum(v^2) mod 2^32, .y = sum(v)
-    uint32_t *cells;     // scratch: min | max << 16 per aligned 4^3 cell
+    uint32_t *cells;     // scratch: min | max << 16 per (plane, tile row, tile column): [nvol][D][ty][tx]
     uint32_t *tcls;      // scratch: class of every matcher tile (bit 16 byte tile + min in bits 0-15,
                          // bit 17 narrow), written by k_tile_class
     uint32_t tau;        // acceptance threshold (SSD <= tau)

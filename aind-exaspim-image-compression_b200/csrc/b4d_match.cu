@@ -31,8 +31,8 @@
 // 4x the multiply-accumulate rate), candidates are cut out of the row words with
 // PRMT on the ALU pipe.  SSD = S2'(a) + S2'(b) - 2*sum(a'b') with the centred
 // energies S2' = S2 - 2m*S1 + 64m^2 rebuilt from the block sums S1 that K0 writes
-// beside S2.  Tiles are classified beforehand (k_cell_minmax, k_tile_class: a
-// conservative range over 4^3 cells); k_match<.., BYTE=true> takes the byte
+// beside S2.  Tiles are classified beforehand (k_plane_ranges, k_tile_class: the
+// exact range of the staged neighbourhood); k_match<.., BYTE=true> takes the byte
 // tiles, k_match<.., false> the others, each exits at once on a foreign tile.
 //
 // Reference-byte path (general kernel).  When the 64 voxels of the REFERENCE block span
@@ -321,42 +321,66 @@ __global__ void __launch_bounds__(K0T_WARPS * 32) k_block_energy_tma(const __gri
 }
 
 // ------------------------------------------------- tile classification ------
-// cells[vol][cz][cy][cx] = min | max << 16 over the in-volume voxels of the aligned 4^3 cell
-__global__ void __launch_bounds__(256) k_cell_minmax(const uint16_t *__restrict__ u, uint32_t *__restrict__ cells,
-                                                     int D, int H, int W, int nvol, int cz0, int cz1) {
-    const int cd = (D + 3) >> 2, ch = (H + 3) >> 2, cw = (W + 3) >> 2, ncz = cz1 - cz0;  // cell planes [cz0, cz1)
-    const long long total = (long long)nvol * ncz * ch * cw;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
-        long long r = j;
-        const int cx = (int)(r % cw);
-        r /= cw;
-        const int cy = (int)(r % ch);
-        r /= ch;
-        const int cz = cz0 + (int)(r % ncz);
-        const int vol = (int)(r / ncz);
-        const long long i = (((long long)vol * cd + cz) * ch + cy) * cw + cx;
-        const uint16_t *v = u + (long long)vol * D * H * W;
-        uint32_t mn = 0xFFFFu, mx = 0u;
-        for (int z = cz * 4; z < min(cz * 4 + 4, D); ++z)
-            for (int y = cy * 4; y < min(cy * 4 + 4, H); ++y) {
-                const uint16_t *row = v + ((long long)z * H + y) * W;
-                for (int x = cx * 4; x < min(cx * 4 + 4, W); ++x) {
-                    const uint32_t q = __ldg(row + x);
-                    mn = min(mn, q);
-                    mx = max(mx, q);
-                }
+// EXACT range of every matcher tile's staged neighbourhood [b, b + E)^3 (clipped to the volume), separably:
+// k_plane_ranges: per voxel plane z and tile (ty, tx), min | max << 16 over the (y, x) window of that tile;
+// k_tile_class: per tile, the reduction of those over its z window.  (Round 1 took the range over the aligned 4^3
+// cells covering the neighbourhood — up to 5 voxels wider per axis, which pushed 12 % of the tiles of the benchmark
+// volume from the byte kernel to the general one.)
+// One CTA per (plane, ty): column min / max over the <= E rows of the window go to shared memory, segment by
+// segment of 64 tiles along x; one warp per tile then reduces its <= E columns.
+template <int NS>
+__global__ void __launch_bounds__(256) k_plane_ranges(const uint16_t *__restrict__ u, const B4dGeom g,
+                                                      uint32_t *__restrict__ rxy, int z0, int z1) {
+    using G = Geo<NS>;
+    constexpr int SEG_T = 64, SEG_W = 12 * (SEG_T - 1) + G::E;  // columns spanned by 64 consecutive tiles
+    __shared__ uint32_t s_col[SEG_W];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long t = blockIdx.x;
+    const int tyi = (int)(t % g.ty);
+    t /= g.ty;
+    const int z = z0 + (int)(t % (z1 - z0));
+    const int vol = (int)(t / (z1 - z0));
+    const int by = g.refy[tyi * 4] - G::R;
+    const int ya = max(by, 0), yb = min(by + G::E, g.H);
+    const uint16_t *pl = u + (long long)vol * g.vol_stride + (long long)z * g.H * g.W;
+    uint32_t *out = rxy + (((long long)vol * g.D + z) * g.ty + tyi) * g.tx;
+    for (int ts = 0; ts < g.tx; ts += SEG_T) {
+        const int te = min(ts + SEG_T, g.tx);
+        const int xs = g.refx[ts * 4] - G::R;                       // first column of the segment (may be < 0)
+        const int xe = min(g.refx[(te - 1) * 4] - G::R + G::E, g.W);  // one past its last column
+        __syncthreads();
+        for (int x = max(xs, 0) + threadIdx.x; x < xe; x += 256) {
+            uint32_t mn = 0xFFFFu, mx = 0u;
+            for (int y = ya; y < yb; ++y) {
+                const uint32_t q = __ldg(pl + (long long)y * g.W + x);
+                mn = min(mn, q);
+                mx = max(mx, q);
             }
-        cells[i] = mn | (mx << 16);
+            s_col[x - xs] = mn | (mx << 16);
+        }
+        __syncthreads();
+        for (int ti = ts + warp; ti < te; ti += 8) {
+            const int bx = g.refx[ti * 4] - G::R;
+            const int x = bx + lane;
+            uint32_t mn = 0xFFFFu, mx = 0u;
+            if (lane < G::E && x >= 0 && x < g.W) {
+                const uint32_t c = s_col[x - xs];
+                mn = c & 0xFFFFu;
+                mx = c >> 16;
+            }
+            mn = __reduce_min_sync(B4D_FULL, mn);
+            mx = __reduce_max_sync(B4D_FULL, mx);
+            if (lane == 0) out[ti] = mn | (mx << 16);
+        }
     }
 }
-// One warp per matcher tile: range over the cells that cover its staged neighbourhood
-// (a superset of it, hence conservative).  tcls[tile]: bit 16 = the range fits a byte (then
-// bits 0-15 hold the minimum), bit 17 = "narrow", range <= 8191 (every SSD < 2^32).
+// One warp per matcher tile.  tcls[tile]: bit 16 = the range fits a byte (then bits 0-15 hold the minimum),
+// bit 17 = "narrow", range <= 8191 (every SSD < 2^32).
 template <int NS>
-__global__ void __launch_bounds__(256) k_tile_class(const uint32_t *__restrict__ cells, const B4dGeom g,
+__global__ void __launch_bounds__(256) k_tile_class(const uint32_t *__restrict__ rxy, const B4dGeom g,
                                                     uint32_t *__restrict__ tcls, long long tile0, long long tile1) {
     using G = Geo<NS>;
+    static_assert(G::E <= 32, "one lane per plane of the z window");
     const int lane = threadIdx.x & 31;
     const long long tile = tile0 + (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= tile1) return;
@@ -367,18 +391,13 @@ __global__ void __launch_bounds__(256) k_tile_class(const uint32_t *__restrict__
     t /= g.ty;
     const int tz = (int)(t % g.tz);
     const int vol = (int)(t / g.tz);
-    const int cd = (g.D + 3) >> 2, ch = (g.H + 3) >> 2, cw = (g.W + 3) >> 2;
-    const int bz = g.refz[tz * 4] - G::R, by = g.refy[ty * 4] - G::R, bx = g.refx[tx * 4] - G::R;
-    const int z0 = max(bz, 0) >> 2, z1 = min(bz + G::E - 1, g.D - 1) >> 2;
-    const int y0 = max(by, 0) >> 2, y1 = min(by + G::E - 1, g.H - 1) >> 2;
-    const int x0 = max(bx, 0) >> 2, x1 = min(bx + G::E - 1, g.W - 1) >> 2;
-    const int nz = z1 - z0 + 1, ny = y1 - y0 + 1, nx = x1 - x0 + 1;
+    const int bz = g.refz[tz * 4] - G::R;
+    const int z = bz + lane;
     uint32_t mn = 0xFFFFu, mx = 0u;
-    for (int i = lane; i < nz * ny * nx; i += 32) {
-        const int x = i % nx, y = (i / nx) % ny, z = i / (nx * ny);
-        const uint32_t c = __ldg(cells + (((long long)vol * cd + z0 + z) * ch + y0 + y) * cw + x0 + x);
-        mn = min(mn, c & 0xFFFFu);
-        mx = max(mx, c >> 16);
+    if (lane < G::E && z >= 0 && z < g.D) {
+        const uint32_t c = __ldg(rxy + (((long long)vol * g.D + z) * g.ty + ty) * g.tx + tx);
+        mn = c & 0xFFFFu;
+        mx = c >> 16;
     }
     mn = __reduce_min_sync(B4D_FULL, mn);
     mx = __reduce_max_sync(B4D_FULL, mx);
@@ -987,12 +1006,10 @@ void launch_k(const MatchParams &pin, long long tile0, long long tile1, cudaStre
 // kernels); the whole volume in one go is cz = [0, cd), tiles = [0, all)
 template <int NS>
 void launch_ns(const MatchParams &p, int cz0, int cz1, long long tile0, long long tile1, cudaStream_t s) {
-    if (cz1 > cz0) {
-        const long long cells = (long long)p.g.nvol * (cz1 - cz0) * ((p.g.H + 3) / 4) * ((p.g.W + 3) / 4);
-        long long blocks = std::min<long long>((cells + 255) / 256, 148ll * 32);
-        k_cell_minmax<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, s>>>(p.u, p.cells, p.g.D, p.g.H, p.g.W,
-                                                                               p.g.nvol, cz0, cz1);
-    }
+    // cz0, cz1 count 4-plane layers (the callers' unit): voxel planes [4 cz0, min(4 cz1, D))
+    const int z0 = 4 * cz0, z1 = std::min(4 * cz1, p.g.D);
+    if (z1 > z0)
+        k_plane_ranges<NS><<<(unsigned)((long long)p.g.nvol * (z1 - z0) * p.g.ty), 256, 0, s>>>(p.u, p.g, p.cells, z0, z1);
     if (tile1 > tile0) {
         k_tile_class<NS><<<(unsigned)((tile1 - tile0 + 7) / 8), 256, 0, s>>>(p.cells, p.g, p.tcls, tile0, tile1);
         if (p.K > 16) launch_k<NS, true>(p, tile0, tile1, s);
