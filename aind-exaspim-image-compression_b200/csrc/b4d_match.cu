@@ -403,7 +403,11 @@ __global__ void __launch_bounds__(256) k_tile_class(const uint32_t *__restrict__
     mx = __reduce_max_sync(B4D_FULL, mx);
     if (lane == 0) {
         const uint32_t range = mx >= mn ? mx - mn : 0u;
-        tcls[tile] = range <= 255u ? ((3u << 16) | mn) : (range <= 8191u ? (2u << 16) : 0u);
+        // bit 18: the four reference columns of the tile exist and sit 3 voxels apart (no flush origin among them):
+        // the byte kernel then matches them as two pairs
+        const int ix0 = tx * 4;
+        const uint32_t reg = (ix0 + 3 < g.nrx && g.refx[ix0 + 3] - g.refx[ix0] == 9) ? (1u << 18) : 0u;
+        tcls[tile] = (range <= 255u ? ((3u << 16) | mn) : (range <= 8191u ? (2u << 16) : 0u)) | reg;
     }
 }
 
@@ -452,6 +456,42 @@ __device__ __forceinline__ void bcorr_row(const uint32_t *__restrict__ base, uin
                                    : (j & 3) == 2 ? __byte_perm(q[j >> 2], q[(j >> 2) + 1], 0x5432)
                                                   : __byte_perm(q[j >> 2], q[(j >> 2) + 1], 0x6543);
                 acc[j] = __dp4a(c, r, acc[j]);
+            }
+        }
+    }
+}
+
+// The same for TWO reference blocks that are neighbours in x (origins 3 voxels apart): their windows cover the same
+// (dz, dy) rows, so one set of row loads and realignments feeds both.  Candidate j of A sits at byte wx0 + j, candidate
+// j of B at byte wx0 + 3 + j: NS + 3 extracted words instead of 2 NS, NQ + 1 loads instead of 2 NWR.
+template <int NS>
+__device__ __forceinline__ void bcorr_row_pair(const uint32_t *__restrict__ base, uint32_t sel, const uint32_t (&refa)[16],
+                                               const uint32_t (&refb)[16], uint32_t (&acca)[NS], uint32_t (&accb)[NS]) {
+    using G = Geo<NS>;
+    constexpr int NQ = (NS + 9) / 4;  // aligned words that cover bytes [0, NS + 6)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) acca[j] = accb[j] = 0u;
+#pragma unroll
+    for (int z = 0; z < 4; ++z) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            uint32_t w[NQ + 1], q[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ + 1; ++i) w[i] = base[z * G::PSW + y * G::RSW + i];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) q[i] = __byte_perm(w[i], w[i + 1], sel);  // bytes wx0 + 4i ..
+            const uint32_t ra = refa[z * 4 + y], rb = refb[z * 4 + y];
+            uint32_t c[NS + 3];
+#pragma unroll
+            for (int pp = 0; pp < NS + 3; ++pp)
+                c[pp] = (pp & 3) == 0   ? q[pp >> 2]
+                        : (pp & 3) == 1 ? __byte_perm(q[pp >> 2], q[(pp >> 2) + 1], 0x4321)
+                        : (pp & 3) == 2 ? __byte_perm(q[pp >> 2], q[(pp >> 2) + 1], 0x5432)
+                                        : __byte_perm(q[pp >> 2], q[(pp >> 2) + 1], 0x6543);
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                acca[j] = __dp4a(c[j], ra, acca[j]);
+                accb[j] = __dp4a(c[j + 3], rb, accb[j]);
             }
         }
     }
@@ -528,7 +568,7 @@ __device__ __forceinline__ void r8corr_row_rolled(const uint32_t *__restrict__ b
 }
 
 template <int NS, bool K32, bool BYTE>
-__global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchParams p,
+__global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p,
                                                                     const __grid_constant__ CUtensorMap tmap) {
     using G = Geo<NS>;
     constexpr int R_ = G::R, E = G::E, EC = G::EC, KB = G::KB, UNITS = G::UNITS, ITERS = G::ITERS;
@@ -545,7 +585,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     unsigned char *s_tab = s_raw + (BYTE ? G::BWIN_BYTES : (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15));
     uint32_t *s_s2 = reinterpret_cast<uint32_t *>(s_tab);  // byte kernel: centred energies S2'
     uint2 *s_e = reinterpret_cast<uint2 *>(s_tab);         // general kernel: {S2 mod 2^32, S1 | S2hi << 24}
-    __shared__ uint32_t s_surv[WARPS][CAP];
+    __shared__ uint32_t s_surv[WARPS][BYTE ? 2 : 1][CAP];  // byte kernel: one list per reference of a pair
     __shared__ uint32_t s_refhi[BYTE ? 1 : WARPS][16];  // high byte plane of a wide-range reference block
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -733,7 +773,155 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
     const int K = p.K;
     const uint32_t tau = p.tau;
 
-    for (int rr = warp; rr < 64; rr += WARPS) {
+    // ---- byte tiles whose four reference columns are regular: two references per pass (neighbours in x).  Only the
+    // common case runs here (one pass, bound refined on the fly); a pair whose survivor list overflows is left to
+    // the one-reference loop below (redo mask).
+    uint32_t redo = 0u;
+    const bool pair_tile = BYTE && ((cls >> 18) & 1u) != 0u;
+    if constexpr (BYTE) {
+        if (pair_tile) {
+#pragma unroll 1
+            for (int pr = warp; pr < 32; pr += WARPS) {
+                const int iz = iz0 + (pr >> 3), iy = iy0 + ((pr >> 1) & 3), ixa = ix0 + 2 * (pr & 1);
+                if (iz >= g.nrz || iy >= g.nry) continue;  // warp-uniform
+                const int oz = g.refz[iz], oy = g.refy[iy], oxa = g.refx[ixa];
+                const int wz0 = oz - R_ - bz, wy0 = oy - R_ - by, wx0 = oxa - R_ - bx;
+                uint32_t refa[16], refb[16];
+                {
+                    const int rxa = wx0 + R_, rxb = rxa + 3;
+                    const uint32_t sa = 0x3210u + 0x1111u * (uint32_t)(rxa & 3), sb = 0x3210u + 0x1111u * (uint32_t)(rxb & 3);
+#pragma unroll
+                    for (int z = 0; z < 4; ++z)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            const uint32_t *row = s_bw + (wz0 + R_ + z) * G::PSW + (wy0 + R_ + y) * G::RSW;
+                            refa[z * 4 + y] = __byte_perm(row[rxa >> 2], row[(rxa >> 2) + 1], sa);
+                            refb[z * 4 + y] = __byte_perm(row[rxb >> 2], row[(rxb >> 2) + 1], sb);
+                        }
+                }
+                const uint32_t *e_ref = s_s2 + (wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_);
+                const uint32_t s2a = e_ref[0], s2b = e_ref[3];
+                const uint32_t bsel = 0x3210u + 0x1111u * (uint32_t)(wx0 & 3);
+                const int jloa = max(0, R_ - oxa), jhia = min(NS - 1, g.W - 4 - oxa + R_);
+                const int jlob = max(0, R_ - oxa - 3), jhib = min(NS - 1, g.W - 4 - oxa - 3 + R_);
+                const long long rlina = (long long)vol * g.refs_per_vol + ((long long)iz * g.nry + iy) * g.nrx + ixa;
+                uint32_t la1 = B4D_INVALID_KEY, la2 = B4D_INVALID_KEY, lb1 = B4D_INVALID_KEY, lb2 = B4D_INVALID_KEY;
+                uint32_t Ba = B4D_INVALID_KEY - 1u, Bb = B4D_INVALID_KEY - 1u;
+                int na = 0, nb = 0;  // survivor counts (warp-uniform)
+                __syncwarp();
+#pragma unroll 1
+                for (int it = 0; it < ITERS; ++it) {
+                    const int unit = (int)((G::ORDER >> (4 * it)) & 15ull) * 32 + lane;
+                    const int dz = unit / NS, dy = unit - dz * NS;
+                    const int cz = oz - R_ + dz, cy = oy - R_ + dy;
+                    const bool uvalid = unit < UNITS && cz >= 0 && cz <= g.D - 4 && cy >= 0 && cy <= g.H - 4;
+                    if (!__any_sync(B4D_FULL, uvalid)) continue;
+                    uint32_t ka[NS], kb[NS];
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) ka[j] = kb[j] = B4D_INVALID_KEY;
+                    if (uvalid) {
+                        uint32_t acca[NS], accb[NS];
+                        bcorr_row_pair<NS>(s_bw + (wz0 + dz) * G::PSW + (wy0 + dy) * G::RSW + (wx0 >> 2), bsel, refa, refb, acca,
+                                           accb);
+                        const uint32_t *e = s_s2 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
+#pragma unroll
+                        for (int j = 0; j < NS; ++j) {
+                            const uint32_t idx = (uint32_t)(unit * NS + j);
+                            const uint32_t da = (e[j] + s2a) - 2u * acca[j];
+                            const bool oka = da <= tau && j >= jloa && j <= jhia;
+                            ka[j] = oka ? ((da << KB) | idx) : B4D_INVALID_KEY;
+                            const uint32_t db = (e[j + 3] + s2b) - 2u * accb[j];
+                            const bool okb = db <= tau && j >= jlob && j <= jhib;
+                            kb[j] = okb ? ((db << KB) | idx) : B4D_INVALID_KEY;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        if (K32) {
+                            la2 = min(la2, max(la1, ka[j]));
+                            lb2 = min(lb2, max(lb1, kb[j]));
+                        }
+                        la1 = min(la1, ka[j]);
+                        lb1 = min(lb1, kb[j]);
+                    }
+                    Ba = min(Ba, kth_smallest32(K32 ? la2 : la1, K32 ? 15 : K - 1, lane));
+                    Bb = min(Bb, kth_smallest32(K32 ? lb2 : lb1, K32 ? 15 : K - 1, lane));
+                    const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        const bool ta = ka[j] <= Ba, tb = kb[j] <= Bb;
+                        const unsigned ma = __ballot_sync(B4D_FULL, ta), mb = __ballot_sync(B4D_FULL, tb);
+                        const int pa = na + __popc(ma & below), pb = nb + __popc(mb & below);
+                        if (ta && pa < CAP) s_surv[warp][0][pa] = ka[j];
+                        if (tb && pb < CAP) s_surv[warp][1][pb] = kb[j];
+                        na += __popc(ma);
+                        nb += __popc(mb);
+                    }
+                }
+                __syncwarp();
+                if (na > CAP || nb > CAP) {  // rare: both references go through the one-reference loop
+                    redo |= 1u << pr;
+                    continue;
+                }
+#pragma unroll 1
+                for (int sref = 0; sref < 2; ++sref) {
+                    uint32_t *lst = s_surv[warp][sref];
+                    const int n = sref ? nb : na;
+                    const uint32_t B = sref ? Bb : Ba;
+                    const long long rlin = rlina + sref;
+                    // compact the survivors that are <= the final bound, then rank-sort them (as below)
+                    uint32_t mine[CAP / 32];
+#pragma unroll
+                    for (int s = 0; s < CAP / 32; ++s) {
+                        const int e = s * 32 + lane;
+                        uint32_t k = (e < n) ? lst[e] : B4D_INVALID_KEY;
+                        mine[s] = (k > B) ? B4D_INVALID_KEY : k;
+                    }
+                    __syncwarp();
+                    int nf = 0;
+#pragma unroll
+                    for (int s = 0; s < CAP / 32; ++s) {
+                        if (s * 32 >= n) break;  // warp-uniform
+                        const bool keep = mine[s] != B4D_INVALID_KEY;
+                        const unsigned bal = __ballot_sync(B4D_FULL, keep);
+                        if (keep) lst[nf + __popc(bal & ((1u << lane) - 1u))] = mine[s];
+                        nf += __popc(bal);
+                    }
+                    __syncwarp();
+                    const int ns = min(nf, K);
+                    const int kp = ns > 0 ? (1 << (31 - __clz(ns))) : 0;
+                    for (int s0 = 0; s0 < nf; s0 += 64) {
+                        const int e0 = s0 + lane, e1 = s0 + 32 + lane;
+                        const uint32_t k0 = e0 < nf ? lst[e0] : B4D_INVALID_KEY;
+                        const uint32_t k1 = e1 < nf ? lst[e1] : B4D_INVALID_KEY;
+                        int r0 = 0, r1 = 0;
+                        for (int e = 0; e < nf; ++e) {
+                            const uint32_t o = lst[e];
+                            r0 += (o < k0) ? 1 : 0;
+                            r1 += (o < k1) ? 1 : 0;
+                        }
+                        if (k0 != B4D_INVALID_KEY && r0 < kp) {
+                            p.widx[rlin * K + r0] = (uint16_t)(k0 & ((1u << KB) - 1u));
+                            if (p.ssd_out) p.ssd_out[rlin * K + r0] = k0 >> KB;
+                        }
+                        if (k1 != B4D_INVALID_KEY && r1 < kp) {
+                            p.widx[rlin * K + r1] = (uint16_t)(k1 & ((1u << KB) - 1u));
+                            if (p.ssd_out) p.ssd_out[rlin * K + r1] = k1 >> KB;
+                        }
+                    }
+                    if (lane == 0) p.cnt[rlin] = (uint8_t)kp;
+                    __syncwarp();
+                }
+            }
+            if (redo == 0u) return;  // warp-uniform: nothing left for this warp
+        }
+    }
+
+    for (int q8 = 0; q8 < 64 / WARPS; ++q8) {
+        // reference index of this warp's q8-th turn: plain tiles, rr = warp + 8 q8; pair tiles, the two references
+        // of the warp's pairs that asked for a second go
+        const int rr = pair_tile ? 2 * (warp + WARPS * (q8 >> 1)) + (q8 & 1) : warp + WARPS * q8;
+        if (pair_tile && ((redo >> (rr >> 1)) & 1u) == 0u) continue;
         const int iz = iz0 + (rr >> 4), iy = iy0 + ((rr >> 2) & 3), ix = ix0 + (rr & 3);
         if (iz >= g.nrz || iy >= g.nry || ix >= g.nrx) continue;  // warp-uniform
         const int oz = g.refz[iz], oy = g.refy[iy], ox = g.refx[ix];
@@ -883,7 +1071,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                         const bool take = key[j] <= B;
                         const unsigned m = __ballot_sync(B4D_FULL, take);
                         const int pos = nsurv + __popc(m & ((1u << lane) - 1u));
-                        if (take && pos < CAP) s_surv[warp][pos] = key[j];
+                        if (take && pos < CAP) s_surv[warp][0][pos] = key[j];
                         nsurv += __popc(m);
                     }
                 } else {
@@ -903,7 +1091,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
 #pragma unroll
                     for (int s = 0; s < CAP / 32; ++s) {
                         const int e = s * 32 + lane;
-                        uint32_t k = (e < n) ? s_surv[warp][e] : B4D_INVALID_KEY;
+                        uint32_t k = (e < n) ? s_surv[warp][0][e] : B4D_INVALID_KEY;
                         mine[s] = (k > B) ? B4D_INVALID_KEY : k;
                     }
                     __syncwarp();
@@ -913,7 +1101,7 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                         if (s * 32 >= n) break;  // warp-uniform
                         const bool keep = mine[s] != B4D_INVALID_KEY;
                         const unsigned bal = __ballot_sync(B4D_FULL, keep);
-                        if (keep) s_surv[warp][nf + __popc(bal & ((1u << lane) - 1u))] = mine[s];
+                        if (keep) s_surv[warp][0][nf + __popc(bal & ((1u << lane) - 1u))] = mine[s];
                         nf += __popc(bal);
                     }
                     __syncwarp();
@@ -921,11 +1109,11 @@ __global__ void __launch_bounds__(WARPS * 32, BYTE ? 3 : 2) k_match(const MatchP
                     const int kp = ns > 0 ? (1 << (31 - __clz(ns))) : 0;
                     for (int s0 = 0; s0 < nf; s0 += 64) {
                         const int e0 = s0 + lane, e1 = s0 + 32 + lane;
-                        const uint32_t k0 = e0 < nf ? s_surv[warp][e0] : B4D_INVALID_KEY;
-                        const uint32_t k1 = e1 < nf ? s_surv[warp][e1] : B4D_INVALID_KEY;
+                        const uint32_t k0 = e0 < nf ? s_surv[warp][0][e0] : B4D_INVALID_KEY;
+                        const uint32_t k1 = e1 < nf ? s_surv[warp][0][e1] : B4D_INVALID_KEY;
                         int r0 = 0, r1 = 0;
                         for (int e = 0; e < nf; ++e) {
-                            const uint32_t o = s_surv[warp][e];
+                            const uint32_t o = s_surv[warp][0][e];
                             r0 += (o < k0) ? 1 : 0;
                             r1 += (o < k1) ? 1 : 0;
                         }
