@@ -958,16 +958,31 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p,
                 const uint2 er = s_e[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
                 s2ref = er.x;
                 s1ref = er.y;
+                // byte planes of r - r_min, one word per block row: every lane already holds two voxels (rows
+                // lane >> 2 and 8 + (lane >> 2)); the four bytes of a row are packed by two shuffles, lane 4 r then holds
+                // the word of row r and hands it to everybody
+                const uint32_t da = va - rmin, db = vb - rmin;
+                uint32_t la = da & 0xFFu, lb = db & 0xFFu;
+                la |= __shfl_down_sync(B4D_FULL, la, 1) << 8;
+                lb |= __shfl_down_sync(B4D_FULL, lb, 1) << 8;
+                la |= __shfl_down_sync(B4D_FULL, la, 2) << 16;
+                lb |= __shfl_down_sync(B4D_FULL, lb, 2) << 16;
 #pragma unroll
-                for (int z = 0; z < 4; ++z)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const uint16_t *rp = refp + z * G::SZ + y * G::SY;
-                        const uint32_t r0 = rp[0] - rmin, r1 = rp[1] - rmin, r2 = rp[2] - rmin, r3 = rp[3] - rmin;
-                        refw[z * 4 + y] = (r0 & 0xFFu) | ((r1 & 0xFFu) << 8) | ((r2 & 0xFFu) << 16) | (r3 << 24);
-                        if (npass == 2 && lane == 0)
-                            s_refhi[warp][z * 4 + y] = (r0 >> 8) | ((r1 >> 8) << 8) | ((r2 >> 8) << 16) | ((r3 >> 8) << 24);
+                for (int r8 = 0; r8 < 8; ++r8) {
+                    refw[r8] = __shfl_sync(B4D_FULL, la, 4 * r8);
+                    refw[8 + r8] = __shfl_sync(B4D_FULL, lb, 4 * r8);
+                }
+                if (npass == 2) {  // warp-uniform
+                    uint32_t ha = da >> 8, hb = db >> 8;
+                    ha |= __shfl_down_sync(B4D_FULL, ha, 1) << 8;
+                    hb |= __shfl_down_sync(B4D_FULL, hb, 1) << 8;
+                    ha |= __shfl_down_sync(B4D_FULL, ha, 2) << 16;
+                    hb |= __shfl_down_sync(B4D_FULL, hb, 2) << 16;
+                    if ((lane & 3) == 0) {
+                        s_refhi[warp][lane >> 2] = ha;
+                        s_refhi[warp][8 + (lane >> 2)] = hb;
                     }
+                }
                 __syncwarp();
             }
         }
