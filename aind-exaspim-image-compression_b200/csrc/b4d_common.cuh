@@ -57,6 +57,7 @@ struct MatchParams {
     long long tile0;     // first tile of this launch (set by the launcher)
     unsigned long long *stats;  // optional: [0] fallback refs, [1] wide tiles
     int use_tma;         // set by the launcher: the byte kernel stages its window with one TMA box load
+    int use_tma_tab;      // general kernel: the {S2, S1} table arrives as one TMA box (W even)
 };
 
 struct FilterParams {

@@ -81,7 +81,13 @@ struct Geo {
     static constexpr int AC0 = EC * BC;
     static constexpr int AC = AC0 + (((NS * BC) % 32 - AC0 % 32) + 32) % 32;
     static constexpr int S2_WORDS = EC * AC;
-    static constexpr size_t SMEM = (((size_t)WIN_ELEMS * 2 + 15) & ~(size_t)15) + (size_t)S2_WORDS * 8;  // S2 + S1
+    // general kernel: the {S2, S1} table is DENSE ([EC][EC][TBW] entries of 8 bytes), the layout a TMA box load
+    // produces; TBW = EC + 2 leaves room for the 16-byte alignment of the box origin (one entry)
+    static constexpr int TBW = EC + 2;
+    static constexpr int TAC = EC * TBW;
+    static constexpr uint32_t TAB_BOX_BYTES = (uint32_t)TBW * EC * EC * 8;
+    static constexpr size_t WIN_BYTES = (((size_t)WIN_ELEMS * 2 + 127) & ~(size_t)127);
+    static constexpr size_t SMEM = WIN_BYTES + (size_t)TAB_BOX_BYTES;
     // byte window: row stride RSW words (odd), plane stride PSW = NS*RSW (mod 32): the 32
     // (dz, dy) rows a warp reads at once fall in 32 distinct banks
     static constexpr int RW = (E + 3) / 4;     // words of a row that hold data
@@ -568,8 +574,8 @@ __device__ __forceinline__ void r8corr_row_rolled(const uint32_t *__restrict__ b
 }
 
 template <int NS, bool K32, bool BYTE>
-__global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p,
-                                                                    const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, const __grid_constant__ CUtensorMap tmap,
+                                                        const __grid_constant__ CUtensorMap emap) {
     using G = Geo<NS>;
     constexpr int R_ = G::R, E = G::E, EC = G::EC, KB = G::KB, UNITS = G::UNITS, ITERS = G::ITERS;
 
@@ -582,7 +588,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p,
     extern __shared__ __align__(128) unsigned char s_raw[];
     uint16_t *s_win = reinterpret_cast<uint16_t *>(s_raw);
     uint32_t *s_bw = reinterpret_cast<uint32_t *>(s_raw);  // byte path: packed bytes
-    unsigned char *s_tab = s_raw + (BYTE ? G::BWIN_BYTES : (((size_t)G::WIN_ELEMS * 2 + 15) & ~(size_t)15));
+    unsigned char *s_tab = s_raw + (BYTE ? G::BWIN_BYTES : G::WIN_BYTES);
     uint32_t *s_s2 = reinterpret_cast<uint32_t *>(s_tab);  // byte kernel: centred energies S2'
     uint2 *s_e = reinterpret_cast<uint2 *>(s_tab);         // general kernel: {S2 mod 2^32, S1 | S2hi << 24}
     __shared__ uint32_t s_surv[WARPS][BYTE ? 2 : 1][CAP];  // byte kernel: one list per reference of a pair
@@ -605,6 +611,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p,
     // General kernel: the staged window starts at an EVEN global x when rows are 4-byte aligned
     // (W even), so that it can be filled by 4-byte cp.async; xo = 0 or 1 shifts window columns.
     const int xo = (BYTE || (g.W & 1)) ? 0 : (bx & 1);
+    const int xt = bx & 1;  // general kernel: table column of origin bx (the box starts at the even column at or below it)
 
     if (BYTE) {
         if (p.use_tma) {
@@ -756,15 +763,29 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p,
                 s_win[z * G::SZ + y * G::SY + x] = (uint16_t)v;
             }
         }
-        for (int id = threadIdx.x; id < EC * EC * EC; id += WARPS * 32) {
-            const int x = id % EC, y = (id / EC) % EC, z = id / (EC * EC);
-            const int gz = bz + z, gy = by + y, gx = bx + x;
-            const bool in = (unsigned)gz <= (unsigned)(g.D - 4) && (unsigned)gy <= (unsigned)(g.H - 4) &&
-                            (unsigned)gx <= (unsigned)(g.W - 4);
-            const uint2 *src = in ? s21v + ((long long)gz * g.H + gy) * g.W + gx : s21v;
-            cp_async8_zfill(tab_base + 8u * (uint32_t)(z * G::AC + y * G::BC + x), src, in ? 8u : 0u);
+        if (p.use_tma_tab) {
+            // the whole table as ONE box load (the map only spans valid block origins, everything else arrives as zero)
+            __shared__ __align__(8) unsigned long long s_mbar_e;
+            const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar_e);
+            if (threadIdx.x == 0) {
+                mbar_init(mbar, 1);
+                mbar_expect_tx(mbar, G::TAB_BOX_BYTES);
+                tma_load_4d(tab_base, &emap, mbar, bx - xt, by, bz, vol);
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();  // the barrier is initialised for everybody
+            mbar_wait(mbar, 0);
+        } else {
+            for (int id = threadIdx.x; id < EC * EC * EC; id += WARPS * 32) {
+                const int x = id % EC, y = (id / EC) % EC, z = id / (EC * EC);
+                const int gz = bz + z, gy = by + y, gx = bx + x;
+                const bool in = (unsigned)gz <= (unsigned)(g.D - 4) && (unsigned)gy <= (unsigned)(g.H - 4) &&
+                                (unsigned)gx <= (unsigned)(g.W - 4);
+                const uint2 *src = in ? s21v + ((long long)gz * g.H + gy) * g.W + gx : s21v;
+                cp_async8_zfill(tab_base + 8u * (uint32_t)(z * G::TAC + y * G::TBW + x + xt), src, in ? 8u : 0u);
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
     if (!narrow && threadIdx.x == 0 && p.stats) atomicAdd(&p.stats[1], 1ull);
@@ -955,7 +976,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p,
                 rmin = __reduce_min_sync(B4D_FULL, min(va, vb));
                 const uint32_t rmax = __reduce_max_sync(B4D_FULL, max(va, vb));
                 npass = (rmax - rmin <= 255u) ? 1 : 2;  // r - r_min < 2^16: low and high byte planes
-                const uint2 er = s_e[(wz0 + R_) * G::AC + (wy0 + R_) * G::BC + (wx0 + R_)];
+                const uint2 er = s_e[(wz0 + R_) * G::TAC + (wy0 + R_) * G::TBW + (wx0 + R_) + xt];
                 s2ref = er.x;
                 s1ref = er.y;
                 // byte planes of r - r_min, one word per block row: every lane already holds two voxels (rows
@@ -1042,7 +1063,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p,
 #pragma unroll
                             for (int j = 0; j < NS; ++j) acch[j] = 0u;
                         }
-                        const uint2 *e = s_e + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
+                        const uint2 *e = s_e + (wz0 + dz) * G::TAC + (wy0 + dy) * G::TBW + wx0 + xt;
                         if (narrow) {
                             // everything modulo 2^32: exact because the true SSD < 2^32 on a narrow tile
                             const uint32_t rm2 = 2u * rmin;
@@ -1198,12 +1219,27 @@ void launch_k(const MatchParams &pin, long long tile0, long long tile1, cudaStre
     p.tile0 = tile0;
     CUtensorMap tmap;
     p.use_tma = make_window_map<NS>(p, &tmap) ? 1 : 0;
+    CUtensorMap emap;
+    std::memset(&emap, 0, sizeof(emap));
+    p.use_tma_tab = 0;
+    if ((p.g.W & 1) == 0 && !getenv("B4D_NO_TMA") && p.g.D >= 4 && p.g.H >= 4 && p.g.W >= 4) {
+        EncodeTiledFn fn = encode_fn();
+        // only valid block origins are inside the tensor: extents (W - 3, H - 3, D - 3), true pitches
+        const cuuint64_t dims[4] = {(cuuint64_t)(p.g.W - 3), (cuuint64_t)(p.g.H - 3), (cuuint64_t)(p.g.D - 3), (cuuint64_t)p.g.nvol};
+        const cuuint64_t strides[3] = {(cuuint64_t)p.g.W * 8, (cuuint64_t)p.g.W * p.g.H * 8, (cuuint64_t)p.g.vol_stride * 8};
+        const cuuint32_t box[4] = {(cuuint32_t)G::TBW, (cuuint32_t)G::EC, (cuuint32_t)G::EC, 1u};
+        const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+        if (fn && fn(&emap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<uint2 *>(p.s21), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            p.use_tma_tab = 1;
+    }
     const unsigned tiles = (unsigned)(tile1 - tile0);
     // byte tiles first (cheap), then everything else; each kernel exits at once on a foreign tile
     cudaFuncSetAttribute(k_match<NS, K32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_B);
-    k_match<NS, K32, true><<<tiles, WARPS * 32, G::SMEM_B, s>>>(p, tmap);
+    k_match<NS, K32, true><<<tiles, WARPS * 32, G::SMEM_B, s>>>(p, tmap, emap);
     cudaFuncSetAttribute(k_match<NS, K32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-    k_match<NS, K32, false><<<tiles, WARPS * 32, G::SMEM, s>>>(p, tmap);
+    k_match<NS, K32, false><<<tiles, WARPS * 32, G::SMEM, s>>>(p, tmap, emap);
 }
 // cell planes [cz0, cz1) (min/max table) and tiles [tile0, tile1) (classification + both matcher
 // kernels); the whole volume in one go is cz = [0, cd), tiles = [0, all)
