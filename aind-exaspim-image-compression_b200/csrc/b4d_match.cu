@@ -1,4 +1,4 @@
-// b4d_match.cu — K0 (block energies) and K1 / K4 (exact-integer block matching)
+// b4d_match.cu — K0 (block energies), tile classification and K1 / K4 (exact-integer block matching)
 // on a uint16 image.
 //
 // Contract: for every reference block
@@ -7,40 +7,25 @@
 // accept SSD <= tau, order by (SSD, window index), keep the first
 // K' = 2^floor(log2(min(K, accepted))).
 //
-// Arithmetic.  SSD(a, b) = S2(a) + S2(b) - 2 * sum(a*b), with S2 the block energy
-// sum(v^2).  Everything is evaluated modulo 2^32: K0 writes S2 mod 2^32 for every
-// block origin once per stage, the matcher accumulates the cross term with one
-// IMAD per voxel pair (no subtract), and the modular result equals the true SSD
-// whenever the true SSD < 2^32 — guaranteed per tile by a range check made while
-// staging (64 * range^2 < 2^32).  Tiles that fail the check (bright structures
-// more than 8191 counts above their surroundings) take a direct 64-bit path.
+// Arithmetic.  SSD(a, b) = S2(a) + S2(b) - 2 * sum(a*b), with S2 the block energy sum(v^2), all exact.
+// K0 writes {S2 mod 2^32, S1 | (S2 >> 32) << 24} for every block origin once per stage (S1 = block sum).
+// The cross term never uses one multiply per voxel pair:
+//   * byte tiles (the staged neighbourhood spans <= 255 counts): v - tile_min fits a byte, four products per
+//     IDP.4A (dp4a), energies of the centred bytes rebuilt in shared memory; k_match<.., BYTE = true>;
+//   * all other tiles: the REFERENCE block is split into byte planes of r - r_min (one plane when the block spans
+//     <= 255 counts, else two), candidates stay 16-bit, two products per IDP.2A (dp2a);
+//     sum(a r) = sum(a rl) + 256 sum(a rh) + r_min S1(a).  On a narrow tile (range <= 8191, every SSD < 2^32) the
+//     combination runs modulo 2^32, on a wide tile exactly in 64 bits; k_match<.., BYTE = false>.
+// Tiles are classified beforehand by the exact range of their neighbourhood (k_plane_ranges, k_tile_class); each
+// instantiation exits at once on a tile of the other class.
 //
-// Mapping.  One CTA per 4x4x4 tile of reference blocks; the (Ns+12)^3 voxel
-// neighbourhood and the (Ns+9)^3 block energies are staged once in shared memory
-// and serve all 64 reference blocks.  One warp per reference block.  A lane owns
-// one (dz, dy) row of the window at a time and slides along dx with Ns
-// accumulators in registers: each shared-memory row of Ns+3 values feeds 4*Ns
-// IMADs, the reference block lives in 64 registers.  Shared-memory strides are
-// padded so that the 32 rows a warp reads at once fall in 32 distinct banks
-// (bank = B * (Ns*dz + dy) mod 32 with B odd).
-//
-// Byte path.  A tile whose staged neighbourhood spans at most 255 counts (pure
-// background: noise only, or the smooth basic estimate of stage 2) is matched on
-// bytes: v - tile_min fits 8 bits, four voxel products go through one IDP.4A
-// (dp4a runs at the IMAD issue rate on sm_100a, measured by tools/mb_pipes.cu:
-// 4x the multiply-accumulate rate), candidates are cut out of the row words with
-// PRMT on the ALU pipe.  SSD = S2'(a) + S2'(b) - 2*sum(a'b') with the centred
-// energies S2' = S2 - 2m*S1 + 64m^2 rebuilt from the block sums S1 that K0 writes
-// beside S2.  Tiles are classified beforehand (k_plane_ranges, k_tile_class: the
-// exact range of the staged neighbourhood); k_match<.., BYTE=true> takes the byte
-// tiles, k_match<.., false> the others, each exits at once on a foreign tile.
-//
-// Reference-byte path (general kernel).  When the 64 voxels of the REFERENCE block span
-// at most 255 counts (almost every block that is not on a bright edge), r' = r - r_min
-// fits a byte while the candidates stay 16-bit: sum(a*r) = sum(a*r') + r_min*S1(a), and
-// sum(a*r') runs through IDP.2A (u16 x u8, two products per instruction at the IMAD issue
-// rate) on the pair words of the uint16 window.  Other references of a narrow tile keep
-// the IMAD path; wide tiles the 64-bit path.
+// Mapping.  One CTA per 4x4x4 tile of reference blocks; the (Ns+12)^3 voxel neighbourhood and the (Ns+9)^3 table
+// entries are staged once in shared memory (TMA box loads: the uint16 window of byte tiles, the 8-byte table of the
+// other tiles; cp.async for the rest and for volumes whose row pitch breaks the 16-byte rule) and serve all 64
+// reference blocks.  One warp per reference block — in the byte kernel per PAIR of blocks that are neighbours in x,
+// which search the same rows.  A lane owns one (dz, dy) row of the window at a time and slides along dx with Ns
+// accumulators (per reference) in registers.  Shared-memory strides are padded so that the 32 rows a warp reads at
+// once fall in 32 distinct banks (bank = B * (Ns*dz + dy) mod 32 with B odd).
 //
 // Selection is exact and deterministic: key = SSD << KB | window index (unique),
 // rejected candidates get 0xFFFFFFFF.  Rows are visited centre-out so the good
@@ -48,7 +33,7 @@
 // gives, through one 32-lane bitonic sort, an upper bound B with at least K keys
 // <= B; only keys <= B are appended to a small per-warp survivor list, which is
 // rank-sorted at the end.  If the list overflows (adversarial key order) the warp
-// falls back to K rounds of "smallest key greater than the previous one".
+// retries once with the final bound, then falls back to K rounds of "smallest key greater than the previous one".
 #include <algorithm>
 #include <cstring>
 #include <type_traits>

@@ -61,7 +61,7 @@ typedef struct b4d_profile {
     int32_t k_wie;          /* max group size, stage 2 (power of two, <= 32)           */
     int32_t stages;         /* 1 = hard-threshold stage only, 2 = + Wiener stage       */
     int32_t deterministic;  /* kept for ABI stability: aggregation is ALWAYS order-      *
-                             * independent 2^32 fixed point (bit-reproducible)          */
+                             * independent fixed point (bit-reproducible): dead field    */
     int32_t reserved0;
     float tau_ht;           /* match acceptance: SSD <= floor(tau*sigma^2*L^3)         */
     float tau_wie;
