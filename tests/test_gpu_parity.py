@@ -467,6 +467,29 @@ def test_exchange_variant_slabs_equal_whole(b4d_mod):
         assert np.array_equal(np.concatenate(parts, 0), whole)
 
 
+def test_tma_and_fallback_staging_give_the_same_bytes(dn, b4d_mod):
+    """Every TMA-fed kernel (K0, byte-matcher window, general-matcher table, normalise) has a cp.async / plain-load
+    twin for volumes whose row pitch breaks the 16-byte rule; B4D_NO_TMA forces the twins on an aligned volume."""
+    import os
+
+    from b4d import synth
+
+    vol = synth.vol(48, 40, 64, seed=11)
+    vol[10:30, 8:30, 16:50] += 3000  # a bright structure: wide and general tiles next to byte tiles
+    y = dn.denoise(vol, 24.0)
+    q = dn.denoise_quantized(vol, 24.0, offset_sub=30.0, step=2.0)
+    idx, ssd, cnt = dn.match_stage1(vol, 24.0)
+    os.environ["B4D_NO_TMA"] = "1"
+    try:
+        y2 = dn.denoise(vol, 24.0)
+        q2 = dn.denoise_quantized(vol, 24.0, offset_sub=30.0, step=2.0)
+        idx2, ssd2, cnt2 = dn.match_stage1(vol, 24.0)
+    finally:
+        del os.environ["B4D_NO_TMA"]
+    assert np.array_equal(y, y2) and np.array_equal(q, q2)
+    assert np.array_equal(idx, idx2) and np.array_equal(ssd, ssd2) and np.array_equal(cnt, cnt2)
+
+
 def test_overlapped_exchange_form_equals_whole(b4d_mod):
     """The device form of the exchange variant: after stage 1 every rank launches the part of the stage-2 front end
     that needs owned planes only (b4d_slab_stage2_begin, no wait) while the neighbours' planes are written straight
