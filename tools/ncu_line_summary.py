@@ -16,7 +16,7 @@ def flush():
     tot = sum(v[0] for v in agg.values()) or 1
     toti = sum(v[1] for v in agg.values()) or 1
     print("==", kern, "samples", tot, "warp-instr", toti)
-    for ln, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    for ln, v in sorted(agg.items(), key=lambda kv: -kv[1][1 if len(sys.argv) > 2 and sys.argv[2] == "ins" else 0])[:top]:
         st = ", ".join("%s %.0f%%" % (k, 100.0 * c / max(v[0], 1)) for k, c in v[2].most_common(3))
         print("  line %4s  smp %5.1f%%  ins %5.1f%%  %-70s %s" % (ln, 100.0 * v[0] / tot, 100.0 * v[1] / toti, text.get(ln, "")[:70], st))
 
