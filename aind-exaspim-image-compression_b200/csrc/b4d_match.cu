@@ -833,6 +833,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                 const uint32_t bsel = 0x3210u + 0x1111u * (uint32_t)(wx0 & 3);
                 const int jloa = max(0, R_ - oxa), jhia = min(NS - 1, g.W - 4 - oxa + R_);
                 const int jlob = max(0, R_ - oxa - 3), jhib = min(NS - 1, g.W - 4 - oxa - 3 + R_);
+                const bool xfull = jloa == 0 && jlob == 0 && jhia == NS - 1 && jhib == NS - 1;
                 const long long rlina = (long long)vol * g.refs_per_vol + ((long long)iz * g.nry + iy) * g.nrx + ixa;
                 uint32_t la1 = B4D_INVALID_KEY, la2 = B4D_INVALID_KEY, lb1 = B4D_INVALID_KEY, lb2 = B4D_INVALID_KEY;
                 uint32_t Ba = B4D_INVALID_KEY - 1u, Bb = B4D_INVALID_KEY - 1u;
@@ -853,15 +854,26 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                         bcorr_row_pair<NS>(s_bw + (wz0 + dz) * G::PSW + (wy0 + dy) * G::RSW + (wx0 >> 2), bsel, refa, refb, acca,
                                            accb);
                         const uint32_t *e = s_s2 + (wz0 + dz) * G::AC + (wy0 + dy) * G::BC + wx0;
+                        if (xfull) {  // warp-uniform: every dx of both windows is inside the volume (all but the edge tiles)
 #pragma unroll
-                        for (int j = 0; j < NS; ++j) {
-                            const uint32_t idx = (uint32_t)(unit * NS + j);
-                            const uint32_t da = (e[j] + s2a) - 2u * acca[j];
-                            const bool oka = da <= tau && j >= jloa && j <= jhia;
-                            ka[j] = oka ? ((da << KB) | idx) : B4D_INVALID_KEY;
-                            const uint32_t db = (e[j + 3] + s2b) - 2u * accb[j];
-                            const bool okb = db <= tau && j >= jlob && j <= jhib;
-                            kb[j] = okb ? ((db << KB) | idx) : B4D_INVALID_KEY;
+                            for (int j = 0; j < NS; ++j) {
+                                const uint32_t idx = (uint32_t)(unit * NS + j);
+                                const uint32_t da = (e[j] + s2a) - 2u * acca[j];
+                                ka[j] = da <= tau ? ((da << KB) | idx) : B4D_INVALID_KEY;
+                                const uint32_t db = (e[j + 3] + s2b) - 2u * accb[j];
+                                kb[j] = db <= tau ? ((db << KB) | idx) : B4D_INVALID_KEY;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < NS; ++j) {
+                                const uint32_t idx = (uint32_t)(unit * NS + j);
+                                const uint32_t da = (e[j] + s2a) - 2u * acca[j];
+                                const bool oka = da <= tau && j >= jloa && j <= jhia;
+                                ka[j] = oka ? ((da << KB) | idx) : B4D_INVALID_KEY;
+                                const uint32_t db = (e[j + 3] + s2b) - 2u * accb[j];
+                                const bool okb = db <= tau && j >= jlob && j <= jhib;
+                                kb[j] = okb ? ((db << KB) | idx) : B4D_INVALID_KEY;
+                            }
                         }
                     }
 #pragma unroll
@@ -1017,6 +1029,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
         }
         // valid dx range of candidates: cx = ox - R_ + j in [0, W-4]
         const int jlo = max(0, R_ - ox), jhi = min(NS - 1, g.W - 4 - ox + R_);
+        const bool xfull = jlo == 0 && jhi == NS - 1;
 
         const long long rlin = (long long)vol * g.refs_per_vol + ((long long)iz * g.nry + iy) * g.nrx + ix;
 
@@ -1051,7 +1064,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
 #pragma unroll
                         for (int j = 0; j < NS; ++j) {
                             const uint32_t ssd = (e[j] + s2ref) - 2u * acc[j];
-                            const bool ok = ssd <= tau && j >= jlo && j <= jhi;
+                            const bool ok = ssd <= tau && (xfull || (j >= jlo && j <= jhi));
                             key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                         }
                     }
@@ -1075,13 +1088,23 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                         if (narrow) {
                             // everything modulo 2^32: exact because the true SSD < 2^32 on a narrow tile
                             const uint32_t rm2 = 2u * rmin;
+                            if (xfull) {  // warp-uniform: no candidate of this window leaves the volume along x
 #pragma unroll
-                            for (int j = 0; j < NS; ++j) {
-                                const uint2 ev = e[j];
-                                const uint32_t dot = acc[j] + (acch[j] << 8);
-                                const uint32_t ssd = (ev.x + s2ref) - 2u * dot - rm2 * (ev.y & 0xFFFFFFu);
-                                const bool ok = ssd <= tau && j >= jlo && j <= jhi;
-                                key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                                for (int j = 0; j < NS; ++j) {
+                                    const uint2 ev = e[j];
+                                    const uint32_t dot = acc[j] + (acch[j] << 8);
+                                    const uint32_t ssd = (ev.x + s2ref) - 2u * dot - rm2 * (ev.y & 0xFFFFFFu);
+                                    key[j] = ssd <= tau ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < NS; ++j) {
+                                    const uint2 ev = e[j];
+                                    const uint32_t dot = acc[j] + (acch[j] << 8);
+                                    const uint32_t ssd = (ev.x + s2ref) - 2u * dot - rm2 * (ev.y & 0xFFFFFFu);
+                                    const bool ok = ssd <= tau && j >= jlo && j <= jhi;
+                                    key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                                }
                             }
                         } else {
                             // wide tile: the same sums, combined exactly in 64 bits
