@@ -426,6 +426,13 @@ __global__ void __launch_bounds__(256) k_tile_class(const uint32_t *__restrict__
 }
 
 // ------------------------------------------------------------ helpers -------
+// key = SSD * 2^KB + window index as ONE multiply-add (IMAD pipe) instead of a shift and an OR (ALU pipe, which is the
+// busier one in these kernels); the low KB bits of the product are zero, so the sum equals the OR
+__device__ __forceinline__ uint32_t mad_key(uint32_t ssd, uint32_t scale, uint32_t idx) {
+    uint32_t k;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k) : "r"(ssd), "r"(scale), "r"(idx));
+    return k;
+}
 __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) { return __reduce_min_sync(B4D_FULL, v); }
 
 // K-th smallest (0-based index kth) of one value per lane: 32-lane bitonic sort.
@@ -859,9 +866,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                             for (int j = 0; j < NS; ++j) {
                                 const uint32_t idx = (uint32_t)(unit * NS + j);
                                 const uint32_t da = (e[j] + s2a) - 2u * acca[j];
-                                ka[j] = da <= tau ? ((da << KB) | idx) : B4D_INVALID_KEY;
+                                ka[j] = da <= tau ? mad_key(da, 1u << KB, idx) : B4D_INVALID_KEY;
                                 const uint32_t db = (e[j + 3] + s2b) - 2u * accb[j];
-                                kb[j] = db <= tau ? ((db << KB) | idx) : B4D_INVALID_KEY;
+                                kb[j] = db <= tau ? mad_key(db, 1u << KB, idx) : B4D_INVALID_KEY;
                             }
                         } else {
 #pragma unroll
@@ -869,10 +876,10 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                                 const uint32_t idx = (uint32_t)(unit * NS + j);
                                 const uint32_t da = (e[j] + s2a) - 2u * acca[j];
                                 const bool oka = da <= tau && j >= jloa && j <= jhia;
-                                ka[j] = oka ? ((da << KB) | idx) : B4D_INVALID_KEY;
+                                ka[j] = oka ? mad_key(da, 1u << KB, idx) : B4D_INVALID_KEY;
                                 const uint32_t db = (e[j + 3] + s2b) - 2u * accb[j];
                                 const bool okb = db <= tau && j >= jlob && j <= jhib;
-                                kb[j] = okb ? ((db << KB) | idx) : B4D_INVALID_KEY;
+                                kb[j] = okb ? mad_key(db, 1u << KB, idx) : B4D_INVALID_KEY;
                             }
                         }
                     }
@@ -1065,7 +1072,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                         for (int j = 0; j < NS; ++j) {
                             const uint32_t ssd = (e[j] + s2ref) - 2u * acc[j];
                             const bool ok = ssd <= tau && (xfull || (j >= jlo && j <= jhi));
-                            key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                            key[j] = ok ? mad_key(ssd, 1u << KB, (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                         }
                     }
                 } else {
@@ -1094,7 +1101,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                                     const uint2 ev = e[j];
                                     const uint32_t dot = acc[j] + (acch[j] << 8);
                                     const uint32_t ssd = (ev.x + s2ref) - 2u * dot - rm2 * (ev.y & 0xFFFFFFu);
-                                    key[j] = ssd <= tau ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                                    key[j] = ssd <= tau ? mad_key(ssd, 1u << KB, (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                                 }
                             } else {
 #pragma unroll
@@ -1103,7 +1110,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                                     const uint32_t dot = acc[j] + (acch[j] << 8);
                                     const uint32_t ssd = (ev.x + s2ref) - 2u * dot - rm2 * (ev.y & 0xFFFFFFu);
                                     const bool ok = ssd <= tau && j >= jlo && j <= jhi;
-                                    key[j] = ok ? ((ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                                    key[j] = ok ? mad_key(ssd, 1u << KB, (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                                 }
                             }
                         } else {
@@ -1118,7 +1125,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                                                                (unsigned long long)rmin * (e1j & 0xFFFFFFu);
                                 const unsigned long long ssd = s2a + s2r - 2ull * dot;
                                 const bool ok = ssd <= (unsigned long long)tau && j >= jlo && j <= jhi;
-                                key[j] = ok ? (((uint32_t)ssd << KB) | (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                                key[j] = ok ? mad_key((uint32_t)ssd, 1u << KB, (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
                             }
                         }
                     }
