@@ -808,6 +808,11 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
 
     const int K = p.K;
     const uint32_t tau = p.tau;
+    // A candidate is acceptable iff its key is <= KEYMAX (SSD <= tau): where no other test is needed the keys are
+    // built without the tau comparison — the SSD is saturated to the key's field instead (one min instead of a
+    // compare and a select) — and every bound starts at KEYMAX.
+    const uint32_t DMAX = (1u << (32 - KB)) - 1u;
+    const uint32_t KEYMAX = (min(tau, DMAX - 1u) << KB) | ((1u << KB) - 1u);
 
     // ---- byte tiles whose four reference columns are regular: two references per pass (neighbours in x).  Only the
     // common case runs here (one pass, bound refined on the fly); a pair whose survivor list overflows is left to
@@ -843,7 +848,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                 const bool xfull = jloa == 0 && jlob == 0 && jhia == NS - 1 && jhib == NS - 1;
                 const long long rlina = (long long)vol * g.refs_per_vol + ((long long)iz * g.nry + iy) * g.nrx + ixa;
                 uint32_t la1 = B4D_INVALID_KEY, la2 = B4D_INVALID_KEY, lb1 = B4D_INVALID_KEY, lb2 = B4D_INVALID_KEY;
-                uint32_t Ba = B4D_INVALID_KEY - 1u, Bb = B4D_INVALID_KEY - 1u;
+                uint32_t Ba = KEYMAX, Bb = KEYMAX;
                 int na = 0, nb = 0;  // survivor counts (warp-uniform)
                 __syncwarp();
 #pragma unroll 1
@@ -865,10 +870,10 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
 #pragma unroll
                             for (int j = 0; j < NS; ++j) {
                                 const uint32_t idx = (uint32_t)(unit * NS + j);
-                                const uint32_t da = (e[j] + s2a) - 2u * acca[j];
-                                ka[j] = da <= tau ? mad_key(da, 1u << KB, idx) : B4D_INVALID_KEY;
-                                const uint32_t db = (e[j + 3] + s2b) - 2u * accb[j];
-                                kb[j] = db <= tau ? mad_key(db, 1u << KB, idx) : B4D_INVALID_KEY;
+                                const uint32_t da = min((e[j] + s2a) - 2u * acca[j], DMAX);
+                                ka[j] = mad_key(da, 1u << KB, idx);
+                                const uint32_t db = min((e[j + 3] + s2b) - 2u * accb[j], DMAX);
+                                kb[j] = mad_key(db, 1u << KB, idx);
                             }
                         } else {
 #pragma unroll
@@ -1044,7 +1049,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
         // one more pass with the final bound of mode 0 fixed from the start.  mode 2 (still
         // overflowing): K rounds of "smallest key greater than the previous one".
         int mode = 0;
-        uint32_t Bfix = B4D_INVALID_KEY - 1u;
+        uint32_t Bfix = KEYMAX;
         uint32_t prev = 0;                 // mode 2: last extracted key
         int nsel = 0;                      // mode 2: keys extracted so far
         uint32_t mykey = B4D_INVALID_KEY;  // mode 2: lane k holds the k-th key
@@ -1100,8 +1105,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                                 for (int j = 0; j < NS; ++j) {
                                     const uint2 ev = e[j];
                                     const uint32_t dot = acc[j] + (acch[j] << 8);
-                                    const uint32_t ssd = (ev.x + s2ref) - 2u * dot - rm2 * (ev.y & 0xFFFFFFu);
-                                    key[j] = ssd <= tau ? mad_key(ssd, 1u << KB, (uint32_t)(unit * NS + j)) : B4D_INVALID_KEY;
+                                    const uint32_t ssd = min((ev.x + s2ref) - 2u * dot - rm2 * (ev.y & 0xFFFFFFu), DMAX);
+                                    key[j] = mad_key(ssd, 1u << KB, (uint32_t)(unit * NS + j));
                                 }
                             } else {
 #pragma unroll
@@ -1151,7 +1156,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_match(const MatchParams p, co
                 } else {
 #pragma unroll
                     for (int j = 0; j < NS; ++j) {
-                        const uint32_t k = (nsel == 0 || key[j] > prev) ? key[j] : B4D_INVALID_KEY;
+                        const uint32_t k = ((nsel == 0 || key[j] > prev) && key[j] <= KEYMAX) ? key[j] : B4D_INVALID_KEY;
                         lmin1 = min(lmin1, k);
                     }
                 }
