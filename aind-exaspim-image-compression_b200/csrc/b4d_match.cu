@@ -125,7 +125,7 @@ struct Geo {
 // current one is summed); the 4-tap sum along x takes the three right-hand neighbours by shuffle (lanes 29-31
 // only feed them), the sums along y and z are register arithmetic (pair sums, three older plane sums per row).
 // HBM-bound: 2 B read + 8 B written per voxel.
-constexpr int K0_TY = 8, K0_TX = 29, K0_ZC = 64, K0_WARPS = 8;
+constexpr int K0_TY = 8, K0_TX = 29, K0_ZC = 128, K0_WARPS = 8;
 __global__ void __launch_bounds__(K0_WARPS * 32) k_block_energy(const uint16_t *__restrict__ u, uint2 *__restrict__ s21,
                                                                int D, int H, int W, int nvol, int zo0, int zo1) {
     const int lane = threadIdx.x & 31;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k_block_energy(const uint16_t *
 // v^2 | v << 40: every partial sum of S2 stays below 2^38 and of S1 below 2^22, so one 64-bit addition serves both.
 // Rows are summed first (registers), then columns by two shuffles (v + right neighbour, pair + pair two lanes on);
 // the three older plane sums per row are kept by phase (z mod 3), nothing is moved.
-constexpr int K0T_WARPS = 4, K0T_WX = 28, K0T_TX = K0T_WARPS * K0T_WX, K0T_BOXW = 120, K0T_ROWS = K0_TY + 3, K0T_NST = 8;
+constexpr int K0T_WARPS = 2, K0T_WX = 28, K0T_TX = K0T_WARPS * K0T_WX, K0T_BOXW = 64, K0T_ROWS = K0_TY + 3, K0T_NST = 8;
 constexpr uint32_t K0T_BOX_BYTES = K0T_BOXW * K0T_ROWS * 2;
 constexpr int K0T_STAGE = ((int)K0T_BOX_BYTES + 127) / 128 * 128;
 static_assert(K0T_TX % 8 == 0 && K0T_BOXW % 8 == 0 && K0T_BOXW >= K0T_TX + 3 && K0T_BOXW >= (K0T_WARPS - 1) * K0T_WX + 32,
