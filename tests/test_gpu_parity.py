@@ -467,6 +467,34 @@ def test_exchange_variant_slabs_equal_whole(b4d_mod):
         assert np.array_equal(np.concatenate(parts, 0), whole)
 
 
+def test_random_shapes_and_contents_equal_the_oracle(dn, oracle_lib):
+    """Fuzz: 40 random shapes (4 .. 43 per axis, every fifth with rows that satisfy the TMA stride rule), noise on a
+    random pedestal, bright blobs (byte, general and wide tiles side by side), flat halves (ties): stage-1 match
+    lists and the two-stage output equal the oracle bit for bit.  (tools/fuzz_shapes.py runs the same at any size.)"""
+    rng = np.random.default_rng(3)
+    for c in range(40):
+        shape = tuple(int(x) for x in rng.integers(4, 44, 3))
+        if c % 5 == 0:
+            shape = shape[:2] + (int(rng.choice([8, 16, 24, 32, 40, 48])),)
+        kind = c % 4
+        base = rng.integers(0, 3000)
+        vol = base + rng.normal(0, 24.0, shape)
+        if kind >= 1:
+            z, y, x = (int(rng.integers(0, n)) for n in shape)
+            vol[max(z - 3, 0) : z + 4, max(y - 3, 0) : y + 4, max(x - 3, 0) : x + 4] += float(rng.choice([400, 5000, 40000]))
+        if kind == 3:
+            vol[:, :, : shape[2] // 2] = base
+        vol = np.clip(np.rint(vol), 0, 65535).astype(np.uint16)
+        sigma = float(rng.choice([10.0, 24.0, 40.0]))
+        o = oracle_lib.Oracle("mirror")
+        gi, gs, gc = dn.match_stage1(vol, sigma)
+        oi, os_, oc = o.match_stage1(vol, sigma)
+        assert np.array_equal(gc, oc), (c, shape)
+        valid = np.arange(gi.shape[1])[None, :] < gc[:, None]
+        assert np.array_equal(gi[valid], oi[valid]) and np.array_equal(gs[valid], os_[valid]), (c, shape)
+        assert np.array_equal(dn.denoise(vol, sigma), o.denoise(vol, sigma)), (c, shape)
+
+
 def test_tma_and_fallback_staging_give_the_same_bytes(dn, b4d_mod):
     """Every TMA-fed kernel (K0, byte-matcher window, general-matcher table, normalise) has a cp.async / plain-load
     twin for volumes whose row pitch breaks the 16-byte rule; B4D_NO_TMA forces the twins on an aligned volume."""
